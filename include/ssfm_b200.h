@@ -1,0 +1,111 @@
+/* ssfm_b200.h -- C ABI of the B200-native split-step Fourier engine.
+ *
+ * Drop-in boundary for ONE hot path of armando-palacio/opticomlib (v2.0.3):
+ *   opticomlib.devices.FIBER   (opticomlib/devices.py:1038-1206)
+ *   opticomlib.devices.DBP     (opticomlib/devices.py:1209-1283)
+ *   opticomlib.devices.LPF     (opticomlib/devices.py:1286-1375)
+ *   opticomlib.devices.BPF     (opticomlib/devices.py:788-826)
+ *
+ * The reference has no FFI of its own (it is pure Python; its only accelerator hook is an
+ * `import cupy` inside FIBER, devices.py:1114-1134), so each entry point below names the block of
+ * reference statements it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on
+ * the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - all "dev" pointers are CUDA device pointers on the plan's device, owned by the caller and
+ *     borrowed for the duration of the call; "host" pointers are ordinary host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns SSFM_OK (0) or a negative error code and never throws; a message
+ *     for the last error of the calling thread is available from ssfm_last_error().
+ *   - complex samples are interleaved (re, im); SSFM_C64 = 2 x float32, SSFM_C128 = 2 x float64.
+ */
+#ifndef SSFM_B200_H
+#define SSFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SSFM_API __attribute__((visibility("default")))
+#else
+#define SSFM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSFM_OK              0
+#define SSFM_ERR_INVALID    -1   /* bad argument (maps to ValueError / TypeError in the wrapper) */
+#define SSFM_ERR_CUDA       -2   /* CUDA runtime error (RuntimeError) */
+#define SSFM_ERR_UNSUPPORTED -3  /* size not supported by this build (ValueError) */
+#define SSFM_ERR_NOMEM      -4
+
+#define SSFM_C64   0   /* float32 arithmetic: the reference as shipped (devices.py:1137-1147) */
+#define SSFM_C128  1   /* float64 arithmetic: the dtype-lifted algorithm (devices.py:2440-2486) */
+
+#define SSFM_ABI_VERSION 1
+
+typedef struct ssfm_plan_s* ssfm_plan_t;
+
+/* Fibre and step-control arguments of FIBER (devices.py:1038-1048), in the reference's units. */
+typedef struct ssfm_fiber_params {
+    double dt_s;           /* sampling period gv.dt [s]  (typing.py:1641 via input.w()) */
+    double length_km;      /* length   [km] */
+    double alpha_db_km;    /* alpha    [dB/km]; divided by the literal 4.343 inside (devices.py:1137) */
+    double beta2_ps2_km;   /* beta_2   [ps^2/km] */
+    double beta3_ps3_km;   /* beta_3   [ps^3/km] */
+    double gamma_w_km;     /* gamma    [1/(W km)] */
+    double phi_max_rad;    /* phi_max  [rad] (code default 0.01, devices.py:1044) */
+    double h_km;           /* fixed step [km]; NaN selects the adaptive rule of devices.py:1156,1194 */
+} ssfm_fiber_params;
+
+SSFM_API int         ssfm_abi_version(void);
+SSFM_API const char* ssfm_last_error(void);
+
+/* Plan for `n_waveforms` independent waveforms of `n_pol` (1|2) polarisation rows of `n_samples`
+ * complex samples each.  n_samples must be a power of two, 2^8 <= n <= 2^22.  Holds the twiddle
+ * tables, the Kerr-phase stash and the per-waveform controller state on `device`. */
+SSFM_API int ssfm_plan_create(ssfm_plan_t* plan, int64_t n_samples, int32_t n_pol, int64_t n_waveforms,
+                     int32_t dtype, int32_t device);
+SSFM_API int ssfm_plan_destroy(ssfm_plan_t plan);
+
+/* Tunables: "chunk_waveforms" (waveforms propagated together so that field + stash stay in L2;
+ * 0 = all), "hlog_cap" (step sizes logged per waveform), "burst_steps". */
+SSFM_API int ssfm_plan_set_option(ssfm_plan_t plan, const char* name, int64_t value);
+
+/* FIBER hot loop, devices.py:1155-1196, in place on field_dev[n_waveforms][n_pol][n_samples].
+ * DBP (devices.py:1280-1283) is the same call with alpha, beta_2, beta_3, gamma negated by the caller.
+ *   max_steps : stop every waveform after this many further steps (0 = run to z >= length)
+ *   resume    : 0 = start at z = 0 (first step size from devices.py:1155-1159);
+ *               1 = continue from the controller state left by the previous call on this plan
+ * Returns when the field is final on `stream` (the call synchronises on its own work). */
+SSFM_API int ssfm_propagate(ssfm_plan_t plan, void* field_dev, const ssfm_fiber_params* prm,
+                   int64_t max_steps, int32_t resume, void* stream);
+
+/* Controller state after ssfm_propagate, copied to host arrays of n_waveforms entries
+ * (any pointer may be NULL): steps taken, z reached [km], size of the next step [km],
+ * 1 if z >= length. */
+SSFM_API int ssfm_get_state(ssfm_plan_t plan, int32_t* steps_host, double* z_host, double* h_next_host,
+                   int32_t* done_host);
+/* Step sizes taken, hlog_host[n_waveforms][cap] (rows are filled up to min(steps, cap)). */
+SSFM_API int ssfm_get_step_log(ssfm_plan_t plan, double* hlog_host, int64_t cap);
+
+/* Same as ssfm_propagate but with HOST buffers: copies field_in_host to the device (casting is the
+ * caller's job: the buffer must already have the plan's dtype), propagates, copies the result to
+ * field_out_host.  This is the block devices.py:1147-1204 (asarray -> loop -> .get()). */
+SSFM_API int ssfm_fiber_host(ssfm_plan_t plan, const void* field_in_host, void* field_out_host,
+                    const ssfm_fiber_params* prm, void* stream);
+
+/* Zero-phase cascaded-biquad filtering (scipy.signal.sosfiltfilt as called at devices.py:820-823 and
+ * 1365-1368): x_dev[n_rows][n_samples] complex128 -> y_dev (may alias x_dev).
+ * sos_host[n_sections][6] = b0 b1 b2 a0 a1 a2 (a0 == 1) from scipy.signal.bessel(..., output='sos').
+ * Real signals are passed as complex with zero imaginary part, or two real rows packed as re/im. */
+SSFM_API int ssfm_filtfilt_sos(void* x_dev, void* y_dev, int64_t n_rows, int64_t n_samples,
+                      const double* sos_host, int32_t n_sections, int32_t device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSFM_B200_H */

@@ -1,0 +1,417 @@
+// C-ABI of the split-step Fourier engine (see include/ssfm_b200.h) and the host-side step loop.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ssfm_b200.h"
+#include "ssfm_kernels.cuh"
+
+using namespace ssfm;
+
+thread_local std::string ssfm_err_slot;   // shared with filtfilt.cu
+
+namespace {
+
+#define g_err ssfm_err_slot
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(SSFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+int ilog2(long long v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
+
+// compile-time geometry ------------------------------------------------------------------------
+constexpr int col_tile(int M) { return M <= 32 ? M : (M <= 128 ? 32 : (M == 256 ? 16 : (M == 512 ? 8 : 4))); }
+constexpr int row_group(int M) { return (4096 / M) < (M / 2) ? (4096 / M) : (M / 2); }
+
+// twiddle tables, built on the device in double and rounded once to R ---------------------------
+template <typename R>
+__global__ void k_build_unit_roots(typename cx_of<R>::type* out, int count, long long stride, long long period) {
+    // out[i] = exp(-2 pi j * (i*stride) / period)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const long long m = ((long long)i * stride) % period;
+    double s, c;
+    sincospi(2.0 * (double)m / (double)period, &s, &c);
+    out[i] = mk<R>((R)c, (R)(-s));
+}
+
+template <typename R>
+__global__ void k_build_pass_table(typename cx_of<R>::type* out, int ns, int radix) {
+    // out[(r-1)*ns + jm] = W_{ns*radix}^{r*jm}
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (radix - 1) * ns) return;
+    const int r = i / ns + 1, jm = i % ns;
+    const long long period = (long long)ns * radix;
+    const long long m = ((long long)r * jm) % period;
+    double s, c;
+    sincospi(2.0 * (double)m / (double)period, &s, &c);
+    out[i] = mk<R>((R)c, (R)(-s));
+}
+
+int pass_table_size(int M) {
+    int total = 0;
+    for (int ns = 1; ns < M;) {
+        const int r = (M / ns >= 16) ? 16 : M / ns;
+        if (ns > 1) total += (r - 1) * ns;
+        ns *= r;
+    }
+    return total;
+}
+
+template <typename R>
+int build_pass_tables(void** out, int M, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    const int total = pass_table_size(M);
+    C* d = nullptr;
+    CU_TRY(cudaMalloc(&d, sizeof(C) * (size_t)(total > 0 ? total : 1)));
+    int off = 0;
+    for (int ns = 1; ns < M;) {
+        const int r = (M / ns >= 16) ? 16 : M / ns;
+        if (ns > 1) {
+            const int cnt = (r - 1) * ns;
+            k_build_pass_table<R><<<(cnt + 127) / 128, 128, 0, st>>>(d + off, ns, r);
+            off += cnt;
+        }
+        ns *= r;
+    }
+    CU_TRY(cudaGetLastError());
+    *out = d;
+    return SSFM_OK;
+}
+
+}  // namespace
+
+struct ssfm_plan_s {
+    int device = 0, dtype = 0, n_pol = 1;
+    long long n = 0, batch = 0;
+    int log2n = 0, n1 = 0, n2 = 0;
+    void *tw_col = nullptr, *tw_row = nullptr, *tw_lo = nullptr, *tw_hi = nullptr;
+    void* stash = nullptr;
+    Ctrl* ctrl = nullptr;
+    int* active = nullptr;       // one counter per chunk
+    int n_active = 0;
+    double* hlog = nullptr;
+    int hlog_cap = 0;
+    int* active_host = nullptr;  // pinned, 2 slots
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    long long chunk = 0;
+    int burst = 8;
+    bool have_state = false;
+    ssfm_fiber_params last{};
+};
+
+namespace {
+
+template <typename R, int M>
+int launch_col_fwd(const Params<R>& p, int nblocks, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    constexpr int T = col_tile(M);
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
+    static bool attr = false;
+    if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_fwd<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_col_fwd<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    return SSFM_OK;
+}
+template <typename R, int M>
+int launch_col_inv(const Params<R>& p, int nblocks, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    constexpr int T = col_tile(M);
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
+    static bool attr = false;
+    if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_inv<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_col_inv<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    return SSFM_OK;
+}
+template <typename R, int M>
+int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    constexpr int G = row_group(M);
+    const size_t smem = sizeof(C) * (size_t)(G * (pad16(M) + 1) + fft_plan<M>::table_size);
+    static bool attr = false;
+    if (!attr) { CU_TRY(cudaFuncSetAttribute(k_row<R, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_row<R, M, G><<<nblocks, G * (M / 16), smem, st>>>(p);
+    return SSFM_OK;
+}
+
+#define SSFM_FOR_M(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+template <typename R>
+int enqueue_step(const Params<R>& p, cudaStream_t st) {
+    const long long rows = (long long)p.batch * p.n_pol;
+    int rc = SSFM_ERR_UNSUPPORTED;
+    // column pass forward
+    switch (p.n1) {
+#define X(M) case M: rc = launch_col_fwd<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
+        SSFM_FOR_M(X)
+#undef X
+        default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported column transform size");
+    }
+    if (rc) return rc;
+    switch (p.n2) {
+#define X(M) case M: rc = launch_row<R, M>(p, (int)(rows * p.n1 / row_group(M)), st); break;
+        SSFM_FOR_M(X)
+#undef X
+        default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported row transform size");
+    }
+    if (rc) return rc;
+    switch (p.n1) {
+#define X(M) case M: rc = launch_col_inv<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
+        SSFM_FOR_M(X)
+#undef X
+        default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported column transform size");
+    }
+    return rc;
+}
+
+template <typename R>
+int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long long max_steps, int resume,
+                cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    // scalar casts exactly as devices.py:1137-1142 (division in double first, then rounded to R)
+    const R a_lin = (R)(prm.alpha_db_km / 4.343);
+    const R b2 = (R)prm.beta2_ps2_km, b3 = (R)prm.beta3_ps3_km, g = (R)prm.gamma_w_km;
+    const R L = (R)prm.length_km, pm = (R)prm.phi_max_rad;
+    const bool fixed = !std::isnan(prm.h_km);
+    const bool single = !fixed && ((b2 == (R)0 && b3 == (R)0) || g == (R)0);
+
+    Params<R> base;
+    std::memset(&base, 0, sizeof(base));
+    base.tw_col = (const C*)pl->tw_col; base.tw_row = (const C*)pl->tw_row;
+    base.tw_lo = (const C*)pl->tw_lo;   base.tw_hi = (const C*)pl->tw_hi;
+    base.lo_bits = ilog2(pl->n2);
+    base.n = (int)pl->n; base.n1 = pl->n1; base.n2 = pl->n2; base.log2_n2 = ilog2(pl->n2);
+    base.n_pol = pl->n_pol;
+    base.hlog_cap = pl->hlog_cap;
+    base.adaptive = fixed ? 0 : 1;
+    base.has_nl = (g != (R)0) ? 1 : 0;
+    base.max_steps = 1 << 30;
+    base.gamma = g; base.abs_gamma = std::fabs(g); base.phi_max = pm; base.length = L;
+    base.att_half = -a_lin / (R)2;
+    base.c2 = (R)0.5 * b2;                       // imag(1j/2 * beta_2): exact scaling
+    base.c3 = (R)(1.0 / 6.0) * b3;               // imag(1j/6 * beta_3): R(1/6) times beta_3, rounded once
+    base.fval = 1.0 / ((double)pl->n * prm.dt_s);
+    base.inv_n = (R)1 / (R)pl->n;
+
+    const long long B = pl->batch;
+    const long long chunk = (pl->chunk > 0 && pl->chunk < B) ? pl->chunk : B;
+    const size_t wf_elems = (size_t)pl->n_pol * (size_t)pl->n;
+    const long long budget = max_steps > 0 ? max_steps : (1ll << 40);
+
+    int ci = 0;
+    for (long long b0 = 0; b0 < B; b0 += chunk, ++ci) {
+        const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        Params<R> p = base;
+        p.field = (C*)field + (size_t)b0 * wf_elems;
+        p.stash = (R*)pl->stash + (size_t)b0 * wf_elems;
+        p.ctrl = pl->ctrl + b0;
+        p.active = pl->active + ci;
+        p.hlog = pl->hlog ? pl->hlog + (size_t)b0 * pl->hlog_cap : nullptr;
+        p.batch = (int)nb;
+
+        if (!resume) {
+            const int nb_i = (int)nb;
+            CU_TRY(cudaMemcpyAsync(p.active, &nb_i, sizeof(int), cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)nb, st));
+            if (!fixed && !single) {
+                int per = (int)((wf_elems + 256 * 16 - 1) / (256 * 16));
+                if (per > 64) per = 64;
+                if (per < 1) per = 1;
+                k_power_max<R><<<(unsigned)(nb * per), 256, 0, st>>>(p, per);
+            }
+            k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, fixed ? 1 : 0, fixed ? (R)prm.h_km : (R)0,
+                                                                      single ? 1 : 0);
+            CU_TRY(cudaGetLastError());
+        } else {
+            // re-arm: waveforms that have not reached `length` continue; recount them on the host
+            std::vector<Ctrl> h((size_t)nb);
+            CU_TRY(cudaMemcpyAsync(h.data(), p.ctrl, sizeof(Ctrl) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            int act = 0;
+            for (auto& c : h) act += c.done ? 0 : 1;
+            CU_TRY(cudaMemcpyAsync(p.active, &act, sizeof(int), cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            if (act == 0) continue;
+        }
+
+        long long enq = 0;
+        int slot = 0;
+        bool pending = false, finished = false;
+        while (!finished) {
+            long long nsteps = pl->burst;
+            if (enq + nsteps > budget) nsteps = budget - enq;
+            for (long long s = 0; s < nsteps; ++s) {
+                int rc = enqueue_step<R>(p, st);
+                if (rc) return rc;
+            }
+            enq += nsteps;
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(&pl->active_host[slot], p.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaEventRecord(pl->ev[slot], st));
+            if (pending) {
+                CU_TRY(cudaEventSynchronize(pl->ev[slot ^ 1]));
+                if (pl->active_host[slot ^ 1] == 0) finished = true;
+            }
+            pending = true;
+            slot ^= 1;
+            if (!finished && enq >= budget) {
+                CU_TRY(cudaEventSynchronize(pl->ev[slot ^ 1]));
+                finished = true;
+            }
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    pl->have_state = true;
+    pl->last = prm;
+    return SSFM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ssfm_abi_version(void) { return SSFM_ABI_VERSION; }
+const char* ssfm_last_error(void) { return g_err.c_str(); }
+
+int ssfm_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, int32_t dtype, int32_t device) {
+    if (!out) return fail(SSFM_ERR_INVALID, "plan pointer is null");
+    *out = nullptr;
+    if (n_pol != 1 && n_pol != 2) return fail(SSFM_ERR_INVALID, "n_pol must be either 1 or 2");
+    if (batch < 1) return fail(SSFM_ERR_INVALID, "n_waveforms must be >= 1");
+    if (dtype != SSFM_C64 && dtype != SSFM_C128) return fail(SSFM_ERR_INVALID, "dtype must be SSFM_C64 or SSFM_C128");
+    if (n < 256 || n > (1ll << 22) || (n & (n - 1)))
+        return fail(SSFM_ERR_UNSUPPORTED, "n_samples must be a power of two in [2^8, 2^22]");
+    CU_TRY(cudaSetDevice(device));
+    ssfm_plan_s* pl = new ssfm_plan_s();
+    pl->device = device; pl->dtype = dtype; pl->n_pol = n_pol; pl->n = n; pl->batch = batch;
+    pl->log2n = ilog2(n);
+    pl->n1 = 1 << (pl->log2n / 2);
+    pl->n2 = (int)(n / pl->n1);
+    pl->hlog_cap = 4096;
+    if ((size_t)batch * pl->hlog_cap * sizeof(double) > (256u << 20)) pl->hlog_cap = (int)((256u << 20) / (batch * sizeof(double)));
+    if (pl->hlog_cap < 16) pl->hlog_cap = 16;
+
+    const size_t rsz = dtype == SSFM_C64 ? 4 : 8, csz = 2 * rsz;
+    const size_t elems = (size_t)batch * n_pol * n;
+    cudaError_t e;
+    e = cudaMalloc(&pl->stash, elems * rsz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ctrl, sizeof(Ctrl) * (size_t)batch);
+    if (e == cudaSuccess) { pl->n_active = (int)batch; e = cudaMalloc((void**)&pl->active, sizeof(int) * (size_t)batch); }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->hlog, sizeof(double) * (size_t)batch * pl->hlog_cap);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->tw_lo, csz * (size_t)pl->n2);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->tw_hi, csz * (size_t)pl->n1);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&pl->active_host, 2 * sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[1], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        ssfm_plan_destroy(pl);
+        return fail(e == cudaErrorMemoryAllocation ? SSFM_ERR_NOMEM : SSFM_ERR_CUDA,
+                    std::string("plan allocation: ") + cudaGetErrorString(e));
+    }
+    CU_TRY(cudaMemset(pl->ctrl, 0, sizeof(Ctrl) * (size_t)batch));
+    CU_TRY(cudaMemset(pl->hlog, 0, sizeof(double) * (size_t)batch * pl->hlog_cap));
+    int rc;
+    if (dtype == SSFM_C64) {
+        k_build_unit_roots<float><<<(pl->n2 + 127) / 128, 128>>>((float2*)pl->tw_lo, pl->n2, 1, n);
+        k_build_unit_roots<float><<<(pl->n1 + 127) / 128, 128>>>((float2*)pl->tw_hi, pl->n1, pl->n2, n);
+        rc = build_pass_tables<float>(&pl->tw_col, pl->n1, 0);
+        if (!rc) rc = build_pass_tables<float>(&pl->tw_row, pl->n2, 0);
+    } else {
+        k_build_unit_roots<double><<<(pl->n2 + 127) / 128, 128>>>((double2*)pl->tw_lo, pl->n2, 1, n);
+        k_build_unit_roots<double><<<(pl->n1 + 127) / 128, 128>>>((double2*)pl->tw_hi, pl->n1, pl->n2, n);
+        rc = build_pass_tables<double>(&pl->tw_col, pl->n1, 0);
+        if (!rc) rc = build_pass_tables<double>(&pl->tw_row, pl->n2, 0);
+    }
+    if (rc) { ssfm_plan_destroy(pl); return rc; }
+    cudaError_t es = cudaDeviceSynchronize();
+    if (es != cudaSuccess) { ssfm_plan_destroy(pl); return fail(SSFM_ERR_CUDA, std::string("table build: ") + cudaGetErrorString(es)); }
+    *out = pl;
+    return SSFM_OK;
+}
+
+int ssfm_plan_destroy(ssfm_plan_t pl) {
+    if (!pl) return SSFM_OK;
+    cudaSetDevice(pl->device);
+    cudaFree(pl->stash); cudaFree(pl->ctrl); cudaFree(pl->active); cudaFree(pl->hlog);
+    cudaFree(pl->tw_col); cudaFree(pl->tw_row); cudaFree(pl->tw_lo); cudaFree(pl->tw_hi);
+    if (pl->active_host) cudaFreeHost(pl->active_host);
+    if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
+    if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
+    delete pl;
+    return SSFM_OK;
+}
+
+int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
+    if (!pl || !name) return fail(SSFM_ERR_INVALID, "null plan or option name");
+    const std::string k(name);
+    if (k == "chunk_waveforms") { if (value < 0) return fail(SSFM_ERR_INVALID, "chunk_waveforms < 0"); pl->chunk = value; }
+    else if (k == "burst_steps") { if (value < 1 || value > 4096) return fail(SSFM_ERR_INVALID, "burst_steps out of range"); pl->burst = (int)value; }
+    else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
+    return SSFM_OK;
+}
+
+int ssfm_propagate(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, int64_t max_steps, int32_t resume,
+                   void* stream) {
+    if (!pl || !field || !prm) return fail(SSFM_ERR_INVALID, "null plan, field or params");
+    if (!(prm->dt_s > 0)) return fail(SSFM_ERR_INVALID, "dt_s must be > 0");
+    if (max_steps < 0) return fail(SSFM_ERR_INVALID, "max_steps < 0");
+    if (resume && !pl->have_state) return fail(SSFM_ERR_INVALID, "resume requested but the plan holds no controller state");
+    CU_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->dtype == SSFM_C64) return propagate_t<float>(pl, field, *prm, max_steps, resume, st);
+    return propagate_t<double>(pl, field, *prm, max_steps, resume, st);
+}
+
+int ssfm_get_state(ssfm_plan_t pl, int32_t* steps, double* z, double* h_next, int32_t* done) {
+    if (!pl) return fail(SSFM_ERR_INVALID, "null plan");
+    CU_TRY(cudaSetDevice(pl->device));
+    std::vector<Ctrl> h((size_t)pl->batch);
+    CU_TRY(cudaMemcpy(h.data(), pl->ctrl, sizeof(Ctrl) * h.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); ++i) {
+        if (steps) steps[i] = h[i].steps;
+        if (z) z[i] = h[i].z;
+        if (h_next) h_next[i] = h[i].h;
+        if (done) done[i] = h[i].done;
+    }
+    return SSFM_OK;
+}
+
+int ssfm_get_step_log(ssfm_plan_t pl, double* out, int64_t cap) {
+    if (!pl || !out || cap < 1) return fail(SSFM_ERR_INVALID, "null plan/buffer or cap < 1");
+    CU_TRY(cudaSetDevice(pl->device));
+    const int64_t w = cap < pl->hlog_cap ? cap : pl->hlog_cap;
+    CU_TRY(cudaMemcpy2D(out, sizeof(double) * (size_t)cap, pl->hlog, sizeof(double) * (size_t)pl->hlog_cap,
+                        sizeof(double) * (size_t)w, (size_t)pl->batch, cudaMemcpyDeviceToHost));
+    return SSFM_OK;
+}
+
+int ssfm_fiber_host(ssfm_plan_t pl, const void* in, void* outp, const ssfm_fiber_params* prm, void* stream) {
+    if (!pl || !in || !outp || !prm) return fail(SSFM_ERR_INVALID, "null plan, buffer or params");
+    CU_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bytes = (size_t)pl->batch * pl->n_pol * pl->n * (pl->dtype == SSFM_C64 ? 8 : 16);
+    void* d = nullptr;
+    CU_TRY(cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemcpyAsync(d, in, bytes, cudaMemcpyHostToDevice, st);
+    int rc = SSFM_OK;
+    if (e != cudaSuccess) rc = fail(SSFM_ERR_CUDA, std::string("H2D: ") + cudaGetErrorString(e));
+    if (!rc) rc = ssfm_propagate(pl, d, prm, 0, 0, stream);
+    if (!rc) {
+        e = cudaMemcpyAsync(outp, d, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(SSFM_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

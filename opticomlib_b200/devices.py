@@ -1,0 +1,292 @@
+"""Drop-in ``FIBER`` / ``DBP`` / ``LPF`` / ``BPF`` running on the B200 kernels.
+
+Same names, argument meaning, defaults, return types and error behaviour as the reference
+(``opticomlib/devices.py``: FIBER 1038-1206, DBP 1209-1283, LPF 1286-1375, BPF 788-826).  The
+functions accept this package's signal objects and, by duck typing, the reference's own
+``optical_signal`` / ``electrical_signal`` objects, and return an object of the same class as the
+input.  ``install()`` rebinds the reference's module attributes so existing scripts use this path.
+
+Additive keyword-only arguments (not in the reference): ``precision`` ('fp32' = the algorithm as
+shipped, complex64 result; 'fp64' = the dtype-lifted algorithm, complex128 result) and ``device``.
+Batch entry points ``fiber_batch`` / ``dbp_batch`` / ``filtfilt_batch`` work on ``[B,(P,)N]`` arrays
+or CUDA tensors; the reference has no batch API.
+"""
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from . import engine
+from .typing import NULL, electrical_signal, gv, optical_signal
+from .utils import tic, toc
+
+DEFAULT_PRECISION = "fp32"   # the reference computes FIBER in float32/complex64 (devices.py:1137-1147)
+
+
+# ---- duck typing of signal objects -----------------------------------------------------------
+def _kind(obj):
+    """'optical' | 'electrical' | None for this package's or the reference's signal classes."""
+    if isinstance(obj, optical_signal):
+        return "optical"
+    if isinstance(obj, electrical_signal):
+        return "electrical"
+    for klass in type(obj).__mro__:
+        if klass.__module__.startswith("opticomlib") and klass.__name__ in ("optical_signal", "electrical_signal"):
+            return "optical" if klass.__name__ == "optical_signal" else "electrical"
+    return None
+
+
+def _gv_of(obj):
+    """The ``gv`` the object's class reads (the reference's when given a reference object)."""
+    mod = sys.modules.get(type(obj).__module__)
+    return getattr(mod, "gv", gv) if mod is not None else gv
+
+
+def _is_null(x):
+    return x is NULL or type(x).__name__ in ("NULLType", "_NullType")
+
+
+def _complex_dtype(precision):
+    torch = engine._torch()
+    p = (precision or DEFAULT_PRECISION).lower()
+    if p in ("fp32", "float32", "single", "complex64"):
+        return torch.complex64, np.complex64
+    if p in ("fp64", "float64", "double", "complex128"):
+        return torch.complex128, np.complex128
+    raise ValueError("precision must be 'fp32' or 'fp64'")
+
+
+def _to_device(a: np.ndarray, tdtype, dev):
+    """Host array -> contiguous CUDA tensor of dtype ``tdtype`` (one H2D copy, cast on the device)."""
+    torch = engine._torch()
+    a = np.ascontiguousarray(a)
+    if not np.iscomplexobj(a):
+        a = a.astype(np.complex128)
+    t = torch.from_numpy(a).to(dev, non_blocking=False)
+    return t.to(tdtype).contiguous()
+
+
+# ---- FIBER / DBP --------------------------------------------------------------------------------
+def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
+                precision=None, device=None, want_log=False, chunk_waveforms=None, inplace=False):
+    """Propagate a batch ``field[B, N]`` or ``field[B, P, N]`` (NumPy array or CUDA tensor).
+
+    Rows are independent waveforms, each with its own step-size sequence (the global max of
+    devices.py:1194 is taken over the P rows of one waveform).  Returns ``(out, StepInfo)``; ``out``
+    is a CUDA tensor when a tensor was given, else a NumPy array.
+    """
+    torch = engine._torch()
+    tdtype, ndtype = _complex_dtype(precision)
+    as_tensor = torch.is_tensor(field)
+    if as_tensor:
+        dev = engine.require_cuda(field.device if field.is_cuda else device)
+        x = field.to(device=dev, dtype=tdtype).contiguous()
+        if not inplace and x.data_ptr() == field.data_ptr():
+            x = x.clone()
+    else:
+        dev = engine.require_cuda(device)
+        x = _to_device(np.asarray(field), tdtype, dev)
+    if x.ndim not in (2, 3):
+        raise ValueError("field must have shape [B, N] or [B, P, N]")
+    B, P, N = (x.shape[0], 1, x.shape[1]) if x.ndim == 2 else tuple(x.shape)
+    plan = engine.get_plan(N, P, B, tdtype, dev)
+    plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
+    info = plan.propagate(x, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
+    return (x if as_tensor else x.cpu().numpy()), info
+
+
+def dbp_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, **kw):
+    """Batched digital back-propagation (devices.py:1280-1283: FIBER with negated parameters)."""
+    return fiber_batch(field, dt, length, -alpha, -beta_2, -beta_3, -gamma, phi_max, h, **kw)
+
+
+def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None,
+          show_progress=False, return_steps=False, *, precision=None, device=None):
+    """Optical fibre by the split-step Fourier method -- reference signature, devices.py:1038-1048.
+
+    Units: km, dB/km, ps^2/km, ps^3/km, 1/(W km), rad.  Returns an ``optical_signal`` (noise NULL),
+    or ``(z, A_z)`` with ``return_steps=True`` exactly like devices.py:1201-1202.
+    """
+    tic()
+    if _kind(input) != "optical":
+        toc()
+        raise TypeError("`input` must be of type 'optical_signal'.")
+    torch = engine._torch()
+    tdtype, ndtype = _complex_dtype(precision)
+    dev = engine.require_cuda(device)
+    dt = _gv_of(input).dt
+    a = np.asarray(input.to_numpy())                      # signal + noise (typing.py:1596)
+    n_pol = 1 if a.ndim == 1 else a.shape[0]
+    n = a.shape[-1]
+    x = _to_device(a.reshape(1, n_pol, n), tdtype, dev)    # cast to the compute dtype on the device
+    plan = engine.get_plan(n, n_pol, 1, tdtype, dev)
+    plan.set_option("chunk_waveforms", 0)
+    args = (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h)
+
+    bar = None
+    if show_progress:
+        try:
+            from tqdm.auto import tqdm
+            bar = tqdm(total=100, desc="Propagando", bar_format="{l_bar}{bar}|[{elapsed}{postfix}]", postfix={"FFTs": 0})
+        except Exception:
+            bar = None
+
+    if return_steps:
+        # one step per call, resuming the device-side controller; snapshots stay on the device
+        z_list, snaps = [0.0], [x.clone()]
+        info = plan.propagate(x, *args, max_steps=1, resume=False)
+        while True:
+            if int(info.steps[0]) == len(z_list) - 1:      # nothing happened (length <= 0)
+                break
+            z_list.append(np.float32(info.z[0]) if ndtype is np.complex64 else np.float64(info.z[0]))
+            snaps.append(x.clone())
+            if bar is not None:
+                bar.set_postfix(FFTs=2 * int(info.steps[0])); bar.n = min(100.0, 100.0 * info.z[0] / length); bar.refresh()
+            if info.done[0]:
+                break
+            info = plan.propagate(x, *args, max_steps=1, resume=True)
+        if bar is not None:
+            bar.close()
+        toc()                                               # (the reference leaks its tic here)
+        traj = torch.stack(snaps).cpu().numpy().reshape((len(snaps),) + a.shape)
+        return np.array(z_list), traj
+
+    info = plan.propagate(x, *args)
+    if bar is not None:
+        bar.set_postfix(FFTs=2 * int(info.steps[0])); bar.update(100); bar.close()
+    out = x.cpu().numpy().reshape(a.shape)
+    output = type(input)(out)
+    output.execution_time = toc()
+    output.ssfm_info = info                                 # additive: steps / z / h of this call
+    return output
+
+
+def DBP(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None,
+        show_progress=False, return_steps=False, **kw):
+    """Digital back-propagation -- reference devices.py:1209-1283 (negated fibre parameters)."""
+    return FIBER(input, length=length, alpha=-alpha, beta_2=-beta_2, beta_3=-beta_3, gamma=-gamma,
+                 phi_max=phi_max, h=h, show_progress=show_progress, return_steps=return_steps, **kw)
+
+
+# ---- LPF / BPF ------------------------------------------------------------------------------------
+def _bessel_sos(n, wn, fs):
+    """Filter design on the host exactly as the reference asks SciPy for it (devices.py:814, 1363)."""
+    from scipy import signal as sg
+
+    return sg.bessel(N=n, Wn=wn, btype="low", fs=fs, output="sos", norm="mag")
+
+
+def filtfilt_batch(x, sos, *, device=None):
+    """Zero-phase filter rows of ``x[..., N]`` (NumPy or CUDA tensor) with cascaded biquads ``sos``."""
+    torch = engine._torch()
+    if torch.is_tensor(x):
+        dev = engine.require_cuda(x.device if x.is_cuda else device)
+        y = engine.filtfilt_sos(x.to(device=dev, dtype=torch.complex128).contiguous(), sos)
+        return y
+    dev = engine.require_cuda(device)
+    a = np.asarray(x)
+    y = engine.filtfilt_sos(_to_device(a, torch.complex128, dev), sos).cpu().numpy()
+    return y if np.iscomplexobj(a) else y.real
+
+
+def _filter_pair(sig, noi, sos, dev):
+    """Filter signal and noise separately (as devices.py:820-823 / 1365-1368 do) in ONE launch:
+    the rows are stacked; for real inputs signal and noise travel as re/im of one complex row."""
+    torch = engine._torch()
+    sig = np.asarray(sig)
+    has_noise = not _is_null(noi)
+    if has_noise:
+        noi = np.asarray(noi)
+    if not np.iscomplexobj(sig) and (not has_noise or not np.iscomplexobj(noi)):
+        packed = sig.astype(np.float64) + 1j * (noi.astype(np.float64) if has_noise else 0.0)
+        y = engine.filtfilt_sos(_to_device(packed, torch.complex128, dev), sos).cpu().numpy()
+        return y.real.copy(), (y.imag.copy() if has_noise else NULL)
+    rows = np.stack([sig, noi]) if has_noise else sig[np.newaxis]
+    y = engine.filtfilt_sos(_to_device(rows, torch.complex128, dev), sos).cpu().numpy()
+    return y[0], (y[1] if has_noise else NULL)
+
+
+def LPF(input, BW, n=4, fs=None, retH=False, *, device=None):
+    """Zero-phase Bessel low-pass of an electrical signal -- reference devices.py:1286-1375."""
+    tic()
+    if _kind(input) is None:
+        input = electrical_signal(input)
+    if input.ndim != 1:
+        toc()
+        raise ValueError("`input` must be a 1D-array.")
+    if not fs:
+        fs = _gv_of(input).fs
+    dev = engine.require_cuda(device)
+    sos = _bessel_sos(n, BW, fs)
+    output = input[:]
+    try:
+        s, nz = _filter_pair(input.signal, input.noise, sos, dev)
+    except Exception:
+        toc()
+        raise
+    output.signal = np.asarray(s).real
+    if not _is_null(input.noise):
+        output.noise = np.asarray(nz).real
+    if retH:
+        from scipy import signal as sg
+        _, H = sg.sosfreqz(sos, worN=input.size, fs=fs, whole=True)
+        toc()
+        return output, np.fft.fftshift(H)
+    output.execution_time = toc()
+    return output
+
+
+def BPF(input, BW, n=4, *, device=None):
+    """Zero-phase Bessel band-pass of an optical envelope -- reference devices.py:788-826."""
+    tic()
+    if _kind(input) != "optical":
+        toc()
+        raise TypeError("`input` must be of type (optical_signal).")
+    dev = engine.require_cuda(device)
+    sos = _bessel_sos(n, BW / 2, _gv_of(input).fs)
+    output = input[:]
+    try:
+        s, nz = _filter_pair(input.signal, input.noise, sos, dev)
+    except Exception:
+        toc()
+        raise
+    output.signal = s
+    if not _is_null(output.noise):
+        output.noise = nz
+    output.execution_time = toc()
+    return output
+
+
+# ---- drop-in installation -----------------------------------------------------------------------
+_SAVED: dict = {}
+
+
+def install(precision: str | None = None):
+    """Rebind ``opticomlib.devices.{FIBER,DBP,LPF,BPF}`` (and the import-time copies
+    ``opticomlib.ook.LPF`` / ``opticomlib.ppm.LPF``, reference ook.py:16, ppm.py:21) to this path.
+    In-module callers (DAC->LPF, PD->LPF, MZM->BPF, EDFA->BPF) resolve the names through the module
+    globals at call time, so they are redirected too."""
+    global DEFAULT_PRECISION
+    import importlib
+
+    dv = importlib.import_module("opticomlib.devices")
+    if precision is not None:
+        _complex_dtype(precision)
+        DEFAULT_PRECISION = precision
+    for name, fn in (("FIBER", FIBER), ("DBP", DBP), ("LPF", LPF), ("BPF", BPF)):
+        _SAVED.setdefault(("opticomlib.devices", name), getattr(dv, name))
+        setattr(dv, name, fn)
+    for modname in ("opticomlib.ook", "opticomlib.ppm"):
+        mod = sys.modules.get(modname)
+        if mod is not None and hasattr(mod, "LPF"):
+            _SAVED.setdefault((modname, "LPF"), mod.LPF)
+            mod.LPF = LPF
+
+
+def uninstall():
+    for (modname, name), fn in list(_SAVED.items()):
+        mod = sys.modules.get(modname)
+        if mod is not None:
+            setattr(mod, name, fn)
+    _SAVED.clear()

@@ -1,0 +1,147 @@
+"""Host-side engine: plan cache + batched propagation over PyTorch CUDA tensors.
+
+PyTorch is plumbing here (device memory, streams, ``torch.distributed``); every numerical
+operation of the hot path runs in the hand-written kernels behind the C-ABI (``_lib``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def require_cuda(device=None):
+    """Resolve the CUDA device to run on or fail loudly (no CPU fallback)."""
+    torch = _torch()
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("opticomlib_b200: no CUDA device visible; FIBER/DBP/LPF/BPF have no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("opticomlib_b200 runs on CUDA devices only, got %r" % (device,))
+    return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+@dataclass
+class StepInfo:
+    """Per-waveform outcome of a propagation (the bookkeeping of devices.py:1155-1196)."""
+    steps: np.ndarray      # int32[B]   number of steps taken
+    z: np.ndarray          # float64[B] position reached [km] (values of the compute real type)
+    h_next: np.ndarray     # float64[B]
+    done: np.ndarray       # bool[B]
+    h_log: np.ndarray | None = None   # float64[B, cap] step sizes taken (row b valid up to steps[b])
+
+    def sample_steps(self, samples_per_waveform: int) -> int:
+        return int(self.steps.astype(np.int64).sum()) * int(samples_per_waveform)
+
+
+class Plan:
+    """Owner of one ``ssfm_plan_t`` (twiddles, Kerr-phase stash, controller state)."""
+
+    def __init__(self, n, n_pol, batch, complex_dtype, device):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.n, self.n_pol, self.batch = int(n), int(n_pol), int(batch)
+        self.device = require_cuda(device)
+        self.cdtype = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
+        self.code = _lib.SSFM_C64 if self.cdtype == torch.complex64 else _lib.SSFM_C128
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.ssfm_plan_create(ctypes.byref(h), self.n, self.n_pol, self.batch, self.code,
+                                             self.device.index))
+        self.handle = h
+
+    def set_option(self, name: str, value: int):
+        _lib.check(self.lib.ssfm_plan_set_option(self.handle, name.encode(), int(value)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ssfm_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def propagate(self, field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01,
+                  h=None, max_steps=0, resume=False, want_log=False) -> StepInfo:
+        """In place on ``field`` (CUDA tensor [B, P, N] or [B, N], plan dtype, contiguous)."""
+        torch = _torch()
+        if field.dtype != self.cdtype or not field.is_cuda or not field.is_contiguous():
+            raise ValueError("field must be a contiguous CUDA tensor of dtype %s" % self.cdtype)
+        if field.numel() != self.batch * self.n_pol * self.n:
+            raise ValueError("field has %d elements, plan expects %d" % (field.numel(), self.batch * self.n_pol * self.n))
+        prm = _lib.FiberParams(float(dt), float(length), float(alpha), float(beta_2), float(beta_3), float(gamma),
+                               float(phi_max), math.nan if h is None else float(h))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ssfm_propagate(self.handle, field.data_ptr(), ctypes.byref(prm), int(max_steps),
+                                               1 if resume else 0, ctypes.c_void_p(stream)))
+        return self.state(want_log)
+
+    def state(self, want_log=False) -> StepInfo:
+        B = self.batch
+        steps = np.empty(B, np.int32); z = np.empty(B, np.float64); hn = np.empty(B, np.float64)
+        done = np.empty(B, np.int32)
+        _lib.check(self.lib.ssfm_get_state(self.handle, steps.ctypes.data, z.ctypes.data, hn.ctypes.data,
+                                           done.ctypes.data))
+        log = None
+        if want_log:
+            cap = int(max(1, steps.max()))
+            log = np.zeros((B, cap), np.float64)
+            _lib.check(self.lib.ssfm_get_step_log(self.handle, log.ctypes.data, cap))
+        return StepInfo(steps, z, hn, done.astype(bool), log)
+
+
+_PLANS: dict = {}
+
+
+def get_plan(n, n_pol, batch, complex_dtype, device=None) -> Plan:
+    torch = _torch()
+    dev = require_cuda(device)
+    cd = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
+    key = (int(n), int(n_pol), int(batch), cd, dev.index)
+    pl = _PLANS.get(key)
+    if pl is None:
+        if len(_PLANS) >= 8:  # plans own O(B*N) device memory: keep the cache small
+            _PLANS.pop(next(iter(_PLANS))).close()
+        pl = _PLANS[key] = Plan(n, n_pol, batch, cd, dev)
+    return pl
+
+
+def clear_plans():
+    while _PLANS:
+        _PLANS.popitem()[1].close()
+
+
+def filtfilt_sos(x, sos: np.ndarray, out=None):
+    """Zero-phase cascaded-biquad filter of a CUDA complex128 tensor [..., N] along the last axis."""
+    torch = _torch()
+    lib = _lib.load()
+    if x.dtype != torch.complex128 or not x.is_cuda or not x.is_contiguous():
+        raise ValueError("x must be a contiguous CUDA complex128 tensor")
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise ValueError("sos must have shape (n_sections, 6)")
+    y = torch.empty_like(x) if out is None else out
+    n = x.shape[-1]
+    rows = x.numel() // n
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        _lib.check(lib.ssfm_filtfilt_sos(x.data_ptr(), y.data_ptr(), rows, n, sos.ctypes.data, sos.shape[0],
+                                         x.device.index, ctypes.c_void_p(stream)))
+    return y

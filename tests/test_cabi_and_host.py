@@ -1,0 +1,119 @@
+"""CPU-side checks: the C-ABI library loads and exports exactly what include/ssfm_b200.h declares,
+the host-side containers mirror the reference surface, and the product refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from opticomlib_b200 import build, _lib
+    build.build()                                      # nvcc cross-compiles without a GPU
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from opticomlib_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ssfm_b200.h")).read()
+    declared = set(re.findall(r"SSFM_API\s+[\w\s\*]+?\b(ssfm_\w+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ssfm_abi_version() == 1
+    m = re.search(r"#define\s+SSFM_ABI_VERSION\s+(\d+)", header)
+    assert int(m.group(1)) == lib.ssfm_abi_version()
+
+
+def test_struct_layout_matches_header():
+    from opticomlib_b200 import _lib
+    assert ctypes.sizeof(_lib.FiberParams) == 8 * 8
+    assert [f[0] for f in _lib.FiberParams._fields_] == [
+        "dt_s", "length_km", "alpha_db_km", "beta2_ps2_km", "beta3_ps3_km", "gamma_w_km", "phi_max_rad", "h_km"]
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    from opticomlib_b200 import _lib
+    h = ctypes.c_void_p()
+    assert lib.ssfm_plan_create(ctypes.byref(h), 1000, 1, 1, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_UNSUPPORTED
+    assert b"power of two" in lib.ssfm_last_error()
+    assert lib.ssfm_plan_create(ctypes.byref(h), 4096, 3, 1, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_INVALID
+    assert b"n_pol" in lib.ssfm_last_error()
+    assert lib.ssfm_plan_create(ctypes.byref(h), 4096, 1, 0, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_INVALID
+    assert lib.ssfm_plan_create(ctypes.byref(h), 4096, 1, 1, 7, 0) == _lib.SSFM_ERR_INVALID
+    assert lib.ssfm_plan_destroy(None) == 0
+    with pytest.raises(ValueError):
+        _lib.check(_lib.SSFM_ERR_INVALID)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import opticomlib_b200 as ob
+    s = ob.optical_signal(np.ones(1024, complex))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ob.FIBER(s, length=1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ob.LPF(np.ones(100), BW=1e9)
+    with pytest.raises(TypeError):                                  # type check comes first, as in the reference
+        ob.FIBER(np.ones(8), length=1.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "opticomlib_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_signal_containers_mirror_reference_surface():
+    import opticomlib_b200 as ob
+    ob.gv(sps=16, R=1e9)
+    assert ob.gv.fs == 16e9 and ob.gv.dt == 1 / 16e9
+    e = ob.electrical_signal([1.0, 2.0, 3.0], [0.1, 0.1, 0.1])
+    assert e.size == 3 and e.ndim == 1 and e.type is ob.electrical_signal
+    assert np.allclose(e.to_numpy(), [1.1, 2.1, 3.1])
+    c = e[:]
+    c.signal[0] = 9
+    assert e.signal[0] == 1.0                                          # slicing copies (typing.py:1366)
+    o = ob.optical_signal(np.ones(8, complex))
+    assert o.n_pol == 1 and o.size == 8 and o.noise is ob.NULL
+    assert np.array_equal(o.to_numpy(), np.ones(8, complex))           # NULL + x -> x
+    o2 = ob.optical_signal(np.ones((2, 8), complex), 0.5 * np.ones((2, 8), complex))
+    assert o2.n_pol == 2 and o2.size == 8 and o2.to_numpy().shape == (2, 8)
+    assert np.allclose(o.w(), 2 * np.pi * np.fft.fftfreq(8) * ob.gv.fs)   # typing_test.py:1244-1251
+    assert ob.optical_signal(np.ones(8), n_pol=2).signal.shape == (2, 8)
+    with pytest.raises(ValueError):
+        ob.optical_signal(np.ones((3, 8)))
+    with pytest.raises(ValueError):
+        ob.electrical_signal(np.ones((2, 8)))
+
+
+def test_reference_objects_are_accepted_by_duck_typing(have_reference):
+    if not have_reference:
+        pytest.skip("reference tree not present")
+    from oracle.ref_shim import import_reference
+    import_reference()
+    import opticomlib
+    import opticomlib.devices as rdv
+    from opticomlib_b200 import devices as dv
+    r = opticomlib.optical_signal(np.ones(16, complex))
+    assert dv._kind(r) == "optical" and dv._gv_of(r) is opticomlib.gv
+    assert dv._kind(opticomlib.electrical_signal(np.ones(4))) == "electrical"
+    assert dv._is_null(r.noise)
+    original = rdv.FIBER
+    dv.install()
+    try:
+        assert rdv.FIBER is dv.FIBER and rdv.LPF is dv.LPF and rdv.BPF is dv.BPF and rdv.DBP is dv.DBP
+    finally:
+        dv.uninstall()
+    assert rdv.FIBER is original

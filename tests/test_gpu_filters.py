@@ -1,0 +1,93 @@
+"""GPU parity tests for LPF / BPF (pytest -m gpu): CUDA filtfilt vs golden reference outputs,
+vs the CPU oracle and vs scipy.signal.sosfiltfilt itself.  Tolerance 1e-10 rel-L2 (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle.filtfilt_oracle import oracle_sosfiltfilt, bessel_sos
+from oracle.ssfm_oracle import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import opticomlib_b200 as ob
+    return ob
+
+
+def _set_fs(ob, fs):
+    ob.gv.fs = float(fs)
+    ob.gv.dt = 1.0 / float(fs)
+
+
+@pytest.mark.parametrize("name", ["lpf_ones_100", "lpf_n3_4096", "lpf_n4_4096", "lpf_n5_4096", "lpf_complex_1000"])
+def test_lpf_matches_reference(ob, name):
+    g = golden(name)
+    _set_fs(ob, g["fs"])
+    has_noise = "xn" in g.files
+    inp = ob.electrical_signal(g["x"], g["xn"]) if has_noise else ob.electrical_signal(g["x"])
+    out = ob.LPF(inp, BW=float(g["bw"]), n=int(g["n"]))
+    assert out.type is ob.electrical_signal and out.size == inp.size
+    assert out.signal.dtype == np.float64
+    assert rel_l2(out.signal, g["out"]) <= TOL
+    if has_noise:
+        assert rel_l2(out.noise, g["outn"]) <= TOL
+    else:
+        assert out.noise is ob.NULL
+    assert out.execution_time > 0
+
+
+@pytest.mark.parametrize("name", ["bpf_2pol_4096", "bpf_1pol_n5_8192"])
+def test_bpf_matches_reference(ob, name):
+    g = golden(name)
+    _set_fs(ob, g["fs"])
+    has_noise = "xn" in g.files
+    inp = ob.optical_signal(g["x"], g["xn"]) if has_noise else ob.optical_signal(g["x"])
+    out = ob.BPF(inp, BW=float(g["bw"]), n=int(g["n"]))
+    assert out.type is ob.optical_signal and out.size == inp.size and out.n_pol == inp.n_pol
+    assert rel_l2(out.signal, g["out"]) <= TOL
+    if has_noise:
+        assert rel_l2(out.noise, g["outn"]) <= TOL
+
+
+def test_lpf_fs_argument_ndarray_input_and_retH(ob):
+    from scipy import signal as sg
+    _set_fs(ob, 1e9)
+    x = np.random.default_rng(3).standard_normal(777)
+    out, H = ob.LPF(x, BW=2e9, n=4, fs=40e9, retH=True)
+    sos = bessel_sos(4, 2e9, 40e9)
+    assert rel_l2(out.signal, sg.sosfiltfilt(sos, x)) <= TOL
+    _, Href = sg.sosfreqz(sos, worN=777, fs=40e9, whole=True)
+    assert np.allclose(H, np.fft.fftshift(Href))
+    assert out.execution_time == 0.0                                    # reference returns before toc() (devices.py:1370-1372)
+
+
+@pytest.mark.parametrize("n_samples,rows", [(1 << 16, 8), (1 << 18, 4), (100000, 3)])
+def test_filtfilt_batch_large_rows_vs_oracle_and_scipy(ob, n_samples, rows):
+    from scipy import signal as sg
+    rng = np.random.default_rng(n_samples)
+    x = rng.standard_normal((rows, n_samples)) + 1j * rng.standard_normal((rows, n_samples))
+    x[0] += 3.0                                                         # non-zero mean exercises the zi*x0 start-up
+    sos = bessel_sos(4, 20e9, 640e9)
+    y = ob.filtfilt_batch(x, sos)
+    assert rel_l2(y, sg.sosfiltfilt(sos, x, axis=-1)) <= TOL
+    assert rel_l2(y[:2], oracle_sosfiltfilt(sos, x[:2])) <= TOL
+    # linearity (size-independent property)
+    y2 = ob.filtfilt_batch(2.5 * x + 1.0, sos)
+    dc = ob.filtfilt_batch(np.ones((1, n_samples), complex), sos)
+    assert rel_l2(y2, 2.5 * y + dc) <= 1e-9
+
+
+def test_filter_errors_match_reference(ob):
+    _set_fs(ob, 16e9)
+    with pytest.raises(TypeError, match="optical_signal"):
+        ob.BPF(ob.electrical_signal(np.ones(100)), BW=1e9)
+    with pytest.raises(ValueError, match="1D-array"):
+        ob.LPF(ob.optical_signal(np.ones((2, 100), complex)), BW=1e9)
+    with pytest.raises(ValueError, match="padlen"):                     # scipy's message for N <= edge
+        ob.LPF(ob.electrical_signal(np.ones(15)), BW=1e9)
