@@ -92,6 +92,14 @@ SSFM_API int ssfm_get_state(ssfm_plan_t plan, int32_t* steps_host, double* z_hos
 /* Step sizes taken, hlog_host[n_waveforms][cap] (rows are filled up to min(steps, cap)). */
 SSFM_API int ssfm_get_step_log(ssfm_plan_t plan, double* hlog_host, int64_t cap);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched in this process, and
+ * the average device time [ms] of the three kernels of one split step (column forward, row,
+ * column inverse) measured with CUDA events on `stream` over `reps` steps on field_dev (the field
+ * is advanced by `reps` fixed steps of prm->h_km or 1e-3 km; use a scratch copy). */
+SSFM_API int64_t ssfm_launch_count(void);
+SSFM_API int ssfm_time_step_kernels(ssfm_plan_t plan, void* field_dev, const ssfm_fiber_params* prm,
+                           int32_t reps, float* ms_out3, void* stream);
+
 /* Same as ssfm_propagate but with HOST buffers: copies field_in_host to the device (casting is the
  * caller's job: the buffer must already have the plan's dtype), propagates, copies the result to
  * field_out_host.  This is the block devices.py:1147-1204 (asarray -> loop -> .get()). */

@@ -13,6 +13,7 @@
 using namespace ssfm;
 
 thread_local std::string ssfm_err_slot;   // shared with filtfilt.cu
+long long ssfm_launches = 0;              // kernels launched by this library (bench.py's gpu_launches)
 
 namespace {
 
@@ -120,6 +121,7 @@ int launch_col_fwd(const Params<R>& p, int nblocks, cudaStream_t st) {
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_fwd<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_col_fwd<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    ++ssfm_launches;
     return SSFM_OK;
 }
 template <typename R, int M>
@@ -130,6 +132,7 @@ int launch_col_inv(const Params<R>& p, int nblocks, cudaStream_t st) {
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_inv<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_col_inv<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    ++ssfm_launches;
     return SSFM_OK;
 }
 template <typename R, int M>
@@ -140,6 +143,7 @@ int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_row<R, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_row<R, M, G><<<nblocks, G * (M / 16), smem, st>>>(p);
+    ++ssfm_launches;
     return SSFM_OK;
 }
 
@@ -174,15 +178,14 @@ int enqueue_step(const Params<R>& p, cudaStream_t st) {
 }
 
 template <typename R>
-int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long long max_steps, int resume,
-                cudaStream_t st) {
+Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed, bool& single) {
     typedef typename cx_of<R>::type C;
     // scalar casts exactly as devices.py:1137-1142 (division in double first, then rounded to R)
     const R a_lin = (R)(prm.alpha_db_km / 4.343);
     const R b2 = (R)prm.beta2_ps2_km, b3 = (R)prm.beta3_ps3_km, g = (R)prm.gamma_w_km;
     const R L = (R)prm.length_km, pm = (R)prm.phi_max_rad;
-    const bool fixed = !std::isnan(prm.h_km);
-    const bool single = !fixed && ((b2 == (R)0 && b3 == (R)0) || g == (R)0);
+    fixed = !std::isnan(prm.h_km);
+    single = !fixed && ((b2 == (R)0 && b3 == (R)0) || g == (R)0);
 
     Params<R> base;
     std::memset(&base, 0, sizeof(base));
@@ -201,6 +204,15 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
     base.c3 = (R)(1.0 / 6.0) * b3;               // imag(1j/6 * beta_3): R(1/6) times beta_3, rounded once
     base.fval = 1.0 / ((double)pl->n * prm.dt_s);
     base.inv_n = (R)1 / (R)pl->n;
+    return base;
+}
+
+template <typename R>
+int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long long max_steps, int resume,
+                cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    bool fixed, single;
+    const Params<R> base = base_params<R>(pl, prm, fixed, single);
 
     const long long B = pl->batch;
     const long long chunk = (pl->chunk > 0 && pl->chunk < B) ? pl->chunk : B;
@@ -227,9 +239,11 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
                 if (per > 64) per = 64;
                 if (per < 1) per = 1;
                 k_power_max<R><<<(unsigned)(nb * per), 256, 0, st>>>(p, per);
+                ++ssfm_launches;
             }
             k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, fixed ? 1 : 0, fixed ? (R)prm.h_km : (R)0,
                                                                       single ? 1 : 0);
+            ++ssfm_launches;
             CU_TRY(cudaGetLastError());
         } else {
             // re-arm: waveforms that have not reached `length` continue; recount them on the host
@@ -275,9 +289,70 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
     return SSFM_OK;
 }
 
+
+// average device time of the three kernels of one step, CUDA events on the launching stream
+template <typename R>
+int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in, int reps, float* ms3, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    ssfm_fiber_params prm = prm_in;
+    if (std::isnan(prm.h_km)) prm.h_km = 1e-3;
+    prm.length_km = 1e30;                                 // never finishes: every launch does full work
+    bool fixed, single;
+    Params<R> p = base_params<R>(pl, prm, fixed, single);
+    p.field = (C*)field; p.stash = (R*)pl->stash; p.ctrl = pl->ctrl; p.active = pl->active; p.hlog = nullptr;
+    p.batch = (int)pl->batch;
+    const int nb = (int)pl->batch;
+    CU_TRY(cudaMemcpyAsync(p.active, &nb, sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)nb, st));
+    k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, 1, (R)prm.h_km, 0);
+    cudaEvent_t ev[4];
+    for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
+    const long long rows = (long long)p.batch * p.n_pol;
+    double acc[3] = {0, 0, 0};
+    int rc = SSFM_OK;
+    for (int r = -2; r < reps && !rc; ++r) {                 // two untimed warm-up steps
+        CU_TRY(cudaEventRecord(ev[0], st));
+        switch (p.n1) {
+#define X(M) case M: rc = launch_col_fwd<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
+            SSFM_FOR_M(X)
+#undef X
+        }
+        CU_TRY(cudaEventRecord(ev[1], st));
+        switch (p.n2) {
+#define X(M) case M: if (!rc) rc = launch_row<R, M>(p, (int)(rows * p.n1 / row_group(M)), st); break;
+            SSFM_FOR_M(X)
+#undef X
+        }
+        CU_TRY(cudaEventRecord(ev[2], st));
+        switch (p.n1) {
+#define X(M) case M: if (!rc) rc = launch_col_inv<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
+            SSFM_FOR_M(X)
+#undef X
+        }
+        CU_TRY(cudaEventRecord(ev[3], st));
+        CU_TRY(cudaEventSynchronize(ev[3]));
+        if (r >= 0)
+            for (int k = 0; k < 3; ++k) { float ms = 0; CU_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); acc[k] += ms; }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (int k = 0; k < 3; ++k) ms3[k] = (float)(acc[k] / (reps > 0 ? reps : 1));
+    pl->have_state = false;
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t ssfm_launch_count(void) { return ssfm_launches; }
+
+int ssfm_time_step_kernels(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, int32_t reps, float* ms3,
+                           void* stream) {
+    if (!pl || !field || !prm || !ms3 || reps < 1) return fail(SSFM_ERR_INVALID, "null argument or reps < 1");
+    CU_TRY(cudaSetDevice(pl->device));
+    if (pl->dtype == SSFM_C64) return time_kernels_t<float>(pl, field, *prm, reps, ms3, (cudaStream_t)stream);
+    return time_kernels_t<double>(pl, field, *prm, reps, ms3, (cudaStream_t)stream);
+}
 
 int ssfm_abi_version(void) { return SSFM_ABI_VERSION; }
 const char* ssfm_last_error(void) { return g_err.c_str(); }

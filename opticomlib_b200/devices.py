@@ -79,21 +79,31 @@ def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
     torch = engine._torch()
     tdtype, ndtype = _complex_dtype(precision)
     as_tensor = torch.is_tensor(field)
-    if as_tensor:
-        dev = engine.require_cuda(field.device if field.is_cuda else device)
-        x = field.to(device=dev, dtype=tdtype).contiguous()
+    on_host = not (as_tensor and field.is_cuda)
+    if not on_host:
+        dev = engine.require_cuda(field.device)
+        x = field.to(dtype=tdtype).contiguous()
         if not inplace and x.data_ptr() == field.data_ptr():
             x = x.clone()
     else:
         dev = engine.require_cuda(device)
-        x = _to_device(np.asarray(field), tdtype, dev)
+        if as_tensor:                                                  # host tensor (pinned => async copy)
+            x = field.to(dev, non_blocking=True).to(tdtype).contiguous()
+        else:
+            x = _to_device(np.asarray(field), tdtype, dev)
     if x.ndim not in (2, 3):
         raise ValueError("field must have shape [B, N] or [B, P, N]")
     B, P, N = (x.shape[0], 1, x.shape[1]) if x.ndim == 2 else tuple(x.shape)
     plan = engine.get_plan(N, P, B, tdtype, dev)
     plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
     info = plan.propagate(x, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
-    return (x if as_tensor else x.cpu().numpy()), info
+    if not on_host:
+        return x, info
+    if as_tensor:
+        out = torch.empty(x.shape, dtype=x.dtype, pin_memory=field.is_pinned())
+        out.copy_(x)
+        return out, info
+    return x.cpu().numpy(), info
 
 
 def dbp_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, **kw):

@@ -93,6 +93,20 @@ class Plan:
                                                1 if resume else 0, ctypes.c_void_p(stream)))
         return self.state(want_log)
 
+    def time_step_kernels(self, field, dt, reps=5, **fiber):
+        """Average device time [ms] of (column forward, row, column inverse) over ``reps`` steps.
+        Advances ``field`` -- pass a scratch copy.  Measurement hook for bench.py."""
+        torch = _torch()
+        prm = _lib.FiberParams(float(dt), 1.0, float(fiber.get("alpha", 0.0)), float(fiber.get("beta_2", 0.0)),
+                               float(fiber.get("beta_3", 0.0)), float(fiber.get("gamma", 0.0)),
+                               float(fiber.get("phi_max", 0.01)), float(fiber.get("h") or 1e-3))
+        ms = (ctypes.c_float * 3)()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ssfm_time_step_kernels(self.handle, field.data_ptr(), ctypes.byref(prm), int(reps),
+                                                       ms, ctypes.c_void_p(stream)))
+        return [float(v) for v in ms]
+
     def state(self, want_log=False) -> StepInfo:
         B = self.batch
         steps = np.empty(B, np.int32); z = np.empty(B, np.float64); hn = np.empty(B, np.float64)
@@ -121,6 +135,11 @@ def get_plan(n, n_pol, batch, complex_dtype, device=None) -> Plan:
             _PLANS.pop(next(iter(_PLANS))).close()
         pl = _PLANS[key] = Plan(n, n_pol, batch, cd, dev)
     return pl
+
+
+def launch_count() -> int:
+    """Kernels launched by the extension in this process (bench.py's ``gpu_launches``)."""
+    return int(_lib.load().ssfm_launch_count())
 
 
 def clear_plans():
