@@ -32,6 +32,7 @@ int ilog2(long long v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
 
 // compile-time geometry ------------------------------------------------------------------------
 constexpr int col_tile(int M) { return M <= 32 ? M : (M <= 128 ? 32 : (M == 256 ? 16 : (M == 512 ? 8 : 4))); }
+int col_tile_rt(int M) { return col_tile(M); }
 constexpr int row_group(int M) { return (4096 / M) < (M / 2) ? (4096 / M) : (M / 2); }
 
 // twiddle tables, built on the device in double and rounded once to R ---------------------------
@@ -100,6 +101,9 @@ struct ssfm_plan_s {
     void* stash = nullptr;
     Ctrl* ctrl = nullptr;
     int* active = nullptr;       // one counter per chunk
+    unsigned int* ticket = nullptr;
+    int fused = 1;               // 1: fused column kernel (2R+2W per step) when its barrier fits on the chip
+    int num_sms = 0;
     int n_active = 0;
     double* hlog = nullptr;
     int hlog_cap = 0;
@@ -136,6 +140,30 @@ int launch_col_inv(const Params<R>& p, int nblocks, cudaStream_t st) {
     return SSFM_OK;
 }
 template <typename R, int M>
+int launch_col_mid(const Params<R>& p, int nblocks, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    constexpr int T = col_tile(M);
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
+    static bool attr = false;
+    if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_col_mid<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    ++ssfm_launches;
+    return SSFM_OK;
+}
+// resident CTAs of the fused kernel on the whole chip (its per-waveform barrier must fit)
+template <typename R, int M>
+int col_mid_capacity(int num_sms, int* out) {
+    typedef typename cx_of<R>::type C;
+    constexpr int T = col_tile(M);
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
+    CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_col_mid<R, M, T>, T * (M / 16), smem));
+    *out = per_sm * num_sms;
+    return SSFM_OK;
+}
+
+template <typename R, int M>
 int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
     constexpr int G = row_group(M);
@@ -149,32 +177,42 @@ int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
 
 #define SSFM_FOR_M(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
+enum ColKind { COL_FWD, COL_INV, COL_MID };
+
 template <typename R>
-int enqueue_step(const Params<R>& p, cudaStream_t st) {
+int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st) {
     const long long rows = (long long)p.batch * p.n_pol;
-    int rc = SSFM_ERR_UNSUPPORTED;
-    // column pass forward
     switch (p.n1) {
-#define X(M) case M: rc = launch_col_fwd<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
+#define X(M) case M: {                                                             \
+            const int nb = (int)(rows * (p.n2 / col_tile(M)));                     \
+            return kind == COL_FWD ? launch_col_fwd<R, M>(p, nb, st)               \
+                 : kind == COL_INV ? launch_col_inv<R, M>(p, nb, st)               \
+                                   : launch_col_mid<R, M>(p, nb, st); }
         SSFM_FOR_M(X)
 #undef X
         default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported column transform size");
     }
-    if (rc) return rc;
+}
+
+template <typename R>
+int enqueue_row(const Params<R>& p, cudaStream_t st) {
+    const long long rows = (long long)p.batch * p.n_pol;
     switch (p.n2) {
-#define X(M) case M: rc = launch_row<R, M>(p, (int)(rows * p.n1 / row_group(M)), st); break;
+#define X(M) case M: return launch_row<R, M>(p, (int)(rows * p.n1 / row_group(M)), st);
         SSFM_FOR_M(X)
 #undef X
         default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported row transform size");
     }
-    if (rc) return rc;
-    switch (p.n1) {
-#define X(M) case M: rc = launch_col_inv<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
+}
+
+template <typename R>
+int fused_capacity(int n1, int num_sms, int* out) {
+    switch (n1) {
+#define X(M) case M: return col_mid_capacity<R, M>(num_sms, out);
         SSFM_FOR_M(X)
 #undef X
         default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported column transform size");
     }
-    return rc;
 }
 
 template <typename R>
@@ -218,6 +256,14 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
     const long long chunk = (pl->chunk > 0 && pl->chunk < B) ? pl->chunk : B;
     const size_t wf_elems = (size_t)pl->n_pol * (size_t)pl->n;
     const long long budget = max_steps > 0 ? max_steps : (1ll << 40);
+    bool use_fused = pl->fused != 0;
+    if (use_fused) {   // the per-waveform barrier of k_col_mid needs all tiles of a waveform resident at once
+        int cap = 0;
+        int rc = fused_capacity<R>(pl->n1, pl->num_sms, &cap);
+        if (rc) return rc;
+        const long long group = (long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1));
+        if (group > cap) use_fused = false;
+    }
 
     int ci = 0;
     for (long long b0 = 0; b0 < B; b0 += chunk, ++ci) {
@@ -227,6 +273,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         p.stash = (R*)pl->stash + (size_t)b0 * wf_elems;
         p.ctrl = pl->ctrl + b0;
         p.active = pl->active + ci;
+        p.ticket = pl->ticket;
         p.hlog = pl->hlog ? pl->hlog + (size_t)b0 * pl->hlog_cap : nullptr;
         p.batch = (int)nb;
 
@@ -257,14 +304,27 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
             if (act == 0) continue;
         }
 
+        // One step = row kernel + column kernel(s).  Fused schedule (2R+2W per step):
+        //   col_fwd | row, col_mid | row, col_mid | ...   (col_mid = end of step s + start of step s+1)
+        // and the last budgeted step ends with col_inv so that the field is back in the time domain.
+        // Unfused schedule (3R+3W): col_fwd, row, col_inv per step.
         long long enq = 0;
         int slot = 0;
         bool pending = false, finished = false;
+        if (use_fused) { int rc = enqueue_col<R>(p, COL_FWD, st); if (rc) return rc; }
         while (!finished) {
             long long nsteps = pl->burst;
             if (enq + nsteps > budget) nsteps = budget - enq;
             for (long long s = 0; s < nsteps; ++s) {
-                int rc = enqueue_step<R>(p, st);
+                int rc = SSFM_OK;
+                if (use_fused) {
+                    rc = enqueue_row<R>(p, st);
+                    if (!rc) rc = enqueue_col<R>(p, (enq + s + 1 == budget) ? COL_INV : COL_MID, st);
+                } else {
+                    rc = enqueue_col<R>(p, COL_FWD, st);
+                    if (!rc) rc = enqueue_row<R>(p, st);
+                    if (!rc) rc = enqueue_col<R>(p, COL_INV, st);
+                }
                 if (rc) return rc;
             }
             enq += nsteps;
@@ -305,34 +365,37 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
     CU_TRY(cudaMemcpyAsync(p.active, &nb, sizeof(int), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)nb, st));
     k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, 1, (R)prm.h_km, 0);
+    p.ticket = pl->ticket;
+    bool use_fused = pl->fused != 0;
+    if (use_fused) {
+        int cap = 0;
+        int rc0 = fused_capacity<R>(pl->n1, pl->num_sms, &cap);
+        if (rc0) return rc0;
+        if ((long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1)) > cap) use_fused = false;
+    }
     cudaEvent_t ev[4];
     for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
-    const long long rows = (long long)p.batch * p.n_pol;
     double acc[3] = {0, 0, 0};
     int rc = SSFM_OK;
+    if (use_fused) {   // steady state: row + fused column kernel; the opening col_fwd is timed once
+        CU_TRY(cudaEventRecord(ev[0], st));
+        rc = enqueue_col<R>(p, COL_FWD, st);
+        CU_TRY(cudaEventRecord(ev[1], st));
+        CU_TRY(cudaEventSynchronize(ev[1]));
+        float ms0 = 0; CU_TRY(cudaEventElapsedTime(&ms0, ev[0], ev[1]));
+        acc[0] = (double)ms0 * (reps > 0 ? reps : 1);
+    }
     for (int r = -2; r < reps && !rc; ++r) {                 // two untimed warm-up steps
         CU_TRY(cudaEventRecord(ev[0], st));
-        switch (p.n1) {
-#define X(M) case M: rc = launch_col_fwd<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
-            SSFM_FOR_M(X)
-#undef X
-        }
+        if (!use_fused) rc = enqueue_col<R>(p, COL_FWD, st);
         CU_TRY(cudaEventRecord(ev[1], st));
-        switch (p.n2) {
-#define X(M) case M: if (!rc) rc = launch_row<R, M>(p, (int)(rows * p.n1 / row_group(M)), st); break;
-            SSFM_FOR_M(X)
-#undef X
-        }
+        if (!rc) rc = enqueue_row<R>(p, st);
         CU_TRY(cudaEventRecord(ev[2], st));
-        switch (p.n1) {
-#define X(M) case M: if (!rc) rc = launch_col_inv<R, M>(p, (int)(rows * (p.n2 / col_tile(M))), st); break;
-            SSFM_FOR_M(X)
-#undef X
-        }
+        if (!rc) rc = enqueue_col<R>(p, use_fused ? COL_MID : COL_INV, st);
         CU_TRY(cudaEventRecord(ev[3], st));
         CU_TRY(cudaEventSynchronize(ev[3]));
         if (r >= 0)
-            for (int k = 0; k < 3; ++k) { float ms = 0; CU_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); acc[k] += ms; }
+            for (int k = use_fused ? 1 : 0; k < 3; ++k) { float ms = 0; CU_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); acc[k] += ms; }
     }
     for (auto& e : ev) cudaEventDestroy(e);
     for (int k = 0; k < 3; ++k) ms3[k] = (float)(acc[k] / (reps > 0 ? reps : 1));
@@ -381,6 +444,9 @@ int ssfm_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, 
     e = cudaMalloc(&pl->stash, elems * rsz);
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ctrl, sizeof(Ctrl) * (size_t)batch);
     if (e == cudaSuccess) { pl->n_active = (int)batch; e = cudaMalloc((void**)&pl->active, sizeof(int) * (size_t)batch); }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ticket, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(pl->ticket, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->hlog, sizeof(double) * (size_t)batch * pl->hlog_cap);
     if (e == cudaSuccess) e = cudaMalloc(&pl->tw_lo, csz * (size_t)pl->n2);
     if (e == cudaSuccess) e = cudaMalloc(&pl->tw_hi, csz * (size_t)pl->n1);
@@ -416,7 +482,7 @@ int ssfm_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, 
 int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (!pl) return SSFM_OK;
     cudaSetDevice(pl->device);
-    cudaFree(pl->stash); cudaFree(pl->ctrl); cudaFree(pl->active); cudaFree(pl->hlog);
+    cudaFree(pl->stash); cudaFree(pl->ctrl); cudaFree(pl->active); cudaFree(pl->hlog); cudaFree(pl->ticket);
     cudaFree(pl->tw_col); cudaFree(pl->tw_row); cudaFree(pl->tw_lo); cudaFree(pl->tw_hi);
     if (pl->active_host) cudaFreeHost(pl->active_host);
     if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
@@ -430,6 +496,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     const std::string k(name);
     if (k == "chunk_waveforms") { if (value < 0) return fail(SSFM_ERR_INVALID, "chunk_waveforms < 0"); pl->chunk = value; }
     else if (k == "burst_steps") { if (value < 1 || value > 4096) return fail(SSFM_ERR_INVALID, "burst_steps out of range"); pl->burst = (int)value; }
+    else if (k == "fused") { pl->fused = value ? 1 : 0; }
     else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
     return SSFM_OK;
 }

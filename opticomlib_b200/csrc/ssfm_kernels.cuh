@@ -41,6 +41,7 @@ struct Params {
     R* stash;            // [B][P][N] Kerr phase of the current step
     Ctrl* ctrl;          // [B]
     int* active;         // number of waveforms with done == 0
+    unsigned int* ticket;// start-order ticket counter of the fused column kernel
     double* hlog;        // [B][hlog_cap] step sizes actually taken (may be null)
     const C* tw_col;     // pass tables of the N1-point transform
     const C* tw_row;     // pass tables of the N2-point transform
@@ -123,10 +124,16 @@ __device__ __forceinline__ void controller_update(const Params<R>& p, int b, R p
     const R rem = p.length - z;
     hn = (rem < hn) ? rem : hn;                         // python min(h_, length - z)
     const int done = !(z < p.length) || (s + 1 >= p.max_steps);
-    c.z = (double)z; c.h = (double)hn; c.steps = s + 1; c.pmax = 0ull; c.arrived = 0u;
+    c.z = (double)z; c.h = (double)hn; c.pmax = 0ull; c.arrived = 0u;
     c.done = done;
     if (done) atomicSub(p.active, 1);
+    __threadfence();                                    // publish the new state, then the step count
+    *reinterpret_cast<volatile int*>(&c.steps) = s + 1; // (waiters of k_col_mid spin on it)
 }
+
+// Two resident CTAs per SM (<= 128 registers) whenever a CTA has at most 256 threads: one CTA's
+// global loads overlap the other's transform.
+__host__ __device__ constexpr int min_ctas(int threads) { return threads <= 256 ? 2 : 1; }
 
 template <typename C>
 __device__ __forceinline__ void load_tables(C* dst, const C* __restrict__ src, int count) {
@@ -184,7 +191,7 @@ __global__ void k_ctrl_init(Params<R> p, int fixed, R h_fixed, int single_step) 
 // column pass, forward
 // ---------------------------------------------------------------------------------------------
 template <typename R, int M, int T>
-__global__ void __launch_bounds__(T * (M / 16)) k_col_fwd(Params<R> p) {
+__global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_fwd(Params<R> p) {
     typedef typename cx_of<R>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* sm = reinterpret_cast<C*>(smem_raw);                   // [M][T] exchange tile
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(T * (M / 16)) k_col_fwd(Params<R> p) {
 // row pass: forward transform, linear operator, inverse transform
 // ---------------------------------------------------------------------------------------------
 template <typename R, int M, int G>
-__global__ void __launch_bounds__(G * (M / 16)) k_row(Params<R> p) {
+__global__ void __launch_bounds__(G * (M / 16), min_ctas(G * (M / 16))) k_row(Params<R> p) {
     typedef typename cx_of<R>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PM = pad16(M) + 1;
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(G * (M / 16)) k_row(Params<R> p) {
 // column pass, inverse, second Kerr half step, power max, controller
 // ---------------------------------------------------------------------------------------------
 template <typename R, int M, int T>
-__global__ void __launch_bounds__(T * (M / 16)) k_col_inv(Params<R> p) {
+__global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_inv(Params<R> p) {
     typedef typename cx_of<R>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
@@ -335,6 +342,121 @@ __global__ void __launch_bounds__(T * (M / 16)) k_col_inv(Params<R> p) {
             const R all = from_bits<R>(atomicMax(&p.ctrl[b].pmax, 0ull));
             controller_update<R>(p, b, all);
         }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// fused column pass: end of step s and start of step s+1 in one visit of the tile
+//   conj twiddle, inverse column transforms, 1/N, max |A|^2  ->  per-waveform barrier + controller
+//   ->  rotation by the stashed phase of step s PLUS the first Kerr half step of step s+1
+//       (one sincos), stash of the new phase, forward column transforms, twiddle.
+// Field traffic per step drops from 3R+3W to 2R+2W (the ideal of SURVEY.md §8(d)).
+//
+// The barrier spans the tiles of ONE waveform (they need its global max, devices.py:1194).  CTAs
+// take a ticket when they start, and the ticket -- not blockIdx -- selects the tile, so the tiles
+// of a waveform are started in order and the lowest unfinished waveform always has all its tiles
+// resident: no deadlock as long as tiles-per-waveform <= resident CTAs (checked by the host).
+// ---------------------------------------------------------------------------------------------
+template <typename R, int M, int T>
+__global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mid(Params<R> p) {
+    typedef typename cx_of<R>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long red[32];
+    __shared__ unsigned int s_ticket;
+    C* sm = reinterpret_cast<C*>(smem_raw);
+    C* tw = sm + M * T;
+
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(p.ticket, 1u);
+        if (tk == gridDim.x - 1) *p.ticket = 0u;             // last CTA to start re-arms the counter
+        s_ticket = tk;
+    }
+    __syncthreads();
+    const int blk = (int)s_ticket;
+    const int tiles = p.n2 / T;
+    const int tile = blk % tiles, row = blk / tiles;
+    const int b = row / p.n_pol;
+    Ctrl* ctl = p.ctrl + b;
+    if (ctl->done) return;
+    const int step_before = ctl->steps;
+
+    const int c = threadIdx.x % T, t = threadIdx.x / T;
+    const int n2 = tile * T + c;
+    load_tables(tw, p.tw_col, fft_plan<M>::table_size);
+
+    C* rowp = p.field + (size_t)row * p.n;
+    R* strow = p.stash + (size_t)row * p.n;
+    C v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int k1 = t + q * (M / 16);
+        v[q] = cmulc(rowp[(size_t)k1 * p.n2 + n2], fourstep_twiddle<R>(p, n2, k1));
+    }
+    __syncthreads();
+    fft_passes<R, M, +1, ColExchange<T> >::run(v, sm + c, tw, t);
+
+    R pm = 0;
+    bool nan = false;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        v[q].x *= p.inv_n; v[q].y *= p.inv_n;                  // numpy ifft scaling (exact: N = 2^n)
+        const R pw = v[q].x * v[q].x + v[q].y * v[q].y;        // the Kerr rotations do not change |A|
+        nan |= (pw != pw);
+        pm = pw > pm ? pw : pm;
+    }
+    if (nan) pm = pw_nan<R>();
+    pm = block_max_bits<R>(pm, red);
+
+    // ---- per-waveform barrier; the last tile to arrive runs the controller ------------------------
+    if (threadIdx.x == 0) {
+        atomicMax(&ctl->pmax, ord_bits(pm));
+        __threadfence();
+        const unsigned total = (unsigned)(tiles * p.n_pol);
+        const unsigned prev = atomicAdd(&ctl->arrived, 1u);
+        if (prev + 1u == total) {
+            __threadfence();
+            const R all = from_bits<R>(atomicMax(&ctl->pmax, 0ull));
+            controller_update<R>(p, b, all);
+        } else {
+            while (*reinterpret_cast<volatile int*>(&ctl->steps) == step_before) __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    const int done = *reinterpret_cast<volatile int*>(&ctl->done);
+    const R hh = (R)(*reinterpret_cast<volatile double*>(&ctl->h)) / (R)2;    // h_/2 of the NEXT step
+
+    if (done) {                                                 // last step of this waveform: time domain out
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
+            if (p.has_nl) {
+                R s, co; sincos_r(strow[off], &s, &co);
+                v[q] = cmul(v[q], mk<R>(co, s));
+            }
+            rowp[off] = v[q];
+        }
+        return;
+    }
+    if (p.has_nl) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
+            const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+            const R ph = mul_rn(hh, mul_rn(p.gamma, pw));       // first half step of the next step
+            const R tot = strow[off] + ph;                      // + second half step of this one
+            strow[off] = ph;
+            R s, co; sincos_r(tot, &s, &co);
+            v[q] = cmul(v[q], mk<R>(co, s));
+        }
+    }
+    fft_passes<R, M, -1, ColExchange<T> >::run(v, sm + c, tw, t);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int k1 = t + q * (M / 16);
+        v[q] = cmul(v[q], fourstep_twiddle<R>(p, n2, k1));
+        rowp[(size_t)k1 * p.n2 + n2] = v[q];
     }
 }
 

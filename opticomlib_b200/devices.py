@@ -69,7 +69,7 @@ def _to_device(a: np.ndarray, tdtype, dev):
 
 # ---- FIBER / DBP --------------------------------------------------------------------------------
 def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
-                precision=None, device=None, want_log=False, chunk_waveforms=None, inplace=False):
+                precision=None, device=None, want_log=False, chunk_waveforms=None, inplace=False, fused=True):
     """Propagate a batch ``field[B, N]`` or ``field[B, P, N]`` (NumPy array or CUDA tensor).
 
     Rows are independent waveforms, each with its own step-size sequence (the global max of
@@ -96,6 +96,7 @@ def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
     B, P, N = (x.shape[0], 1, x.shape[1]) if x.ndim == 2 else tuple(x.shape)
     plan = engine.get_plan(N, P, B, tdtype, dev)
     plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
+    plan.set_option("fused", 1 if fused else 0)
     info = plan.propagate(x, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
     if not on_host:
         return x, info
@@ -132,6 +133,7 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
     x = _to_device(a.reshape(1, n_pol, n), tdtype, dev)    # cast to the compute dtype on the device
     plan = engine.get_plan(n, n_pol, 1, tdtype, dev)
     plan.set_option("chunk_waveforms", 0)
+    plan.set_option("fused", 1)
     args = (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h)
 
     bar = None

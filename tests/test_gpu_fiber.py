@@ -160,6 +160,22 @@ def test_batch_rows_have_their_own_step_sequences(ob):
         assert info.done.all()
 
 
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-13), ("fp32", 2e-6)])
+def test_fused_and_unfused_schedules_agree(ob, precision, tol):
+    """k_col_mid (2R+2W per step, one merged Kerr rotation) vs col_inv + col_fwd (3R+3W)."""
+    g = golden("fiber_beta3_4096")
+    kw = fiber_kwargs(g)
+    rows = np.stack([g["x"], 0.7 * np.roll(g["x"], 100), 1.3 * g["x"][::-1]])
+    for extra in ({}, {"h": 0.37}):
+        k = {**kw, **extra}
+        a, ia = ob.fiber_batch(rows, float(g["dt"]), precision=precision, fused=True, want_log=True, **k)
+        b, ib = ob.fiber_batch(rows, float(g["dt"]), precision=precision, fused=False, want_log=True, **k)
+        assert np.array_equal(ia.steps, ib.steps)
+        assert rel_l2(a, b) <= tol
+        if "h" in extra:
+            assert np.array_equal(ia.h_log, ib.h_log) and np.array_equal(ia.z, ib.z)
+
+
 def test_two_polarisations_share_one_controller(ob):
     g = golden("fiber_2pol_noise_4096")
     kw = fiber_kwargs(g)
