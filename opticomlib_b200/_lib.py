@@ -9,7 +9,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_ssfm_b200.so")
+LIB_PATH = os.environ.get("SSFM_B200_LIB") or os.path.join(HERE, "_ssfm_b200.so")
 
 SSFM_OK, SSFM_ERR_INVALID, SSFM_ERR_CUDA, SSFM_ERR_UNSUPPORTED, SSFM_ERR_NOMEM = 0, -1, -2, -3, -4
 SSFM_C64, SSFM_C128 = 0, 1

@@ -31,9 +31,15 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int ilog2(long long v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
 
 // compile-time geometry ------------------------------------------------------------------------
-constexpr int col_tile(int M) { return M <= 32 ? M : (M <= 128 ? 32 : (M == 256 ? 16 : (M == 512 ? 8 : 4))); }
+#ifndef SSFM_T256
+#define SSFM_T256 16
+#endif
+#ifndef SSFM_G256
+#define SSFM_G256 16
+#endif
+constexpr int col_tile(int M) { return M <= 32 ? M : (M <= 128 ? 32 : (M == 256 ? SSFM_T256 : (M == 512 ? 8 : (M == 1024 ? 4 : 2)))); }
 int col_tile_rt(int M) { return col_tile(M); }
-constexpr int row_group(int M) { return (4096 / M) < (M / 2) ? (4096 / M) : (M / 2); }
+constexpr int row_group(int M) { return M == 256 ? SSFM_G256 : ((4096 / M) < (M / 2) ? (4096 / M) : (M / 2)); }
 
 // twiddle tables, built on the device in double and rounded once to R ---------------------------
 template <typename R>
@@ -60,6 +66,15 @@ __global__ void k_build_pass_table(typename cx_of<R>::type* out, int ns, int rad
     out[i] = mk<R>((R)c, (R)(-s));
 }
 
+template <typename R>
+__global__ void k_build_sincos_table(typename cx_of<R>::type* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // out[i] = (cos, sin)(2 pi i / SC_N)
+    if (i >= SC_N) return;
+    double s, c;
+    sincospi(2.0 * (double)i / (double)SC_N, &s, &c);
+    out[i] = mk<R>((R)c, (R)s);
+}
+
 int pass_table_size(int M) {
     int total = 0;
     for (int ns = 1; ns < M;) {
@@ -75,7 +90,8 @@ int build_pass_tables(void** out, int M, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
     const int total = pass_table_size(M);
     C* d = nullptr;
-    CU_TRY(cudaMalloc(&d, sizeof(C) * (size_t)(total > 0 ? total : 1)));
+    CU_TRY(cudaMalloc(&d, sizeof(C) * (size_t)(total + SC_N)));
+    k_build_sincos_table<R><<<(SC_N + 127) / 128, 128, 0, st>>>(d + total);
     int off = 0;
     for (int ns = 1; ns < M;) {
         const int r = (M / ns >= 16) ? 16 : M / ns;
@@ -104,6 +120,7 @@ struct ssfm_plan_s {
     unsigned int* ticket = nullptr;
     int fused = 1;               // 1: fused column kernel (2R+2W per step) when its barrier fits on the chip
     int num_sms = 0;
+    int debug = 0;
     int n_active = 0;
     double* hlog = nullptr;
     int hlog_cap = 0;
@@ -121,7 +138,7 @@ template <typename R, int M>
 int launch_col_fwd(const Params<R>& p, int nblocks, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
     constexpr int T = col_tile(M);
-    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size + SC_N);
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_fwd<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_col_fwd<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
@@ -132,7 +149,7 @@ template <typename R, int M>
 int launch_col_inv(const Params<R>& p, int nblocks, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
     constexpr int T = col_tile(M);
-    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_inv<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_col_inv<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
@@ -140,26 +157,63 @@ int launch_col_inv(const Params<R>& p, int nblocks, cudaStream_t st) {
     return SSFM_OK;
 }
 template <typename R, int M>
-int launch_col_mid(const Params<R>& p, int nblocks, cudaStream_t st) {
+size_t col_mid_smem() {
     typedef typename cx_of<R>::type C;
     constexpr int T = col_tile(M);
-    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
+    return sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
+}
+template <typename R, int M, int SYNC>
+int launch_col_mid(const Params<R>& p, int nblocks, int cluster, cudaStream_t st) {
+    constexpr int T = col_tile(M);
+    const size_t smem = col_mid_smem<R, M>();
     static bool attr = false;
-    if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k_col_mid<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    if (!attr) {
+        CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (SYNC == SYNC_CLUSTER)
+            CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr = true;
+    }
+    if (SYNC == SYNC_CLUSTER) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)nblocks); cfg.blockDim = dim3(T * (M / 16));
+        cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU_TRY(cudaLaunchKernelEx(&cfg, k_col_mid<R, M, T, SYNC>, p));
+    } else {
+        k_col_mid<R, M, T, SYNC><<<nblocks, T * (M / 16), smem, st>>>(p);
+    }
     ++ssfm_launches;
     return SSFM_OK;
 }
-// resident CTAs of the fused kernel on the whole chip (its per-waveform barrier must fit)
+// How can the fused kernel synchronise the `group` tiles of one waveform on this device?
+//   returns SYNC_CLUSTER if a cluster of `group` CTAs can be scheduled, else SYNC_GLOBAL if `group`
+//   CTAs are resident at once, else -1 (use the unfused schedule).
 template <typename R, int M>
-int col_mid_capacity(int num_sms, int* out) {
-    typedef typename cx_of<R>::type C;
+int col_mid_sync_mode(int num_sms, long long group, int* mode) {
     constexpr int T = col_tile(M);
-    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size);
-    CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = col_mid_smem<R, M>();
+    *mode = -1;
+    if (group <= 16) {
+        CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_CLUSTER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(group * 64)); cfg.blockDim = dim3(T * (M / 16)); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)group; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, k_col_mid<R, M, T, SYNC_CLUSTER>, &cfg);
+        if (e == cudaSuccess && nclusters > 0) { *mode = SYNC_CLUSTER; return SSFM_OK; }
+        (void)cudaGetLastError();
+    }
+    CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_col_mid<R, M, T>, T * (M / 16), smem));
-    *out = per_sm * num_sms;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_col_mid<R, M, T, SYNC_GLOBAL>, T * (M / 16), smem));
+    if (group <= (long long)per_sm * num_sms) *mode = SYNC_GLOBAL;
     return SSFM_OK;
 }
 
@@ -167,7 +221,7 @@ template <typename R, int M>
 int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
     constexpr int G = row_group(M);
-    const size_t smem = sizeof(C) * (size_t)(G * (pad16(M) + 1) + fft_plan<M>::table_size);
+    const size_t smem = sizeof(C) * (size_t)(G * (pad16(M) + 1) + fft_plan<M>::table_size + SC_N);
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_row<R, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_row<R, M, G><<<nblocks, G * (M / 16), smem, st>>>(p);
@@ -180,14 +234,17 @@ int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
 enum ColKind { COL_FWD, COL_INV, COL_MID };
 
 template <typename R>
-int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st) {
+int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st, int sync = SYNC_GLOBAL) {
     const long long rows = (long long)p.batch * p.n_pol;
     switch (p.n1) {
 #define X(M) case M: {                                                             \
-            const int nb = (int)(rows * (p.n2 / col_tile(M)));                     \
-            return kind == COL_FWD ? launch_col_fwd<R, M>(p, nb, st)               \
-                 : kind == COL_INV ? launch_col_inv<R, M>(p, nb, st)               \
-                                   : launch_col_mid<R, M>(p, nb, st); }
+            const int tiles = p.n2 / col_tile(M);                                  \
+            const int nb = (int)(rows * tiles);                                    \
+            if (kind == COL_FWD) return launch_col_fwd<R, M>(p, nb, st);           \
+            if (kind == COL_INV) return launch_col_inv<R, M>(p, nb, st);           \
+            if (sync == SYNC_FIXED) return launch_col_mid<R, M, SYNC_FIXED>(p, nb, 1, st);              \
+            if (sync == SYNC_CLUSTER) return launch_col_mid<R, M, SYNC_CLUSTER>(p, nb, tiles * p.n_pol, st); \
+            return launch_col_mid<R, M, SYNC_GLOBAL>(p, nb, 1, st); }
         SSFM_FOR_M(X)
 #undef X
         default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported column transform size");
@@ -206,9 +263,9 @@ int enqueue_row(const Params<R>& p, cudaStream_t st) {
 }
 
 template <typename R>
-int fused_capacity(int n1, int num_sms, int* out) {
+int fused_sync_mode(int n1, int num_sms, long long group, int* mode) {
     switch (n1) {
-#define X(M) case M: return col_mid_capacity<R, M>(num_sms, out);
+#define X(M) case M: return col_mid_sync_mode<R, M>(num_sms, group, mode);
         SSFM_FOR_M(X)
 #undef X
         default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported column transform size");
@@ -236,11 +293,12 @@ Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed,
     base.adaptive = fixed ? 0 : 1;
     base.has_nl = (g != (R)0) ? 1 : 0;
     base.max_steps = 1 << 30;
+    base.debug = pl->debug;
     base.gamma = g; base.abs_gamma = std::fabs(g); base.phi_max = pm; base.length = L;
     base.att_half = -a_lin / (R)2;
     base.c2 = (R)0.5 * b2;                       // imag(1j/2 * beta_2): exact scaling
     base.c3 = (R)(1.0 / 6.0) * b3;               // imag(1j/6 * beta_3): R(1/6) times beta_3, rounded once
-    base.fval = 1.0 / ((double)pl->n * prm.dt_s);
+    base.wscale = ((1.0 / ((double)pl->n * prm.dt_s)) * 2.0) * 3.141592653589793 * 1e-12;
     base.inv_n = (R)1 / (R)pl->n;
     return base;
 }
@@ -257,14 +315,15 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
     const size_t wf_elems = (size_t)pl->n_pol * (size_t)pl->n;
     const long long budget = max_steps > 0 ? max_steps : (1ll << 40);
     bool use_fused = pl->fused != 0;
-    if (use_fused) {   // the per-waveform barrier of k_col_mid needs all tiles of a waveform resident at once
-        int cap = 0;
-        int rc = fused_capacity<R>(pl->n1, pl->num_sms, &cap);
-        if (rc) return rc;
+    int sync = SYNC_FIXED;                                 // fixed step: no barrier in the fused kernel
+    if (use_fused && !fixed) {                             // adaptive: the tiles of a waveform must synchronise
         const long long group = (long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1));
-        if (group > cap) use_fused = false;
+        int rc = fused_sync_mode<R>(pl->n1, pl->num_sms, group, &sync);
+        if (rc) return rc;
+        if (sync == SYNC_CLUSTER && pl->fused != 3) sync = SYNC_GLOBAL;   // clusters of 16 CTAs schedule poorly (measured
+                                                                          // slower than the global-memory barrier): opt-in only
+        if (sync < 0) use_fused = false;
     }
-
     int ci = 0;
     for (long long b0 = 0; b0 < B; b0 += chunk, ++ci) {
         const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
@@ -319,7 +378,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
                 int rc = SSFM_OK;
                 if (use_fused) {
                     rc = enqueue_row<R>(p, st);
-                    if (!rc) rc = enqueue_col<R>(p, (enq + s + 1 == budget) ? COL_INV : COL_MID, st);
+                    if (!rc) rc = enqueue_col<R>(p, (enq + s + 1 == budget) ? COL_INV : COL_MID, st, sync);
                 } else {
                     rc = enqueue_col<R>(p, COL_FWD, st);
                     if (!rc) rc = enqueue_row<R>(p, st);
@@ -367,11 +426,14 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
     k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, 1, (R)prm.h_km, 0);
     p.ticket = pl->ticket;
     bool use_fused = pl->fused != 0;
-    if (use_fused) {
-        int cap = 0;
-        int rc0 = fused_capacity<R>(pl->n1, pl->num_sms, &cap);
+    int sync = SYNC_FIXED;
+    if (use_fused && prm_in.phi_max_rad >= 0) {            // time the adaptive-mode kernel (same work, plus the barrier)
+        const long long group = (long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1));
+        int rc0 = fused_sync_mode<R>(pl->n1, pl->num_sms, group, &sync);
         if (rc0) return rc0;
-        if ((long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1)) > cap) use_fused = false;
+        if (sync == SYNC_CLUSTER && pl->fused != 3) sync = SYNC_GLOBAL;
+        if (sync < 0) use_fused = false;
+        p.adaptive = 1;                                     // controller follows phi_max / max; length is 1e30
     }
     cudaEvent_t ev[4];
     for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
@@ -391,7 +453,7 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
         CU_TRY(cudaEventRecord(ev[1], st));
         if (!rc) rc = enqueue_row<R>(p, st);
         CU_TRY(cudaEventRecord(ev[2], st));
-        if (!rc) rc = enqueue_col<R>(p, use_fused ? COL_MID : COL_INV, st);
+        if (!rc) rc = enqueue_col<R>(p, use_fused ? COL_MID : COL_INV, st, sync);
         CU_TRY(cudaEventRecord(ev[3], st));
         CU_TRY(cudaEventSynchronize(ev[3]));
         if (r >= 0)
@@ -496,7 +558,8 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     const std::string k(name);
     if (k == "chunk_waveforms") { if (value < 0) return fail(SSFM_ERR_INVALID, "chunk_waveforms < 0"); pl->chunk = value; }
     else if (k == "burst_steps") { if (value < 1 || value > 4096) return fail(SSFM_ERR_INVALID, "burst_steps out of range"); pl->burst = (int)value; }
-    else if (k == "fused") { pl->fused = value ? 1 : 0; }
+    else if (k == "fused") { pl->fused = (int)value; }   // 0 unfused, 1 fused, 3 fused with cluster barrier when possible
+    else if (k == "debug") { pl->debug = (int)value; }
     else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
     return SSFM_OK;
 }

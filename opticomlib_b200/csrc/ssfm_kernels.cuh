@@ -55,11 +55,14 @@ struct Params {
     int adaptive;        // 1: h = phi_max / max(|gamma| |A|^2) after every step
     int has_nl;          // gamma != 0
     int max_steps;       // safety stop
+    int debug;           // bit0: no barrier spin (timing experiments only), bit1: blockIdx instead of tickets
     R gamma, abs_gamma, phi_max, length;
     R att_half;          // -alpha_lin/2            (devices.py:1145)
     R c2;                // imag(1j/2*beta_2)       (devices.py:1145)
     R c3;                // imag(1j/6*beta_3)
-    double fval;         // 1.0/(N*dt): numpy.fft.fftfreq scale (typing.py:1641)
+    double wscale;       // ((1.0/(N*dt))*2*pi)*1e-12: omega grid of typing.py:1641 and devices.py:1144 folded
+                         // into one factor (differs from the three separate roundings by <= 2 ulp of
+                         // float64, i.e. < 1e-12 rad on the largest phase; invisible after the cast to float32)
     R inv_n;
 };
 
@@ -68,8 +71,27 @@ __device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float  add_rn(float a, float b)   { return __fadd_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ void sincos_r(float x, float* s, float* c)    { sincosf(x, s, c); }
-__device__ __forceinline__ void sincos_r(double x, double* s, double* c) { sincos(x, s, c); }
+// sin/cos for the phase rotations.  float: CUDA's sincosf (full range, <= 2 ulp).
+// double: 256-entry table of exp(j 2 pi i/256) in shared memory + a three-part Cody-Waite reduction
+// to |r| <= pi/256 + degree-5/6 Taylor polynomials: 17 FP64 instructions instead of ~40 for
+// sincos(), absolute error < 3e-16 for |x| < 1e7 rad (the linear-operator phase is O(1e3) rad).
+constexpr int SC_N = 256;
+__device__ __forceinline__ void sincos_r(float x, const float2*, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_r(double x, const double2* tab, double* s, double* c) {
+    const double magic = 6755399441055744.0;                       // 1.5 * 2^52
+    const double m = fma(x, 40.74366543152521, magic);             // x * 256/(2 pi), integer part in the low bits
+    const int idx = __double2loint(m) & (SC_N - 1);
+    const double k = m - magic;
+    double r = fma(-k, 0x1.921fb54400000p-6, x);                   // 2 pi/256 = C1 + C2 + C3
+    r = fma(-k, 0x1.0b4611a600000p-40, r);
+    r = fma(-k, 0x1.3198a2e037073p-75, r);
+    const double r2 = r * r;
+    const double sr = fma(r * r2, fma(r2, 8.3333333333333332e-3, -1.6666666666666666e-1), r);
+    const double cr = fma(r2, fma(r2, fma(r2, -1.3888888888888889e-3, 4.1666666666666664e-2), -0.5), 1.0);
+    const double2 e = tab[idx];                                    // (cos, sin) of 2 pi idx/256
+    *c = fma(e.x, cr, -(e.y * sr));
+    *s = fma(e.y, cr, e.x * sr);
+}
 __device__ __forceinline__ float  exp_r(float x)  { return expf(x); }
 __device__ __forceinline__ double exp_r(double x) { return exp(x); }
 // w**3 as numpy.power gives it (correctly rounded cube): exact product in higher precision
@@ -111,29 +133,58 @@ template <typename R> __device__ __forceinline__ R block_max_bits(R v, unsigned 
     return from_bits<R>(red[0]);
 }
 
-// Step-size controller, one thread per waveform per step (devices.py:1173, 1193-1196).
+// Step-size controller (devices.py:1173, 1193-1196) as a pure function of the state before the
+// step and the waveform's max |A|^2 after it; every rounding is one IEEE operation in R.
+template <typename R> struct CtrlNext { R z, h; int done; };
 template <typename R>
-__device__ __forceinline__ void controller_update(const Params<R>& p, int b, R pmax) {
-    Ctrl& c = p.ctrl[b];
-    R z = (R)c.z, h = (R)c.h;
-    z = add_rn(z, h);                                   // z += h_
-    const int s = c.steps;
-    if (p.hlog && s < p.hlog_cap) p.hlog[(size_t)b * p.hlog_cap + s] = (double)h;
+__device__ __forceinline__ CtrlNext<R> controller_next(const Params<R>& p, R z, R h, int steps, R pmax) {
+    CtrlNext<R> n;
+    n.z = add_rn(z, h);                                           // z += h_
     R hn = h;
     if (p.adaptive) hn = p.phi_max / mul_rn(p.abs_gamma, pmax);   // phi_max / max(|gamma| |A|^2)
-    const R rem = p.length - z;
-    hn = (rem < hn) ? rem : hn;                         // python min(h_, length - z)
-    const int done = !(z < p.length) || (s + 1 >= p.max_steps);
-    c.z = (double)z; c.h = (double)hn; c.pmax = 0ull; c.arrived = 0u;
-    c.done = done;
-    if (done) atomicSub(p.active, 1);
-    __threadfence();                                    // publish the new state, then the step count
-    *reinterpret_cast<volatile int*>(&c.steps) = s + 1; // (waiters of k_col_mid spin on it)
+    const R rem = p.length - n.z;
+    n.h = (rem < hn) ? rem : hn;                                  // python min(h_, length - z)
+    n.done = !(n.z < p.length) || (steps + 1 >= p.max_steps);
+    return n;
+}
+// One thread per waveform per step stores the new state.
+template <typename R>
+__device__ __forceinline__ void controller_commit(const Params<R>& p, int b, R h_taken, int steps, const CtrlNext<R>& n) {
+    Ctrl& c = p.ctrl[b];
+    if (p.hlog && steps < p.hlog_cap) p.hlog[(size_t)b * p.hlog_cap + steps] = (double)h_taken;
+    c.z = (double)n.z; c.h = (double)n.h; c.pmax = 0ull; c.arrived = 0u;
+    c.done = n.done;
+    if (n.done) atomicSub(p.active, 1);
+    __threadfence();                                              // publish the new state, then the step count
+    *reinterpret_cast<volatile int*>(&c.steps) = steps + 1;       // (waiters of k_col_mid<SYNC_GLOBAL> spin on it)
+}
+template <typename R>
+__device__ __forceinline__ void controller_update(const Params<R>& p, int b, R pmax) {
+    const Ctrl& c = p.ctrl[b];
+    const R h = (R)c.h;
+    const int s = c.steps;
+    const CtrlNext<R> n = controller_next<R>(p, (R)c.z, h, s, pmax);
+    controller_commit<R>(p, b, h, s, n);
 }
 
-// Two resident CTAs per SM (<= 128 registers) whenever a CTA has at most 256 threads: one CTA's
-// global loads overlap the other's transform.
-__host__ __device__ constexpr int min_ctas(int threads) { return threads <= 256 ? 2 : 1; }
+// Ask for SSFM_THREADS_PER_SM resident threads per SM (512 -> at most 128 registers per thread):
+// several small CTAs per SM so that one CTA's global loads overlap another's transform.
+#ifndef SSFM_THREADS_PER_SM
+#define SSFM_THREADS_PER_SM 512
+#endif
+__host__ __device__ constexpr int min_ctas(int threads) {
+    return threads >= SSFM_THREADS_PER_SM ? 1 : (SSFM_THREADS_PER_SM / threads > 16 ? 16 : SSFM_THREADS_PER_SM / threads);
+}
+
+// cp.async (LDGSTS): global -> shared without staging registers; used to prefetch the Kerr-phase
+// stash of a tile while the inverse column transforms run.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <typename C>
 __device__ __forceinline__ void load_tables(C* dst, const C* __restrict__ src, int count) {
@@ -205,13 +256,15 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_fw
 
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int n2 = tile * T + c;
-    load_tables(tw, p.tw_col, fft_plan<M>::table_size);
+    load_tables(tw, p.tw_col, fft_plan<M>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M>::table_size;            // sincos table rides behind the pass tables
 
     C* rowp = p.field + (size_t)row * p.n;
     R* strow = p.stash + (size_t)row * p.n;
     C v[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = rowp[(size_t)(t + q * (M / 16)) * p.n2 + n2];
+    __syncthreads();                                            // tables (incl. the sincos table) are in place
 
     if (p.has_nl) {
         const R hh = (R)ctl.h / (R)2;                           // h_/2
@@ -220,11 +273,10 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_fw
             const R pw = v[q].x * v[q].x + v[q].y * v[q].y;     // |A|^2
             const R ph = mul_rn(hh, mul_rn(p.gamma, pw));       // (h_/2) * (gamma |A|^2)
             strow[(size_t)(t + q * (M / 16)) * p.n2 + n2] = ph;
-            R s, co; sincos_r(ph, &s, &co);
+            R s, co; sincos_r(ph, sct, &s, &co);
             v[q] = cmul(v[q], mk<R>(co, s));
         }
     }
-    __syncthreads();
     fft_passes<R, M, -1, ColExchange<T> >::run(v, sm + c, tw, t);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -252,7 +304,8 @@ __global__ void __launch_bounds__(G * (M / 16), min_ctas(G * (M / 16))) k_row(Pa
     const Ctrl ctl = p.ctrl[b];
     if (ctl.done) return;                                       // G divides N1: uniform per block
 
-    load_tables(tw, p.tw_row, fft_plan<M>::table_size);
+    load_tables(tw, p.tw_row, fft_plan<M>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M>::table_size;
     C* base = p.field + (size_t)bp * p.n + (size_t)k1 * p.n2;
     C v[16];
 #pragma unroll
@@ -269,11 +322,10 @@ __global__ void __launch_bounds__(G * (M / 16), min_ctas(G * (M / 16))) k_row(Pa
             const int k2 = t + q * (M / 16);
             int k = k1 + p.n1 * k2;                             // transposed-order bin index
             k = (k < half) ? k : k - p.n;                       // fftfreq ordering
-            const double w64 = ((double)k * p.fval * 2.0) * 3.141592653589793 * 1e-12;   // rad/ps
-            const R w = (R)w64;
+            const R w = (R)((double)k * p.wscale);              // rad/ps, = fftfreq*2*pi*1e-12 (see Params::wscale)
             const R dim = add_rn(mul_rn(p.c2, mul_rn(w, w)), mul_rn(p.c3, cube_r(w)));
             const R ph = mul_rn(dim, h);
-            R s, co; sincos_r(ph, &s, &co);
+            R s, co; sincos_r(ph, sct, &s, &co);
             v[q] = cmul(v[q], mk<R>(att * co, att * s));
         }
     }
@@ -292,6 +344,7 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_in
     __shared__ unsigned long long red[32];
     C* sm = reinterpret_cast<C*>(smem_raw);
     C* tw = sm + M * T;
+    R* st_sm = reinterpret_cast<R*>(tw + fft_plan<M>::table_size + SC_N);   // [16][threads] stash prefetch
 
     const int tiles = p.n2 / T;
     const int tile = blockIdx.x % tiles, row = blockIdx.x / tiles;
@@ -300,10 +353,17 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_in
 
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int n2 = tile * T + c;
-    load_tables(tw, p.tw_col, fft_plan<M>::table_size);
+    load_tables(tw, p.tw_col, fft_plan<M>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M>::table_size;            // sincos table rides behind the pass tables
 
-    C* rowp = p.field + (size_t)row * p.n;
-    const R* strow = p.stash + (size_t)row * p.n;
+    C* __restrict__ rowp = p.field + (size_t)row * p.n;
+    const R* __restrict__ strow = p.stash + (size_t)row * p.n;
+    if (p.has_nl) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            cp_async<sizeof(R)>(st_sm + q * (T * (M / 16)) + threadIdx.x, strow + (size_t)(t + q * (M / 16)) * p.n2 + n2);
+        cp_async_commit();
+    }
     C v[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -315,13 +375,14 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_in
 
     R pm = 0;
     bool nan = false;
+    cp_async_wait_all();
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
         C a = v[q];
         a.x *= p.inv_n; a.y *= p.inv_n;                         // numpy ifft scaling (exact: N = 2^n)
         if (p.has_nl) {
-            R s, co; sincos_r(strow[off], &s, &co);
+            R s, co; sincos_r(st_sm[q * (T * (M / 16)) + threadIdx.x], sct, &s, &co);
             a = cmul(a, mk<R>(co, s));
         }
         const R pw = a.x * a.x + a.y * a.y;
@@ -348,45 +409,97 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_in
 
 // ---------------------------------------------------------------------------------------------
 // fused column pass: end of step s and start of step s+1 in one visit of the tile
-//   conj twiddle, inverse column transforms, 1/N, max |A|^2  ->  per-waveform barrier + controller
+//   conj twiddle, inverse column transforms, 1/N, max |A|^2  ->  step-size controller
 //   ->  rotation by the stashed phase of step s PLUS the first Kerr half step of step s+1
 //       (one sincos), stash of the new phase, forward column transforms, twiddle.
 // Field traffic per step drops from 3R+3W to 2R+2W (the ideal of SURVEY.md §8(d)).
 //
-// The barrier spans the tiles of ONE waveform (they need its global max, devices.py:1194).  CTAs
-// take a ticket when they start, and the ticket -- not blockIdx -- selects the tile, so the tiles
-// of a waveform are started in order and the lowest unfinished waveform always has all its tiles
-// resident: no deadlock as long as tiles-per-waveform <= resident CTAs (checked by the host).
+// The controller needs the max |A|^2 over the WHOLE waveform (devices.py:1194) before the next
+// Kerr half step can be applied, i.e. a barrier over the tiles of one waveform in mid-kernel:
+//   SYNC_FIXED   fixed step size: h' does not depend on the field, no barrier at all; every tile
+//                derives the new state locally, tile 0 commits it once all tiles have read the old one.
+//   SYNC_CLUSTER the tiles of a waveform form one thread-block cluster (<= 16 CTAs): maxima are
+//                exchanged through distributed shared memory, one hardware cluster barrier.
+//   SYNC_GLOBAL  any number of tiles: atomics in global memory and a spin wait.  CTAs take a ticket
+//                when they start and the ticket -- not blockIdx -- selects the tile, so the tiles of a
+//                waveform start in order and the lowest unfinished waveform always has all its tiles
+//                resident: no deadlock as long as tiles-per-waveform <= resident CTAs (host check).
 // ---------------------------------------------------------------------------------------------
-template <typename R, int M, int T>
+enum { SYNC_FIXED = 0, SYNC_CLUSTER = 1, SYNC_GLOBAL = 2 };
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_u64(void* local_smem, unsigned rank, unsigned long long v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem);
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(ra), "l"(v) : "memory");
+}
+
+template <typename R, int M, int T, int SYNC>
 __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mid(Params<R> p) {
     typedef typename cx_of<R>::type C;
+    constexpr int NT = T * (M / 16);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
+    __shared__ unsigned long long cl_max[16];
     __shared__ unsigned int s_ticket;
+    __shared__ int s_done, s_steps;
+    __shared__ double s_hnext, s_z;
     C* sm = reinterpret_cast<C*>(smem_raw);
     C* tw = sm + M * T;
+    R* st_sm = reinterpret_cast<R*>(tw + fft_plan<M>::table_size + SC_N);   // [16][threads] stash prefetch
 
+    // Thread 0 takes the ticket (SYNC_GLOBAL), reads the controller state ONCE for the whole CTA and
+    // only then reports "state read" (SYNC_FIXED): no thread of this CTA can see a state committed
+    // by a faster tile of the same waveform.
+    const int tiles = p.n2 / T;
+    const unsigned total = (unsigned)(tiles * p.n_pol);
     if (threadIdx.x == 0) {
-        const unsigned int tk = atomicAdd(p.ticket, 1u);
-        if (tk == gridDim.x - 1) *p.ticket = 0u;             // last CTA to start re-arms the counter
+        unsigned int tk = blockIdx.x;
+        if (SYNC == SYNC_GLOBAL) {
+            tk = atomicAdd(p.ticket, 1u);
+            if (tk == gridDim.x - 1) *p.ticket = 0u;          // last CTA to start re-arms the counter
+        }
         s_ticket = tk;
+        Ctrl* c0 = p.ctrl + (tk / tiles) / p.n_pol;
+        s_done = *reinterpret_cast<volatile int*>(&c0->done);
+        s_steps = *reinterpret_cast<volatile int*>(&c0->steps);
+        s_z = *reinterpret_cast<volatile double*>(&c0->z);
+        s_hnext = *reinterpret_cast<volatile double*>(&c0->h);
+        if (SYNC == SYNC_FIXED) { __threadfence(); atomicAdd(&c0->arrived, 1u); }
     }
     __syncthreads();
     const int blk = (int)s_ticket;
-    const int tiles = p.n2 / T;
     const int tile = blk % tiles, row = blk / tiles;
     const int b = row / p.n_pol;
     Ctrl* ctl = p.ctrl + b;
-    if (ctl->done) return;
-    const int step_before = ctl->steps;
+    const int step_before = s_steps;
+    const R z_before = (R)s_z, h_before = (R)s_hnext;
+    const bool finished = s_done != 0;
+    if (finished) {                                            // uniform over the waveform (and its cluster)
+        if (SYNC == SYNC_FIXED && tile == 0 && (row % p.n_pol) == 0 && threadIdx.x == 0) {
+            while (*reinterpret_cast<volatile unsigned int*>(&ctl->arrived) < total) __nanosleep(32);
+            ctl->arrived = 0u;
+        }
+        return;
+    }
+    __syncthreads();                                           // s_done / s_hnext are reused after the barrier
 
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int n2 = tile * T + c;
-    load_tables(tw, p.tw_col, fft_plan<M>::table_size);
+    load_tables(tw, p.tw_col, fft_plan<M>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M>::table_size;
 
-    C* rowp = p.field + (size_t)row * p.n;
-    R* strow = p.stash + (size_t)row * p.n;
+    C* __restrict__ rowp = p.field + (size_t)row * p.n;
+    R* __restrict__ strow = p.stash + (size_t)row * p.n;
+    if (p.has_nl) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            cp_async<sizeof(R)>(st_sm + q * NT + threadIdx.x, strow + (size_t)(t + q * (M / 16)) * p.n2 + n2);
+        cp_async_commit();
+    }
     C v[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -396,67 +509,92 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mi
     __syncthreads();
     fft_passes<R, M, +1, ColExchange<T> >::run(v, sm + c, tw, t);
 
-    R pm = 0;
-    bool nan = false;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        v[q].x *= p.inv_n; v[q].y *= p.inv_n;                  // numpy ifft scaling (exact: N = 2^n)
-        const R pw = v[q].x * v[q].x + v[q].y * v[q].y;        // the Kerr rotations do not change |A|
-        nan |= (pw != pw);
-        pm = pw > pm ? pw : pm;
-    }
-    if (nan) pm = pw_nan<R>();
-    pm = block_max_bits<R>(pm, red);
+    for (int q = 0; q < 16; ++q) { v[q].x *= p.inv_n; v[q].y *= p.inv_n; }   // numpy ifft scaling (exact: N = 2^n)
 
-    // ---- per-waveform barrier; the last tile to arrive runs the controller ------------------------
-    if (threadIdx.x == 0) {
-        atomicMax(&ctl->pmax, ord_bits(pm));
-        __threadfence();
-        const unsigned total = (unsigned)(tiles * p.n_pol);
-        const unsigned prev = atomicAdd(&ctl->arrived, 1u);
-        if (prev + 1u == total) {
-            __threadfence();
-            const R all = from_bits<R>(atomicMax(&ctl->pmax, 0ull));
-            controller_update<R>(p, b, all);
-        } else {
-            while (*reinterpret_cast<volatile int*>(&ctl->steps) == step_before) __nanosleep(64);
+    CtrlNext<R> nx;
+    if (SYNC == SYNC_FIXED) {
+        nx = controller_next<R>(p, z_before, h_before, step_before, (R)0);
+    } else {
+        R pm = 0;
+        bool nan = false;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const R pw = v[q].x * v[q].x + v[q].y * v[q].y;    // the Kerr rotations do not change |A|
+            nan |= (pw != pw);
+            pm = pw > pm ? pw : pm;
         }
-        __threadfence();
+        if (nan) pm = pw_nan<R>();
+        pm = block_max_bits<R>(pm, red);
+        if (SYNC == SYNC_CLUSTER) {
+            const unsigned rank = cluster_ctarank();
+            if (threadIdx.x < total) st_cluster_u64(&cl_max[rank], threadIdx.x, ord_bits(pm));
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            unsigned long long m = 0ull;
+            for (unsigned i = 0; i < total; ++i) m = cl_max[i] > m ? cl_max[i] : m;
+            nx = controller_next<R>(p, z_before, h_before, step_before, from_bits<R>(m));
+            if (rank == 0 && threadIdx.x == 0) controller_commit<R>(p, b, h_before, step_before, nx);
+        } else {
+            if (threadIdx.x == 0) {
+                atomicMax(&ctl->pmax, ord_bits(pm));
+                __threadfence();
+                const unsigned prev = atomicAdd(&ctl->arrived, 1u);
+                if (prev + 1u == total) {
+                    __threadfence();
+                    const R all = from_bits<R>(atomicMax(&ctl->pmax, 0ull));
+                    const CtrlNext<R> n0 = controller_next<R>(p, z_before, h_before, step_before, all);
+                    controller_commit<R>(p, b, h_before, step_before, n0);
+                    s_done = n0.done; s_hnext = (double)n0.h;
+                } else {
+                    while (*reinterpret_cast<volatile int*>(&ctl->steps) == step_before) __nanosleep(32);
+                    __threadfence();
+                    s_done = *reinterpret_cast<volatile int*>(&ctl->done);
+                    s_hnext = *reinterpret_cast<volatile double*>(&ctl->h);
+                }
+            }
+            __syncthreads();
+            nx.done = s_done; nx.h = (R)s_hnext; nx.z = 0;
+        }
     }
-    __syncthreads();
-    const int done = *reinterpret_cast<volatile int*>(&ctl->done);
-    const R hh = (R)(*reinterpret_cast<volatile double*>(&ctl->h)) / (R)2;    // h_/2 of the NEXT step
+    cp_async_wait_all();
 
-    if (done) {                                                 // last step of this waveform: time domain out
+    if (nx.done) {                                              // last step of this waveform: time domain out
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
             if (p.has_nl) {
-                R s, co; sincos_r(strow[off], &s, &co);
+                R s, co; sincos_r(st_sm[q * NT + threadIdx.x], sct, &s, &co);
                 v[q] = cmul(v[q], mk<R>(co, s));
             }
             rowp[off] = v[q];
         }
-        return;
-    }
-    if (p.has_nl) {
+    } else {
+        if (p.has_nl) {
+            const R hh = nx.h / (R)2;                           // h_/2 of the NEXT step
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
+                const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // first half step of the next step
+                const R tot = st_sm[q * NT + threadIdx.x] + ph; // + second half step of this one
+                strow[off] = ph;
+                R s, co; sincos_r(tot, sct, &s, &co);
+                v[q] = cmul(v[q], mk<R>(co, s));
+            }
+        }
+        fft_passes<R, M, -1, ColExchange<T> >::run(v, sm + c, tw, t);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
-            const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
-            const R ph = mul_rn(hh, mul_rn(p.gamma, pw));       // first half step of the next step
-            const R tot = strow[off] + ph;                      // + second half step of this one
-            strow[off] = ph;
-            R s, co; sincos_r(tot, &s, &co);
-            v[q] = cmul(v[q], mk<R>(co, s));
+            const int k1 = t + q * (M / 16);
+            v[q] = cmul(v[q], fourstep_twiddle<R>(p, n2, k1));
+            rowp[(size_t)k1 * p.n2 + n2] = v[q];
         }
     }
-    fft_passes<R, M, -1, ColExchange<T> >::run(v, sm + c, tw, t);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const int k1 = t + q * (M / 16);
-        v[q] = cmul(v[q], fourstep_twiddle<R>(p, n2, k1));
-        rowp[(size_t)k1 * p.n2 + n2] = v[q];
+    if (SYNC == SYNC_FIXED && tile == 0 && (row % p.n_pol) == 0 && threadIdx.x == 0) {
+        // every tile of the waveform has read the old state by now (or will within microseconds)
+        while (*reinterpret_cast<volatile unsigned int*>(&ctl->arrived) < total) __nanosleep(32);
+        controller_commit<R>(p, b, h_before, step_before, nx);
     }
 }
 
