@@ -106,6 +106,12 @@ SSFM_API int ssfm_time_step_kernels(ssfm_plan_t plan, void* field_dev, const ssf
 SSFM_API int ssfm_fiber_host(ssfm_plan_t plan, const void* field_in_host, void* field_out_host,
                     const ssfm_fiber_params* prm, void* stream);
 
+/* FFT-domain transfer function, in place on field_dev[n_waveforms][n_pol][n_samples]:
+ *   row <- ifft(fft(row) * H),  H = h_dev[n_samples] (plan dtype, numpy bin order k = 0..N-1).
+ * This is the operation of DM (devices.py:1025-1029) and of the apply step of FBG (devices.py:2314-2316);
+ * the zero-phase filters use it internally with H = |H_sos|^2. */
+SSFM_API int ssfm_apply_transfer(ssfm_plan_t plan, void* field_dev, const void* h_dev, void* stream);
+
 /* Zero-phase cascaded-biquad filtering (scipy.signal.sosfiltfilt as called at devices.py:820-823 and
  * 1365-1368): x_dev[n_rows][n_samples] complex128 -> y_dev (may alias x_dev).
  * sos_host[n_sections][6] = b0 b1 b2 a0 a1 a2 (a0 == 1) from scipy.signal.bessel(..., output='sos').

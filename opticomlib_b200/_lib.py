@@ -41,6 +41,7 @@ PROTOTYPES = {
     "ssfm_launch_count": (ctypes.c_int64, []),
     "ssfm_time_step_kernels": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FiberParams),
                                               ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    "ssfm_apply_transfer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "ssfm_fiber_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.POINTER(FiberParams), ctypes.c_void_p]),
     "ssfm_filtfilt_sos": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,

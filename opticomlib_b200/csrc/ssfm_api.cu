@@ -9,6 +9,10 @@
 
 #include "../../include/ssfm_b200.h"
 #include "ssfm_kernels.cuh"
+#include "ssfm_internal.h"
+#include <map>
+#include <mutex>
+#include <tuple>
 
 using namespace ssfm;
 
@@ -115,6 +119,7 @@ struct ssfm_plan_s {
     int log2n = 0, n1 = 0, n2 = 0;
     void *tw_col = nullptr, *tw_row = nullptr, *tw_lo = nullptr, *tw_hi = nullptr;
     void* stash = nullptr;
+    void* xfer = nullptr;        // transfer function table (transposed order), allocated on first use
     Ctrl* ctrl = nullptr;
     int* active = nullptr;       // one counter per chunk
     unsigned int* ticket = nullptr;
@@ -131,6 +136,9 @@ struct ssfm_plan_s {
     bool have_state = false;
     ssfm_fiber_params last{};
 };
+
+static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, int32_t dtype, int32_t device,
+                            bool with_stash);
 
 namespace {
 
@@ -465,9 +473,117 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
     return rc;
 }
 
+
+// ---- transfer functions: y = IFFT(H * FFT(y)) per row, spectrum kept in transposed order ------------
+// |H(e^{jw})|^2 of a biquad cascade, written straight into the transposed layout (bin k1 + N1*k2 at [k1][k2])
+template <typename R>
+__global__ void k_fill_xfer_sos(typename cx_of<R>::type* out, int n, int n1, int n2, ssfm_filt::Sos f) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    const int k1 = pos / n2, k2 = pos % n2;
+    const int k = k1 + n1 * k2;
+    double s, c;
+    sincospi(2.0 * (double)k / (double)n, &s, &c);             // z^-1 = (c, -s), z^-2 = (c2, -s2)
+    const double c2 = c * c - s * s, s2 = 2.0 * s * c;
+    double g = 1.0;
+    for (int i = 0; i < f.n_sections; ++i) {
+        const double* q = f.c[i];
+        const double nr = q[0] + q[1] * c + q[2] * c2, ni = -(q[1] * s + q[2] * s2);
+        const double dr = q[3] + q[4] * c + q[5] * c2, di = -(q[4] * s + q[5] * s2);
+        g *= (nr * nr + ni * ni) / (dr * dr + di * di);
+    }
+    out[pos] = mk<R>((R)g, (R)0);
+}
+// user table H[k] in natural bin order -> transposed layout
+template <typename R>
+__global__ void k_transpose_xfer(typename cx_of<R>::type* out, const typename cx_of<R>::type* in, int n, int n1, int n2) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n) return;
+    out[pos] = in[(pos / n2) + n1 * (pos % n2)];
+}
+
+template <typename R>
+int apply_transfer_t(ssfm_plan_t pl, void* field, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    ssfm_fiber_params prm{};
+    prm.dt_s = 1.0; prm.length_km = 1e30; prm.phi_max_rad = 0.01; prm.h_km = 1.0;   // linear, one "step"
+    bool fixed, single;
+    Params<R> p = base_params<R>(pl, prm, fixed, single);
+    p.field = (C*)field; p.stash = nullptr; p.ctrl = pl->ctrl; p.active = pl->active; p.hlog = nullptr;
+    p.ticket = pl->ticket; p.batch = (int)pl->batch; p.xfer = (const C*)pl->xfer;
+    const int nb = (int)pl->batch;
+    CU_TRY(cudaMemcpyAsync(p.active, &nb, sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)nb, st));
+    k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, 1, (R)1, 0);
+    ++ssfm_launches;
+    int rc = enqueue_col<R>(p, COL_FWD, st);
+    if (!rc) rc = enqueue_row<R>(p, st);
+    if (!rc) rc = enqueue_col<R>(p, COL_INV, st);
+    if (rc) return rc;
+    CU_TRY(cudaGetLastError());
+    pl->have_state = false;
+    return SSFM_OK;
+}
+
+int ensure_xfer(ssfm_plan_t pl) {
+    if (pl->xfer) return SSFM_OK;
+    const size_t csz = pl->dtype == SSFM_C64 ? 8 : 16;
+    CU_TRY(cudaMalloc(&pl->xfer, csz * (size_t)pl->n));
+    return SSFM_OK;
+}
+
+std::mutex g_filter_mu;
+std::map<std::tuple<int, long long, long long>, ssfm_plan_t> g_filter_plans;   // (device, n, rows) -> plan without stash
+
 }  // namespace
 
+int ssfm_internal_zero_phase_circular(int device, long long n, long long rows, const ssfm_filt::Sos& f, void* y_dev,
+                                      cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_filter_mu);
+    const auto key = std::make_tuple(device, n, rows);
+    ssfm_plan_t pl = nullptr;
+    auto it = g_filter_plans.find(key);
+    if (it == g_filter_plans.end()) {
+        if (g_filter_plans.size() >= 8) {                        // plans are small (tables only) but keep the map bounded
+            ssfm_plan_destroy(g_filter_plans.begin()->second);
+            g_filter_plans.erase(g_filter_plans.begin());
+        }
+        int rc = plan_create_impl(&pl, n, 1, rows, SSFM_C128, device, false);
+        if (rc) return rc;
+        g_filter_plans[key] = pl;
+    } else {
+        pl = it->second;
+    }
+    CU_TRY(cudaSetDevice(device));
+    int rc = ensure_xfer(pl);
+    if (rc) return rc;
+    k_fill_xfer_sos<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((double2*)pl->xfer, (int)n, pl->n1, pl->n2, f);
+    ++ssfm_launches;
+    return apply_transfer_t<double>(pl, y_dev, st);
+}
+
 extern "C" {
+
+int ssfm_apply_transfer(ssfm_plan_t pl, void* field, const void* h_dev, void* stream) {
+    if (!pl || !field || !h_dev) return fail(SSFM_ERR_INVALID, "null plan, field or transfer function");
+    CU_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_xfer(pl);
+    if (rc) return rc;
+    const unsigned nb = (unsigned)((pl->n + 255) / 256);
+    if (pl->dtype == SSFM_C64) {
+        k_transpose_xfer<float><<<nb, 256, 0, st>>>((float2*)pl->xfer, (const float2*)h_dev, (int)pl->n, pl->n1, pl->n2);
+        ++ssfm_launches;
+        rc = apply_transfer_t<float>(pl, field, st);
+    } else {
+        k_transpose_xfer<double><<<nb, 256, 0, st>>>((double2*)pl->xfer, (const double2*)h_dev, (int)pl->n, pl->n1, pl->n2);
+        ++ssfm_launches;
+        rc = apply_transfer_t<double>(pl, field, st);
+    }
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(st));
+    return SSFM_OK;
+}
 
 int64_t ssfm_launch_count(void) { return ssfm_launches; }
 
@@ -483,6 +599,13 @@ int ssfm_abi_version(void) { return SSFM_ABI_VERSION; }
 const char* ssfm_last_error(void) { return g_err.c_str(); }
 
 int ssfm_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, int32_t dtype, int32_t device) {
+    return plan_create_impl(out, n, n_pol, batch, dtype, device, true);
+}
+
+}  // extern "C"
+
+static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, int32_t dtype, int32_t device,
+                            bool with_stash) {
     if (!out) return fail(SSFM_ERR_INVALID, "plan pointer is null");
     *out = nullptr;
     if (n_pol != 1 && n_pol != 2) return fail(SSFM_ERR_INVALID, "n_pol must be either 1 or 2");
@@ -503,7 +626,7 @@ int ssfm_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, 
     const size_t rsz = dtype == SSFM_C64 ? 4 : 8, csz = 2 * rsz;
     const size_t elems = (size_t)batch * n_pol * n;
     cudaError_t e;
-    e = cudaMalloc(&pl->stash, elems * rsz);
+    e = with_stash ? cudaMalloc(&pl->stash, elems * rsz) : cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ctrl, sizeof(Ctrl) * (size_t)batch);
     if (e == cudaSuccess) { pl->n_active = (int)batch; e = cudaMalloc((void**)&pl->active, sizeof(int) * (size_t)batch); }
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ticket, sizeof(unsigned int));
@@ -541,10 +664,12 @@ int ssfm_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, 
     return SSFM_OK;
 }
 
+extern "C" {
+
 int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (!pl) return SSFM_OK;
     cudaSetDevice(pl->device);
-    cudaFree(pl->stash); cudaFree(pl->ctrl); cudaFree(pl->active); cudaFree(pl->hlog); cudaFree(pl->ticket);
+    cudaFree(pl->stash); cudaFree(pl->xfer); cudaFree(pl->ctrl); cudaFree(pl->active); cudaFree(pl->hlog); cudaFree(pl->ticket);
     cudaFree(pl->tw_col); cudaFree(pl->tw_row); cudaFree(pl->tw_lo); cudaFree(pl->tw_hi);
     if (pl->active_host) cudaFreeHost(pl->active_host);
     if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
@@ -567,6 +692,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
 int ssfm_propagate(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, int64_t max_steps, int32_t resume,
                    void* stream) {
     if (!pl || !field || !prm) return fail(SSFM_ERR_INVALID, "null plan, field or params");
+    if (!pl->stash) return fail(SSFM_ERR_INVALID, "this plan was created for transfer functions only");
     if (!(prm->dt_s > 0)) return fail(SSFM_ERR_INVALID, "dt_s must be > 0");
     if (max_steps < 0) return fail(SSFM_ERR_INVALID, "max_steps < 0");
     if (resume && !pl->have_state) return fail(SSFM_ERR_INVALID, "resume requested but the plan holds no controller state");

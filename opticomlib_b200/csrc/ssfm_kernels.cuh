@@ -47,6 +47,8 @@ struct Params {
     const C* tw_row;     // pass tables of the N2-point transform
     const C* tw_lo;      // W_N^i,          i < 2^lo_bits
     const C* tw_hi;      // W_N^(i*2^lo_bits)
+    const C* xfer;       // optional transfer function H[k] in transposed order ([k1][k2], bin k1 + N1*k2):
+                         // when set, the row kernel multiplies by it instead of exp(D~ h) (filters, DM)
     int lo_bits;
     int n, n1, n2, log2_n2;
     int n_pol;
@@ -313,7 +315,11 @@ __global__ void __launch_bounds__(G * (M / 16), min_ctas(G * (M / 16))) k_row(Pa
     __syncthreads();
     fft_passes<R, M, -1, RowExchange<M> >::run(v, sm + g * PM, tw, t);
 
-    {   // exp(D~ h): real part -alpha/2*h (attenuation), imaginary part (b2/2 w^2 + b3/6 w^3) h
+    if (p.xfer) {   // arbitrary transfer function (zero-phase filters: |H|^2; DM: exp(j w^2 D/2))
+        const C* __restrict__ hrow = p.xfer + (size_t)k1 * p.n2;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], __ldg(hrow + t + q * (M / 16)));
+    } else {        // exp(D~ h): real part -alpha/2*h (attenuation), imaginary part (b2/2 w^2 + b3/6 w^3) h
         const R h = (R)ctl.h;
         const R att = exp_r(mul_rn(p.att_half, h));
         const int half = p.n >> 1;

@@ -83,6 +83,41 @@ def test_filtfilt_batch_large_rows_vs_oracle_and_scipy(ob, n_samples, rows):
     assert rel_l2(y2, 2.5 * y + dc) <= 1e-9
 
 
+def test_fft_path_and_sequential_path_agree(ob, monkeypatch):
+    """2^16-sample rows take the FFT path (circular |H|^2 + exact end segments); forcing the sequential
+    recursion must give the same samples, including the very first and last ones."""
+    from scipy import signal as sg
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((3, 1 << 16)) + 1j * rng.standard_normal((3, 1 << 16)) + (1.5 - 0.5j)
+    for order, bw in ((4, 7.5e9), (5, 30e9), (3, 12e9), (1, 10e9), (2, 10e9)):
+        sos = bessel_sos(order, bw, 640e9)
+        monkeypatch.delenv("SSFM_FILTFILT_SEQUENTIAL", raising=False)
+        a = ob.filtfilt_batch(x, sos)
+        monkeypatch.setenv("SSFM_FILTFILT_SEQUENTIAL", "1")
+        b = ob.filtfilt_batch(x, sos)
+        monkeypatch.delenv("SSFM_FILTFILT_SEQUENTIAL", raising=False)
+        ref = sg.sosfiltfilt(sos, x, axis=-1)
+        assert rel_l2(b, ref) <= 1e-13
+        assert rel_l2(a, ref) <= 1e-12
+        assert np.abs(a - ref)[:, :2000].max() <= 1e-11 and np.abs(a - ref)[:, -2000:].max() <= 1e-11
+
+
+def test_apply_transfer_is_the_dm_operation(ob):
+    """ssfm_apply_transfer: ifft(fft(x) * H) with H in numpy bin order (reference DM, devices.py:1025-1029)."""
+    import ctypes, torch
+    from opticomlib_b200 import engine, _lib
+    rng = np.random.default_rng(5)
+    n = 1 << 14
+    x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    w = 2 * np.pi * np.fft.fftfreq(n, 1 / 640e9) * 1e-12
+    H = np.exp(1j * w ** 2 * (-21.27 * 30) / 2)
+    plan = engine.get_plan(n, 1, 2, torch.complex128, None)
+    xt = torch.from_numpy(x).cuda(); ht = torch.from_numpy(H).cuda()
+    _lib.check(plan.lib.ssfm_apply_transfer(plan.handle, xt.data_ptr(), ht.data_ptr(), None))
+    ref = np.fft.ifft(np.fft.fft(x, axis=-1) * H, axis=-1)
+    assert rel_l2(xt.cpu().numpy(), ref) <= 1e-13
+
+
 def test_filter_errors_match_reference(ob):
     _set_fs(ob, 16e9)
     with pytest.raises(TypeError, match="optical_signal"):
