@@ -202,7 +202,8 @@ def main():
 
     w = workload(a.workload, a.rows)
     n, rows_total = w["n"], w["rows"]
-    rows = rows_total // world if rows_total >= world else 1           # strong scaling: rows sharded over ranks
+    from opticomlib_b200.scheduler import row_shard
+    rows = max(1, row_shard(rows_total, world, rank).count)            # strong scaling: rows sharded over ranks
     tdtype = torch.complex128 if a.precision == "fp64" else torch.complex64
     csize = 16 if a.precision == "fp64" else 8
 
