@@ -1,9 +1,9 @@
 // In-register / shared-memory Stockham FFT building blocks for sm_100a.
 //
-// Every thread owns 16 complex points of one M-point transform (M = 2^m, 16 <= M <= 2048),
-// always in the "load layout"   v[q] = x[t + q*M/16],  t = thread index inside the transform.
-// A transform is a sequence of radix passes (16, 16, ..., tail radix 2|4|8|16); between two
-// passes the points are exchanged through shared memory.  Natural order in, natural order out,
+// Every thread owns E complex points (E = 16 for complex64, 8 for complex128) of one M-point
+// transform (M = 2^m, 16 <= M <= 2048), always in the "load layout"   v[q] = x[t + q*M/E],
+// t = thread index inside the transform.  A transform is a sequence of radix passes
+// (E, E, ..., tail radix 2|4|8|16); between two passes the points are exchanged through shared memory.  Natural order in, natural order out,
 // and the output is again in the load layout, so a forward transform, a point-wise operator and
 // an inverse transform chain without touching memory (that is what the SSFM row kernel does).
 //
@@ -119,11 +119,22 @@ template <int S, typename C> __device__ __forceinline__ void dft16(C (&a)[16]) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Points per thread.  E = 16 for complex64 (32 data registers); E = 8 for complex128 (32 data
+// registers as well): with 16 complex128 points a thread needs 128 registers, two 256-thread CTAs
+// fill the register file and the SM runs 16 warps -- measured latency-bound.  Eight points per thread
+// cost one more radix pass per transform but allow 24 warps per SM.
+// ---------------------------------------------------------------------------------------------
+#ifndef SSFM_E64
+#define SSFM_E64 16   // measured: 8 points per thread (24 warps/SM) gains 5 % in the column kernel but loses 17 % in the
+#endif                // row kernel (one more pass = more shared-memory wavefronts; the LSU path is the busiest unit)
+template <typename R> struct points_per_thread { static constexpr int value = sizeof(R) == 8 ? SSFM_E64 : 16; };
+
+// ---------------------------------------------------------------------------------------------
 // Pass tables.  For a pass (Ns, R) with Ns > 1 the table holds W_{Ns*R}^{r*jm} at [(r-1)*Ns + jm],
 // r = 1..R-1, jm = 0..Ns-1 (forward sign).  Tables of consecutive passes are concatenated.
 // ---------------------------------------------------------------------------------------------
-template <int M> struct fft_plan {
-    __host__ __device__ static constexpr int radix_at(int ns) { return (M / ns >= 16) ? 16 : (M / ns); }
+template <int M, int E> struct fft_plan {
+    __host__ __device__ static constexpr int radix_at(int ns) { return (M / ns >= E) ? E : (M / ns); }
     __host__ __device__ static constexpr int table_size_from(int ns) {
         return (ns >= M) ? 0 : ((ns > 1 ? (radix_at(ns) - 1) * ns : 0) + table_size_from(ns * radix_at(ns)));
     }
@@ -133,7 +144,7 @@ template <int M> struct fft_plan {
     }
 };
 
-__host__ __device__ constexpr int pad16(int a) { return a + (a >> 4); }
+template <int E> __host__ __device__ constexpr int pad_e(int a) { return a + a / E; }
 
 // Exchange policies -----------------------------------------------------------------------------
 // Column transforms: T transforms interleaved, element i of column c at sm[i*T + c]; the threads of
@@ -143,32 +154,34 @@ template <int T> struct ColExchange {
     __device__ static __forceinline__ int idx(int a) { return a * T; }
     __device__ static __forceinline__ void sync() { __syncthreads(); }
 };
-// Row transforms: one padded private buffer per transform; the threads of one transform are
-// consecutive, so for M <= 512 they share a warp and a warp barrier is enough.
-template <int M> struct RowExchange {
+// Row transforms: one padded private buffer per transform (one pad slot every E points keeps both the
+// scattered writes and the contiguous reads conflict-free); the M/E threads of one transform are
+// consecutive, so when they fit in a warp a warp barrier is enough.
+template <int M, int E> struct RowExchange {
     static constexpr int stride = 1;
-    __device__ static __forceinline__ int idx(int a) { return pad16(a); }
+    static constexpr int size = pad_e<E>(M) + 1;
+    __device__ static __forceinline__ int idx(int a) { return pad_e<E>(a); }
     __device__ static __forceinline__ void sync() {
-        if (M / 16 <= 32) __syncwarp(); else __syncthreads();
+        if (M / E <= 32) __syncwarp(); else __syncthreads();
     }
 };
 
-// One M-point transform on v[16] (load layout).  `sm` points at this transform's exchange buffer
-// (already offset by the column for ColExchange), `tw` at the pass tables in shared memory.
-template <typename R, int M, int S, typename X, int Ns = 1>
+// One M-point transform on v[E] (load layout v[q] = x[t + q*M/E]).  `sm` points at this transform's exchange
+// buffer (already offset by the column for ColExchange), `tw` at the pass tables in shared memory.
+template <typename R, int M, int S, typename X, int E, int Ns = 1>
 struct fft_passes {
     typedef typename cx_of<R>::type C;
-    static constexpr int Rr = fft_plan<M>::radix_at(Ns);
-    static constexpr int NB = 16 / Rr;
-    __device__ static __forceinline__ void run(C (&v)[16], C* sm, const C* tw, int t) {
+    static constexpr int Rr = fft_plan<M, E>::radix_at(Ns);
+    static constexpr int NB = E / Rr;
+    __device__ static __forceinline__ void run(C (&v)[E], C* sm, const C* tw, int t) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const int j = t + i * (M / 16);
+            const int j = t + i * (M / E);
             C a[Rr];
 #pragma unroll
             for (int r = 0; r < Rr; ++r) a[r] = v[i + r * NB];
             if constexpr (Ns > 1) {
-                constexpr int toff = fft_plan<M>::table_offset(Ns);
+                constexpr int toff = fft_plan<M, E>::table_offset(Ns);
                 const C* tp = tw + toff + (j & (Ns - 1));
 #pragma unroll
                 for (int r = 1; r < Rr; ++r) a[r] = twmul<S>(a[r], tp[(r - 1) * Ns]);
@@ -180,22 +193,22 @@ struct fft_passes {
 #pragma unroll
             for (int r = 0; r < Rr; ++r) v[i + r * NB] = a[r];
         }
-        if constexpr (Ns * Rr < M) {  // exchange, then the next pass (only radix-16 passes get here: NB == 1, j == t)
+        if constexpr (Ns * Rr < M) {  // exchange, then the next pass (only full-radix passes get here: NB == 1, j == t)
             const int j0 = (t / Ns) * (Ns * Rr) + (t & (Ns - 1));
             X::sync();  // every reader of the previous exchange is done
 #pragma unroll
             for (int r = 0; r < Rr; ++r) sm[X::idx(j0 + r * Ns)] = v[r];
             X::sync();
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = sm[X::idx(t + q * (M / 16))];
-            fft_passes<R, M, S, X, Ns * Rr>::run(v, sm, tw, t);
+            for (int q = 0; q < E; ++q) v[q] = sm[X::idx(t + q * (M / E))];
+            fft_passes<R, M, S, X, E, Ns * Rr>::run(v, sm, tw, t);
         }
     }
 };
-template <typename R, int M, int S, typename X>
-struct fft_passes<R, M, S, X, M> {
+template <typename R, int M, int S, typename X, int E>
+struct fft_passes<R, M, S, X, E, M> {
     typedef typename cx_of<R>::type C;
-    __device__ static __forceinline__ void run(C (&)[16], C*, const C*, int) {}
+    __device__ static __forceinline__ void run(C (&)[E], C*, const C*, int) {}
 };
 
 }  // namespace ssfm

@@ -35,15 +35,15 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int ilog2(long long v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
 
 // compile-time geometry ------------------------------------------------------------------------
-#ifndef SSFM_T256
-#define SSFM_T256 16
-#endif
-#ifndef SSFM_G256
-#define SSFM_G256 16
-#endif
-constexpr int col_tile(int M) { return M <= 32 ? M : (M <= 128 ? 32 : (M == 256 ? SSFM_T256 : (M == 512 ? 8 : (M == 1024 ? 4 : 2)))); }
-int col_tile_rt(int M) { return col_tile(M); }
-constexpr int row_group(int M) { return M == 256 ? SSFM_G256 : ((4096 / M) < (M / 2) ? (4096 / M) : (M / 2)); }
+// Column tile width T (columns per CTA) and row group G (rows per CTA) for transforms of M points
+// with E points per thread: aim at 256-thread CTAs, keep at least 2 columns (32 B of complex128) per
+// row segment, never more than 32, and never more rows/columns than the matrix has.
+constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+constexpr int col_tile(int M, int E) { return clampi(clampi(256 * E / M, 2, 32), 1, M); }
+constexpr int row_group(int M, int E) { return clampi(256 * E / M, 1, M / 2); }
+template <typename R> constexpr int col_tile_of(int M) { return col_tile(M, points_per_thread<R>::value); }
+template <typename R> constexpr int row_group_of(int M) { return row_group(M, points_per_thread<R>::value); }
+int col_tile_rt(int M, int dtype) { return dtype == SSFM_C64 ? col_tile(M, 16) : col_tile(M, 8); }
 
 // twiddle tables, built on the device in double and rounded once to R ---------------------------
 template <typename R>
@@ -55,6 +55,16 @@ __global__ void k_build_unit_roots(typename cx_of<R>::type* out, int count, long
     double s, c;
     sincospi(2.0 * (double)m / (double)period, &s, &c);
     out[i] = mk<R>((R)c, (R)(-s));
+}
+
+template <typename R>
+__global__ void k_build_fourstep(typename cx_of<R>::type* out, int n, int n2) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;   // out[k1*N2 + n2] = exp(-2 pi j n2 k1 / N)
+    if (pos >= n) return;
+    const long long m = ((long long)(pos / n2) * (pos % n2)) % n;
+    double s, c;
+    sincospi(2.0 * (double)m / (double)n, &s, &c);
+    out[pos] = mk<R>((R)c, (R)(-s));
 }
 
 template <typename R>
@@ -79,10 +89,10 @@ __global__ void k_build_sincos_table(typename cx_of<R>::type* out) {
     out[i] = mk<R>((R)c, (R)s);
 }
 
-int pass_table_size(int M) {
+int pass_table_size(int M, int E) {
     int total = 0;
     for (int ns = 1; ns < M;) {
-        const int r = (M / ns >= 16) ? 16 : M / ns;
+        const int r = (M / ns >= E) ? E : M / ns;
         if (ns > 1) total += (r - 1) * ns;
         ns *= r;
     }
@@ -92,13 +102,14 @@ int pass_table_size(int M) {
 template <typename R>
 int build_pass_tables(void** out, int M, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
-    const int total = pass_table_size(M);
+    constexpr int E = points_per_thread<R>::value;
+    const int total = pass_table_size(M, E);
     C* d = nullptr;
     CU_TRY(cudaMalloc(&d, sizeof(C) * (size_t)(total + SC_N)));
     k_build_sincos_table<R><<<(SC_N + 127) / 128, 128, 0, st>>>(d + total);
     int off = 0;
     for (int ns = 1; ns < M;) {
-        const int r = (M / ns >= 16) ? 16 : M / ns;
+        const int r = (M / ns >= E) ? E : M / ns;
         if (ns > 1) {
             const int cnt = (r - 1) * ns;
             k_build_pass_table<R><<<(cnt + 127) / 128, 128, 0, st>>>(d + off, ns, r);
@@ -117,15 +128,19 @@ struct ssfm_plan_s {
     int device = 0, dtype = 0, n_pol = 1;
     long long n = 0, batch = 0;
     int log2n = 0, n1 = 0, n2 = 0;
-    void *tw_col = nullptr, *tw_row = nullptr, *tw_lo = nullptr, *tw_hi = nullptr;
+    void *tw_col = nullptr, *tw_row = nullptr, *tw_lo = nullptr, *tw_hi = nullptr, *tw_full = nullptr;
     void* stash = nullptr;
     void* xfer = nullptr;        // transfer function table (transposed order), allocated on first use
     Ctrl* ctrl = nullptr;
     int* active = nullptr;       // one counter per chunk
     unsigned int* ticket = nullptr;
+    unsigned long long* slots = nullptr;   // SYNC_LL words, [batch][tiles*P][2]
+    size_t slots_bytes = 0;
     int fused = 1;               // 1: fused column kernel (2R+2W per step) when its barrier fits on the chip
     int num_sms = 0;
     int debug = 0;
+    int use_tw_full = 1;
+    int pipe = 0;                // 1: persistent pipelined fused kernel (k_col_pipe) when a waveform fits on the chip
     int n_active = 0;
     double* hlog = nullptr;
     int hlog_cap = 0;
@@ -145,34 +160,38 @@ namespace {
 template <typename R, int M>
 int launch_col_fwd(const Params<R>& p, int nblocks, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
-    constexpr int T = col_tile(M);
-    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size + SC_N);
+    constexpr int T = col_tile_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M, E>::table_size + SC_N);
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_fwd<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k_col_fwd<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    k_col_fwd<R, M, T><<<nblocks, T * (M / E), smem, st>>>(p);
     ++ssfm_launches;
     return SSFM_OK;
 }
 template <typename R, int M>
 int launch_col_inv(const Params<R>& p, int nblocks, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
-    constexpr int T = col_tile(M);
-    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
+    constexpr int T = col_tile_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
+    const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M, E>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_inv<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k_col_inv<R, M, T><<<nblocks, T * (M / 16), smem, st>>>(p);
+    k_col_inv<R, M, T><<<nblocks, T * (M / E), smem, st>>>(p);
     ++ssfm_launches;
     return SSFM_OK;
 }
 template <typename R, int M>
 size_t col_mid_smem() {
     typedef typename cx_of<R>::type C;
-    constexpr int T = col_tile(M);
-    return sizeof(C) * (size_t)(M * T + fft_plan<M>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
+    constexpr int T = col_tile_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
+    return sizeof(C) * (size_t)(M * T + fft_plan<M, E>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
 }
 template <typename R, int M, int SYNC>
 int launch_col_mid(const Params<R>& p, int nblocks, int cluster, cudaStream_t st) {
-    constexpr int T = col_tile(M);
+    constexpr int T = col_tile_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
     const size_t smem = col_mid_smem<R, M>();
     static bool attr = false;
     if (!attr) {
@@ -183,7 +202,7 @@ int launch_col_mid(const Params<R>& p, int nblocks, int cluster, cudaStream_t st
     }
     if (SYNC == SYNC_CLUSTER) {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)nblocks); cfg.blockDim = dim3(T * (M / 16));
+        cfg.gridDim = dim3((unsigned)nblocks); cfg.blockDim = dim3(T * (M / E));
         cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -191,24 +210,59 @@ int launch_col_mid(const Params<R>& p, int nblocks, int cluster, cudaStream_t st
         cfg.attrs = at; cfg.numAttrs = 1;
         CU_TRY(cudaLaunchKernelEx(&cfg, k_col_mid<R, M, T, SYNC>, p));
     } else {
-        k_col_mid<R, M, T, SYNC><<<nblocks, T * (M / 16), smem, st>>>(p);
+        k_col_mid<R, M, T, SYNC><<<nblocks, T * (M / E), smem, st>>>(p);
     }
     ++ssfm_launches;
     return SSFM_OK;
 }
-// How can the fused kernel synchronise the `group` tiles of one waveform on this device?
-//   returns SYNC_CLUSTER if a cluster of `group` CTAs can be scheduled, else SYNC_GLOBAL if `group`
-//   CTAs are resident at once, else -1 (use the unfused schedule).
 template <typename R, int M>
-int col_mid_sync_mode(int num_sms, long long group, int* mode) {
-    constexpr int T = col_tile(M);
+size_t col_pipe_smem() {
+    typedef typename cx_of<R>::type C;
+    constexpr int T = col_tile_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
+    return sizeof(C) * (size_t)(fft_plan<M, E>::table_size + SC_N + 2 * M * T) + sizeof(R) * (size_t)(2 * M * T);
+}
+// persistent pipelined fused kernel: grid = groups x (tiles of one waveform), every CTA resident.
+// Returns SSFM_ERR_UNSUPPORTED (without setting an error text) when one waveform does not fit on the chip.
+template <typename R, int M, int SYNC>
+int launch_col_pipe(const Params<R>& p, int num_sms, cudaStream_t st) {
+    constexpr int T = col_tile_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
+    const size_t smem = col_pipe_smem<R, M>();
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        if (smem > 227 * 1024) { per_sm = 0; }
+        else {
+            CU_TRY(cudaFuncSetAttribute(k_col_pipe<R, M, T, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int v = 0;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_col_pipe<R, M, T, SYNC>, T * (M / E), smem));
+            per_sm = v;
+        }
+    }
+    const long long total = (long long)p.n_pol * (p.n2 / T);
+    long long groups = (long long)per_sm * num_sms / total;
+    if (groups > p.batch) groups = p.batch;
+    if (groups < 1) return SSFM_ERR_UNSUPPORTED;
+    k_col_pipe<R, M, T, SYNC><<<(unsigned)(groups * total), T * (M / E), smem, st>>>(p);
+    ++ssfm_launches;
+    return SSFM_OK;
+}
+
+// How can the fused kernel synchronise the `group` tiles of one waveform on this device?
+//   want = SYNC_CLUSTER : a cluster of `group` CTAs if it can be scheduled (group <= 16)
+//   want = SYNC_GLOBAL / SYNC_LL : that protocol if `group` CTAs are resident at once
+//   *mode = -1 when nothing fits (use the unfused schedule).
+template <typename R, int M>
+int col_mid_sync_mode(int num_sms, long long group, int want, int* mode) {
+    constexpr int T = col_tile_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
     const size_t smem = col_mid_smem<R, M>();
     *mode = -1;
-    if (group <= 16) {
+    if (want == SYNC_CLUSTER && group <= 16) {
         CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_CLUSTER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(group * 64)); cfg.blockDim = dim3(T * (M / 16)); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3((unsigned)(group * 64)); cfg.blockDim = dim3(T * (M / E)); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)group; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -218,21 +272,28 @@ int col_mid_sync_mode(int num_sms, long long group, int* mode) {
         if (e == cudaSuccess && nclusters > 0) { *mode = SYNC_CLUSTER; return SSFM_OK; }
         (void)cudaGetLastError();
     }
-    CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_col_mid<R, M, T, SYNC_GLOBAL>, T * (M / 16), smem));
-    if (group <= (long long)per_sm * num_sms) *mode = SYNC_GLOBAL;
+    if (want == SYNC_GLOBAL) {
+        CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_col_mid<R, M, T, SYNC_GLOBAL>, T * (M / E), smem));
+        if (group <= (long long)per_sm * num_sms) *mode = SYNC_GLOBAL;
+    } else {
+        CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_col_mid<R, M, T, SYNC_LL>, T * (M / E), smem));
+        if (group <= (long long)per_sm * num_sms) *mode = SYNC_LL;
+    }
     return SSFM_OK;
 }
 
 template <typename R, int M>
 int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
     typedef typename cx_of<R>::type C;
-    constexpr int G = row_group(M);
-    const size_t smem = sizeof(C) * (size_t)(G * (pad16(M) + 1) + fft_plan<M>::table_size + SC_N);
+    constexpr int G = row_group_of<R>(M);
+    constexpr int E = points_per_thread<R>::value;
+    const size_t smem = sizeof(C) * (size_t)(G * RowExchange<M, E>::size + fft_plan<M, E>::table_size + SC_N);
     static bool attr = false;
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_row<R, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    k_row<R, M, G><<<nblocks, G * (M / 16), smem, st>>>(p);
+    k_row<R, M, G><<<nblocks, G * (M / E), smem, st>>>(p);
     ++ssfm_launches;
     return SSFM_OK;
 }
@@ -242,16 +303,23 @@ int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
 enum ColKind { COL_FWD, COL_INV, COL_MID };
 
 template <typename R>
-int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st, int sync = SYNC_GLOBAL) {
+int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st, int sync = SYNC_GLOBAL, bool pipe = false,
+                int num_sms = 0) {
     const long long rows = (long long)p.batch * p.n_pol;
     switch (p.n1) {
 #define X(M) case M: {                                                             \
-            const int tiles = p.n2 / col_tile(M);                                  \
+            const int tiles = p.n2 / col_tile_of<R>(M);                                 \
             const int nb = (int)(rows * tiles);                                    \
             if (kind == COL_FWD) return launch_col_fwd<R, M>(p, nb, st);           \
             if (kind == COL_INV) return launch_col_inv<R, M>(p, nb, st);           \
+            if (pipe && (sync == SYNC_FIXED || sync == SYNC_LL)) {                                      \
+                const int rp = sync == SYNC_FIXED ? launch_col_pipe<R, M, SYNC_FIXED>(p, num_sms, st)   \
+                                                  : launch_col_pipe<R, M, SYNC_LL>(p, num_sms, st);     \
+                if (rp != SSFM_ERR_UNSUPPORTED) return rp;                                              \
+            }                                                                                           \
             if (sync == SYNC_FIXED) return launch_col_mid<R, M, SYNC_FIXED>(p, nb, 1, st);              \
             if (sync == SYNC_CLUSTER) return launch_col_mid<R, M, SYNC_CLUSTER>(p, nb, tiles * p.n_pol, st); \
+            if (sync == SYNC_LL) return launch_col_mid<R, M, SYNC_LL>(p, nb, 1, st);                    \
             return launch_col_mid<R, M, SYNC_GLOBAL>(p, nb, 1, st); }
         SSFM_FOR_M(X)
 #undef X
@@ -263,7 +331,7 @@ template <typename R>
 int enqueue_row(const Params<R>& p, cudaStream_t st) {
     const long long rows = (long long)p.batch * p.n_pol;
     switch (p.n2) {
-#define X(M) case M: return launch_row<R, M>(p, (int)(rows * p.n1 / row_group(M)), st);
+#define X(M) case M: return launch_row<R, M>(p, (int)(rows * p.n1 / row_group_of<R>(M)), st);
         SSFM_FOR_M(X)
 #undef X
         default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported row transform size");
@@ -271,9 +339,9 @@ int enqueue_row(const Params<R>& p, cudaStream_t st) {
 }
 
 template <typename R>
-int fused_sync_mode(int n1, int num_sms, long long group, int* mode) {
+int fused_sync_mode(int n1, int num_sms, long long group, int want, int* mode) {
     switch (n1) {
-#define X(M) case M: return col_mid_sync_mode<R, M>(num_sms, group, mode);
+#define X(M) case M: return col_mid_sync_mode<R, M>(num_sms, group, want, mode);
         SSFM_FOR_M(X)
 #undef X
         default: return fail(SSFM_ERR_UNSUPPORTED, "unsupported column transform size");
@@ -294,6 +362,8 @@ Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed,
     std::memset(&base, 0, sizeof(base));
     base.tw_col = (const C*)pl->tw_col; base.tw_row = (const C*)pl->tw_row;
     base.tw_lo = (const C*)pl->tw_lo;   base.tw_hi = (const C*)pl->tw_hi;
+    base.tw_full = pl->use_tw_full ? (const C*)pl->tw_full : nullptr;
+    base.small_phase = (!fixed && !single && pm <= (R)0.05 && pm >= (R)0) ? 1 : 0;   // |Kerr phase| <= phi_max in adaptive mode
     base.lo_bits = ilog2(pl->n2);
     base.n = (int)pl->n; base.n1 = pl->n1; base.n2 = pl->n2; base.log2_n2 = ilog2(pl->n2);
     base.n_pol = pl->n_pol;
@@ -325,11 +395,12 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
     bool use_fused = pl->fused != 0;
     int sync = SYNC_FIXED;                                 // fixed step: no barrier in the fused kernel
     if (use_fused && !fixed) {                             // adaptive: the tiles of a waveform must synchronise
-        const long long group = (long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1));
-        int rc = fused_sync_mode<R>(pl->n1, pl->num_sms, group, &sync);
+        const long long group = (long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1, pl->dtype));
+        // plan option "fused": 1 = LL words (default), 2 = atomics + spin, 3 = thread-block clusters (16-CTA clusters
+        // schedule poorly: measured slower than either global-memory protocol, so they are opt-in only)
+        const int want = pl->fused == 3 ? SYNC_CLUSTER : (pl->fused == 2 ? SYNC_GLOBAL : SYNC_LL);
+        int rc = fused_sync_mode<R>(pl->n1, pl->num_sms, group, want, &sync);
         if (rc) return rc;
-        if (sync == SYNC_CLUSTER && pl->fused != 3) sync = SYNC_GLOBAL;   // clusters of 16 CTAs schedule poorly (measured
-                                                                          // slower than the global-memory barrier): opt-in only
         if (sync < 0) use_fused = false;
     }
     int ci = 0;
@@ -341,6 +412,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         p.ctrl = pl->ctrl + b0;
         p.active = pl->active + ci;
         p.ticket = pl->ticket;
+        p.slots = pl->slots + (size_t)b0 * pl->n_pol * (size_t)(pl->n2 / col_tile_rt(pl->n1, pl->dtype)) * 2;
         p.hlog = pl->hlog ? pl->hlog + (size_t)b0 * pl->hlog_cap : nullptr;
         p.batch = (int)nb;
 
@@ -348,6 +420,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
             const int nb_i = (int)nb;
             CU_TRY(cudaMemcpyAsync(p.active, &nb_i, sizeof(int), cudaMemcpyHostToDevice, st));
             CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)nb, st));
+            if (ci == 0) CU_TRY(cudaMemsetAsync(pl->slots, 0, pl->slots_bytes, st));     // step tags restart at 1
             if (!fixed && !single) {
                 int per = (int)((wf_elems + 256 * 16 - 1) / (256 * 16));
                 if (per > 64) per = 64;
@@ -386,7 +459,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
                 int rc = SSFM_OK;
                 if (use_fused) {
                     rc = enqueue_row<R>(p, st);
-                    if (!rc) rc = enqueue_col<R>(p, (enq + s + 1 == budget) ? COL_INV : COL_MID, st, sync);
+                    if (!rc) rc = enqueue_col<R>(p, (enq + s + 1 == budget) ? COL_INV : COL_MID, st, sync, pl->pipe != 0, pl->num_sms);
                 } else {
                     rc = enqueue_col<R>(p, COL_FWD, st);
                     if (!rc) rc = enqueue_row<R>(p, st);
@@ -433,13 +506,15 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
     CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)nb, st));
     k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, 1, (R)prm.h_km, 0);
     p.ticket = pl->ticket;
+    p.slots = pl->slots;
+    CU_TRY(cudaMemsetAsync(pl->slots, 0, pl->slots_bytes, st));
     bool use_fused = pl->fused != 0;
     int sync = SYNC_FIXED;
     if (use_fused && prm_in.phi_max_rad >= 0) {            // time the adaptive-mode kernel (same work, plus the barrier)
-        const long long group = (long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1));
-        int rc0 = fused_sync_mode<R>(pl->n1, pl->num_sms, group, &sync);
+        const long long group = (long long)pl->n_pol * (pl->n2 / col_tile_rt(pl->n1, pl->dtype));
+        const int want = pl->fused == 3 ? SYNC_CLUSTER : (pl->fused == 2 ? SYNC_GLOBAL : SYNC_LL);
+        int rc0 = fused_sync_mode<R>(pl->n1, pl->num_sms, group, want, &sync);
         if (rc0) return rc0;
-        if (sync == SYNC_CLUSTER && pl->fused != 3) sync = SYNC_GLOBAL;
         if (sync < 0) use_fused = false;
         p.adaptive = 1;                                     // controller follows phi_max / max; length is 1e30
     }
@@ -461,7 +536,7 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
         CU_TRY(cudaEventRecord(ev[1], st));
         if (!rc) rc = enqueue_row<R>(p, st);
         CU_TRY(cudaEventRecord(ev[2], st));
-        if (!rc) rc = enqueue_col<R>(p, use_fused ? COL_MID : COL_INV, st, sync);
+        if (!rc) rc = enqueue_col<R>(p, use_fused ? COL_MID : COL_INV, st, sync, pl->pipe != 0, pl->num_sms);
         CU_TRY(cudaEventRecord(ev[3], st));
         CU_TRY(cudaEventSynchronize(ev[3]));
         if (r >= 0)
@@ -629,6 +704,9 @@ static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t 
     e = with_stash ? cudaMalloc(&pl->stash, elems * rsz) : cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ctrl, sizeof(Ctrl) * (size_t)batch);
     if (e == cudaSuccess) { pl->n_active = (int)batch; e = cudaMalloc((void**)&pl->active, sizeof(int) * (size_t)batch); }
+    pl->slots_bytes = sizeof(unsigned long long) * 2 * (size_t)batch * n_pol * (size_t)(pl->n2 / col_tile_rt(pl->n1, pl->dtype));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->slots, pl->slots_bytes);
+    if (e == cudaSuccess) e = cudaMemset(pl->slots, 0, pl->slots_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ticket, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(pl->ticket, 0, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -657,6 +735,12 @@ static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t 
         rc = build_pass_tables<double>(&pl->tw_col, pl->n1, 0);
         if (!rc) rc = build_pass_tables<double>(&pl->tw_row, pl->n2, 0);
     }
+    if (!rc && n <= (1ll << 20)) {   // full four-step table W_N^{n2*k1} (16 MiB of complex128 at N = 2^20; it lives in L2)
+        cudaError_t ef = cudaMalloc(&pl->tw_full, csz * (size_t)n);
+        if (ef != cudaSuccess) { (void)cudaGetLastError(); pl->tw_full = nullptr; }
+        else if (dtype == SSFM_C64) k_build_fourstep<float><<<(unsigned)((n + 255) / 256), 256>>>((float2*)pl->tw_full, (int)n, pl->n2);
+        else k_build_fourstep<double><<<(unsigned)((n + 255) / 256), 256>>>((double2*)pl->tw_full, (int)n, pl->n2);
+    }
     if (rc) { ssfm_plan_destroy(pl); return rc; }
     cudaError_t es = cudaDeviceSynchronize();
     if (es != cudaSuccess) { ssfm_plan_destroy(pl); return fail(SSFM_ERR_CUDA, std::string("table build: ") + cudaGetErrorString(es)); }
@@ -669,8 +753,8 @@ extern "C" {
 int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (!pl) return SSFM_OK;
     cudaSetDevice(pl->device);
-    cudaFree(pl->stash); cudaFree(pl->xfer); cudaFree(pl->ctrl); cudaFree(pl->active); cudaFree(pl->hlog); cudaFree(pl->ticket);
-    cudaFree(pl->tw_col); cudaFree(pl->tw_row); cudaFree(pl->tw_lo); cudaFree(pl->tw_hi);
+    cudaFree(pl->stash); cudaFree(pl->xfer); cudaFree(pl->ctrl); cudaFree(pl->active); cudaFree(pl->hlog); cudaFree(pl->ticket); cudaFree(pl->slots);
+    cudaFree(pl->tw_col); cudaFree(pl->tw_row); cudaFree(pl->tw_lo); cudaFree(pl->tw_hi); cudaFree(pl->tw_full);
     if (pl->active_host) cudaFreeHost(pl->active_host);
     if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
     if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
@@ -683,8 +767,10 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     const std::string k(name);
     if (k == "chunk_waveforms") { if (value < 0) return fail(SSFM_ERR_INVALID, "chunk_waveforms < 0"); pl->chunk = value; }
     else if (k == "burst_steps") { if (value < 1 || value > 4096) return fail(SSFM_ERR_INVALID, "burst_steps out of range"); pl->burst = (int)value; }
-    else if (k == "fused") { pl->fused = (int)value; }   // 0 unfused, 1 fused, 3 fused with cluster barrier when possible
+    else if (k == "fused") { pl->fused = (int)value; }   // 0 unfused, 1 fused (LL barrier), 2 fused (atomic barrier), 3 fused (cluster barrier when possible)
     else if (k == "debug") { pl->debug = (int)value; }
+    else if (k == "pipe") { pl->pipe = value ? 1 : 0; }
+    else if (k == "tw_full") { pl->use_tw_full = value ? 1 : 0; }
     else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
     return SSFM_OK;
 }

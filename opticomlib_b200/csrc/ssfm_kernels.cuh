@@ -18,6 +18,7 @@
 // Memory traffic per sample and step: 3 field reads + 3 field writes + 1 stash write + 1 stash read.
 #pragma once
 #include "fft_core.cuh"
+#include <type_traits>
 
 namespace ssfm {
 
@@ -42,11 +43,15 @@ struct Params {
     Ctrl* ctrl;          // [B]
     int* active;         // number of waveforms with done == 0
     unsigned int* ticket;// start-order ticket counter of the fused column kernel
+    unsigned long long* slots;   // [B][tiles*P][2] self-validating max words of SYNC_LL
     double* hlog;        // [B][hlog_cap] step sizes actually taken (may be null)
     const C* tw_col;     // pass tables of the N1-point transform
     const C* tw_row;     // pass tables of the N2-point transform
     const C* tw_lo;      // W_N^i,          i < 2^lo_bits
     const C* tw_hi;      // W_N^(i*2^lo_bits)
+    const C* tw_full;    // optional full four-step table W_N^{n2*k1} at [k1][n2] (N <= 2^20): one coalesced L2 load
+                         // instead of two table look-ups and a complex product
+    int small_phase;     // 1: every Kerr phase is <= 0.05 rad (adaptive mode with phi_max <= 0.05): short Taylor sincos
     const C* xfer;       // optional transfer function H[k] in transposed order ([k1][k2], bin k1 + N1*k2):
                          // when set, the row kernel multiplies by it instead of exp(D~ h) (filters, DM)
     int lo_bits;
@@ -93,6 +98,19 @@ __device__ __forceinline__ void sincos_r(double x, const double2* tab, double* s
     const double2 e = tab[idx];                                    // (cos, sin) of 2 pi idx/256
     *c = fma(e.x, cr, -(e.y * sr));
     *s = fma(e.y, cr, e.x * sr);
+}
+// |x| <= 0.05 rad: Taylor series to x^7 / x^8 (truncation < 1e-17), 9 instructions, no table
+template <typename R> __device__ __forceinline__ void sincos_small(R x, R* s, R* c) {
+    const R x2 = x * x;
+    *s = x + x * x2 * ((R)-1.6666666666666666e-1 + x2 * ((R)8.3333333333333332e-3 + x2 * (R)-1.9841269841269841e-4));
+    *c = (R)1 + x2 * ((R)-0.5 + x2 * ((R)4.1666666666666664e-2 + x2 * ((R)-1.3888888888888889e-3 + x2 * (R)2.4801587301587302e-5)));
+}
+// compile-time selection; the kernels unswitch their unrolled Kerr loops on Params::small_phase with
+//   auto body = [&](auto small) { ... kerr_sincos<decltype(small)::value>(...) ... };
+//   if (p.small_phase) body(std::true_type{}); else body(std::false_type{});
+template <bool SMALL, typename R, typename C>
+__device__ __forceinline__ void kerr_sincos(R x, const C* tab, R* s, R* c) {
+    if constexpr (SMALL) sincos_small<R>(x, s, c); else sincos_r(x, tab, s, c);
 }
 __device__ __forceinline__ float  exp_r(float x)  { return expf(x); }
 __device__ __forceinline__ double exp_r(double x) { return exp(x); }
@@ -172,10 +190,16 @@ __device__ __forceinline__ void controller_update(const Params<R>& p, int b, R p
 // Ask for SSFM_THREADS_PER_SM resident threads per SM (512 -> at most 128 registers per thread):
 // several small CTAs per SM so that one CTA's global loads overlap another's transform.
 #ifndef SSFM_THREADS_PER_SM
-#define SSFM_THREADS_PER_SM 512
+#define SSFM_THREADS_PER_SM (SSFM_E64 == 16 ? 512 : 768)
 #endif
-__host__ __device__ constexpr int min_ctas(int threads) {
-    return threads >= SSFM_THREADS_PER_SM ? 1 : (SSFM_THREADS_PER_SM / threads > 16 ? 16 : SSFM_THREADS_PER_SM / threads);
+#ifndef SSFM_THREADS_PER_SM_F32
+#define SSFM_THREADS_PER_SM_F32 768
+#endif
+__host__ __device__ constexpr int min_ctas_for(int threads, int per_sm) {
+    return threads >= per_sm ? 1 : (per_sm / threads > 16 ? 16 : per_sm / threads);
+}
+template <typename R> __host__ __device__ constexpr int min_ctas(int threads) {
+    return min_ctas_for(threads, sizeof(R) == 4 ? SSFM_THREADS_PER_SM_F32 : SSFM_THREADS_PER_SM);
 }
 
 // cp.async (LDGSTS): global -> shared without staging registers; used to prefetch the Kerr-phase
@@ -193,12 +217,27 @@ __device__ __forceinline__ void load_tables(C* dst, const C* __restrict__ src, i
     for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
 }
 
-template <typename R>
-__device__ __forceinline__ typename cx_of<R>::type fourstep_twiddle(const Params<R>& p, int n2, int k1) {
-    const unsigned idx = (unsigned)n2 * (unsigned)k1;   // < N
-    typename cx_of<R>::type lo = __ldg(p.tw_lo + (idx & ((1u << p.lo_bits) - 1u)));
-    typename cx_of<R>::type hi = __ldg(p.tw_hi + (idx >> p.lo_bits));
-    return cmul(lo, hi);
+// v[q] *= W_N^{n2*k1} (or its conjugate), k1 = t + q*M/E.  The table choice is made ONCE outside the
+// unrolled loop (a per-element branch doubles the code of every iteration and costs ~10 %).
+template <bool CONJ, typename R, int E, int M>
+__device__ __forceinline__ void apply_fourstep(const Params<R>& p, typename cx_of<R>::type (&v)[E], int n2, int t) {
+    typedef typename cx_of<R>::type C;
+    if (p.tw_full) {                                     // full table [k1][n2]: one coalesced L2 load per point
+        const C* __restrict__ base = p.tw_full + (size_t)t * p.n2 + n2;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const C w = __ldg(base + (size_t)q * (M / E) * p.n2);
+            v[q] = CONJ ? cmulc(v[q], w) : cmul(v[q], w);
+        }
+    } else {                                             // two sqrt(N) tables: W_N^lo * W_N^(hi*2^lo_bits)
+        const unsigned mask = (1u << p.lo_bits) - 1u;
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const unsigned idx = (unsigned)n2 * (unsigned)(t + q * (M / E));   // < N
+            const C w = cmul(__ldg(p.tw_lo + (idx & mask)), __ldg(p.tw_hi + (idx >> p.lo_bits)));
+            v[q] = CONJ ? cmulc(v[q], w) : cmul(v[q], w);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -244,8 +283,9 @@ __global__ void k_ctrl_init(Params<R> p, int fixed, R h_fixed, int single_step) 
 // column pass, forward
 // ---------------------------------------------------------------------------------------------
 template <typename R, int M, int T>
-__global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_fwd(Params<R> p) {
+__global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_ctas<R>(T * (M / points_per_thread<R>::value))) k_col_fwd(Params<R> p) {
     typedef typename cx_of<R>::type C;
+    constexpr int E = points_per_thread<R>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* sm = reinterpret_cast<C*>(smem_raw);                   // [M][T] exchange tile
     C* tw = sm + M * T;                                       // pass tables
@@ -258,137 +298,137 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_fw
 
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int n2 = tile * T + c;
-    load_tables(tw, p.tw_col, fft_plan<M>::table_size + SC_N);
-    const C* sct = tw + fft_plan<M>::table_size;            // sincos table rides behind the pass tables
+    load_tables(tw, p.tw_col, fft_plan<M, E>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M, E>::table_size;            // sincos table rides behind the pass tables
 
     C* rowp = p.field + (size_t)row * p.n;
     R* strow = p.stash + (size_t)row * p.n;
-    C v[16];
+    C v[E];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = rowp[(size_t)(t + q * (M / 16)) * p.n2 + n2];
+    for (int q = 0; q < E; ++q) v[q] = rowp[(size_t)(t + q * (M / E)) * p.n2 + n2];
     __syncthreads();                                            // tables (incl. the sincos table) are in place
 
     if (p.has_nl) {
         const R hh = (R)ctl.h / (R)2;                           // h_/2
+        auto kerr = [&](auto small) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const R pw = v[q].x * v[q].x + v[q].y * v[q].y;     // |A|^2
-            const R ph = mul_rn(hh, mul_rn(p.gamma, pw));       // (h_/2) * (gamma |A|^2)
-            strow[(size_t)(t + q * (M / 16)) * p.n2 + n2] = ph;
-            R s, co; sincos_r(ph, sct, &s, &co);
-            v[q] = cmul(v[q], mk<R>(co, s));
-        }
+            for (int q = 0; q < E; ++q) {
+                const R pw = v[q].x * v[q].x + v[q].y * v[q].y; // |A|^2
+                const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // (h_/2) * (gamma |A|^2)
+                strow[(size_t)(t + q * (M / E)) * p.n2 + n2] = ph;
+                R s, co; kerr_sincos<decltype(small)::value>(ph, sct, &s, &co);
+                v[q] = cmul(v[q], mk<R>(co, s));
+            }
+        };
+        if (sizeof(R) == 8 && p.small_phase) kerr(std::true_type{}); else kerr(std::false_type{});   // fp32: sincosf is cheap
     }
-    fft_passes<R, M, -1, ColExchange<T> >::run(v, sm + c, tw, t);
+    fft_passes<R, M, -1, ColExchange<T>, E>::run(v, sm + c, tw, t);
+    apply_fourstep<false, R, E, M>(p, v, n2, t);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const int k1 = t + q * (M / 16);
-        v[q] = cmul(v[q], fourstep_twiddle<R>(p, n2, k1));
-        rowp[(size_t)k1 * p.n2 + n2] = v[q];
-    }
+    for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
 }
 
 // ---------------------------------------------------------------------------------------------
 // row pass: forward transform, linear operator, inverse transform
 // ---------------------------------------------------------------------------------------------
 template <typename R, int M, int G>
-__global__ void __launch_bounds__(G * (M / 16), min_ctas(G * (M / 16))) k_row(Params<R> p) {
+__global__ void __launch_bounds__(G * (M / points_per_thread<R>::value), min_ctas<R>(G * (M / points_per_thread<R>::value))) k_row(Params<R> p) {
     typedef typename cx_of<R>::type C;
+    constexpr int E = points_per_thread<R>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int PM = pad16(M) + 1;
+    constexpr int PM = RowExchange<M, E>::size;
     C* sm = reinterpret_cast<C*>(smem_raw);                   // [G][PM] private exchange buffers
     C* tw = sm + G * PM;
 
-    const int g = threadIdx.x / (M / 16), t = threadIdx.x % (M / 16);
+    const int g = threadIdx.x / (M / E), t = threadIdx.x % (M / E);
     const long long grow = (long long)blockIdx.x * G + g;       // global row index over [B*P][N1]
     const int bp = (int)(grow / p.n1), k1 = (int)(grow % p.n1);
     const int b = bp / p.n_pol;
     const Ctrl ctl = p.ctrl[b];
     if (ctl.done) return;                                       // G divides N1: uniform per block
 
-    load_tables(tw, p.tw_row, fft_plan<M>::table_size + SC_N);
-    const C* sct = tw + fft_plan<M>::table_size;
+    load_tables(tw, p.tw_row, fft_plan<M, E>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M, E>::table_size;
     C* base = p.field + (size_t)bp * p.n + (size_t)k1 * p.n2;
-    C v[16];
+    C v[E];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = base[t + q * (M / 16)];
+    for (int q = 0; q < E; ++q) v[q] = base[t + q * (M / E)];
     __syncthreads();
-    fft_passes<R, M, -1, RowExchange<M> >::run(v, sm + g * PM, tw, t);
+    fft_passes<R, M, -1, RowExchange<M, E>, E>::run(v, sm + g * PM, tw, t);
 
     if (p.xfer) {   // arbitrary transfer function (zero-phase filters: |H|^2; DM: exp(j w^2 D/2))
         const C* __restrict__ hrow = p.xfer + (size_t)k1 * p.n2;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], __ldg(hrow + t + q * (M / 16)));
+        for (int q = 0; q < E; ++q) v[q] = cmul(v[q], __ldg(hrow + t + q * (M / E)));
     } else {        // exp(D~ h): real part -alpha/2*h (attenuation), imaginary part (b2/2 w^2 + b3/6 w^3) h
-        const R h = (R)ctl.h;
-        const R att = exp_r(mul_rn(p.att_half, h));
-        const int half = p.n >> 1;
+        const R h = (R)ctl.h;                                   // (the attenuation exp(-alpha/2 h) of D~ is a per-step
+        const int half = p.n >> 1;                              //  scalar: it is folded into the 1/N of the column pass)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int k2 = t + q * (M / 16);
+        for (int q = 0; q < E; ++q) {
+            const int k2 = t + q * (M / E);
             int k = k1 + p.n1 * k2;                             // transposed-order bin index
             k = (k < half) ? k : k - p.n;                       // fftfreq ordering
             const R w = (R)((double)k * p.wscale);              // rad/ps, = fftfreq*2*pi*1e-12 (see Params::wscale)
             const R dim = add_rn(mul_rn(p.c2, mul_rn(w, w)), mul_rn(p.c3, cube_r(w)));
             const R ph = mul_rn(dim, h);
             R s, co; sincos_r(ph, sct, &s, &co);
-            v[q] = cmul(v[q], mk<R>(att * co, att * s));
+            v[q] = cmul(v[q], mk<R>(co, s));
         }
     }
-    fft_passes<R, M, +1, RowExchange<M> >::run(v, sm + g * PM, tw, t);
+    fft_passes<R, M, +1, RowExchange<M, E>, E>::run(v, sm + g * PM, tw, t);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) base[t + q * (M / 16)] = v[q];
+    for (int q = 0; q < E; ++q) base[t + q * (M / E)] = v[q];
 }
 
 // ---------------------------------------------------------------------------------------------
 // column pass, inverse, second Kerr half step, power max, controller
 // ---------------------------------------------------------------------------------------------
 template <typename R, int M, int T>
-__global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_inv(Params<R> p) {
+__global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_ctas<R>(T * (M / points_per_thread<R>::value))) k_col_inv(Params<R> p) {
     typedef typename cx_of<R>::type C;
+    constexpr int E = points_per_thread<R>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
     C* sm = reinterpret_cast<C*>(smem_raw);
     C* tw = sm + M * T;
-    R* st_sm = reinterpret_cast<R*>(tw + fft_plan<M>::table_size + SC_N);   // [16][threads] stash prefetch
+    R* st_sm = reinterpret_cast<R*>(tw + fft_plan<M, E>::table_size + SC_N);   // [E][threads] stash prefetch
 
     const int tiles = p.n2 / T;
     const int tile = blockIdx.x % tiles, row = blockIdx.x / tiles;
     const int b = row / p.n_pol;
     if (p.ctrl[b].done) return;
+    const R sc = p.inv_n * exp_r(mul_rn(p.att_half, (R)p.ctrl[b].h));   // 1/N and exp(-alpha/2 h) (real part of D~ h)
 
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int n2 = tile * T + c;
-    load_tables(tw, p.tw_col, fft_plan<M>::table_size + SC_N);
-    const C* sct = tw + fft_plan<M>::table_size;            // sincos table rides behind the pass tables
+    load_tables(tw, p.tw_col, fft_plan<M, E>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M, E>::table_size;            // sincos table rides behind the pass tables
 
     C* __restrict__ rowp = p.field + (size_t)row * p.n;
     const R* __restrict__ strow = p.stash + (size_t)row * p.n;
     if (p.has_nl) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-            cp_async<sizeof(R)>(st_sm + q * (T * (M / 16)) + threadIdx.x, strow + (size_t)(t + q * (M / 16)) * p.n2 + n2);
+        for (int q = 0; q < E; ++q)
+            cp_async<sizeof(R)>(st_sm + q * (T * (M / E)) + threadIdx.x, strow + (size_t)(t + q * (M / E)) * p.n2 + n2);
         cp_async_commit();
     }
-    C v[16];
+    C v[E];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const int k1 = t + q * (M / 16);
-        v[q] = cmulc(rowp[(size_t)k1 * p.n2 + n2], fourstep_twiddle<R>(p, n2, k1));
-    }
+    for (int q = 0; q < E; ++q) v[q] = rowp[(size_t)(t + q * (M / E)) * p.n2 + n2];
+    apply_fourstep<true, R, E, M>(p, v, n2, t);
     __syncthreads();
-    fft_passes<R, M, +1, ColExchange<T> >::run(v, sm + c, tw, t);
+    fft_passes<R, M, +1, ColExchange<T>, E>::run(v, sm + c, tw, t);
 
     R pm = 0;
     bool nan = false;
     cp_async_wait_all();
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
+    for (int q = 0; q < E; ++q) {
+        const size_t off = (size_t)(t + q * (M / E)) * p.n2 + n2;
         C a = v[q];
-        a.x *= p.inv_n; a.y *= p.inv_n;                         // numpy ifft scaling (exact: N = 2^n)
+        a.x *= sc; a.y *= sc;                                   // numpy ifft scaling (exact: N = 2^n) x attenuation of the step
         if (p.has_nl) {
-            R s, co; sincos_r(st_sm[q * (T * (M / 16)) + threadIdx.x], sct, &s, &co);
+            R s, co; sincos_r(st_sm[q * (T * (M / E)) + threadIdx.x], sct, &s, &co);
             a = cmul(a, mk<R>(co, s));
         }
         const R pw = a.x * a.x + a.y * a.y;
@@ -426,12 +466,18 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_in
 //                derives the new state locally, tile 0 commits it once all tiles have read the old one.
 //   SYNC_CLUSTER the tiles of a waveform form one thread-block cluster (<= 16 CTAs): maxima are
 //                exchanged through distributed shared memory, one hardware cluster barrier.
+//   SYNC_LL      (default) any number of tiles: every tile publishes its maximum as self-validating
+//                64-bit words {32 bits of the value, step tag} (the NCCL "LL" idea: the flag travels with the
+//                data, so no fence and no atomic is needed), every tile polls the words of its waveform and
+//                runs the controller itself.  One store + one polling round trip instead of
+//                atomicMax / fence / atomicAdd / spin / fence / reload.
 //   SYNC_GLOBAL  any number of tiles: atomics in global memory and a spin wait.  CTAs take a ticket
 //                when they start and the ticket -- not blockIdx -- selects the tile, so the tiles of a
 //                waveform start in order and the lowest unfinished waveform always has all its tiles
 //                resident: no deadlock as long as tiles-per-waveform <= resident CTAs (host check).
+//                (SYNC_LL uses the same tickets.)
 // ---------------------------------------------------------------------------------------------
-enum { SYNC_FIXED = 0, SYNC_CLUSTER = 1, SYNC_GLOBAL = 2 };
+enum { SYNC_FIXED = 0, SYNC_CLUSTER = 1, SYNC_GLOBAL = 2, SYNC_LL = 3 };
 
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -444,9 +490,10 @@ __device__ __forceinline__ void st_cluster_u64(void* local_smem, unsigned rank, 
 }
 
 template <typename R, int M, int T, int SYNC>
-__global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mid(Params<R> p) {
+__global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_ctas<R>(T * (M / points_per_thread<R>::value))) k_col_mid(Params<R> p) {
     typedef typename cx_of<R>::type C;
-    constexpr int NT = T * (M / 16);
+    constexpr int E = points_per_thread<R>::value;
+    constexpr int NT = T * (M / E);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
     __shared__ unsigned long long cl_max[16];
@@ -455,68 +502,69 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mi
     __shared__ double s_hnext, s_z;
     C* sm = reinterpret_cast<C*>(smem_raw);
     C* tw = sm + M * T;
-    R* st_sm = reinterpret_cast<R*>(tw + fft_plan<M>::table_size + SC_N);   // [16][threads] stash prefetch
+    R* st_sm = reinterpret_cast<R*>(tw + fft_plan<M, E>::table_size + SC_N);   // [E][threads] stash prefetch
 
-    // Thread 0 takes the ticket (SYNC_GLOBAL), reads the controller state ONCE for the whole CTA and
-    // only then reports "state read" (SYNC_FIXED): no thread of this CTA can see a state committed
-    // by a faster tile of the same waveform.
+    // Thread 0 takes the ticket (SYNC_GLOBAL / SYNC_LL) and reads the controller state ONCE for the whole
+    // CTA (only then does it report "state read" in SYNC_FIXED), so no thread can see a state committed by
+    // a faster tile of the same waveform.  The state loads overlap the tile loads issued below; the
+    // values are handed over at the barrier in front of the transforms.
+    constexpr bool kTicket = (SYNC == SYNC_GLOBAL || SYNC == SYNC_LL);
     const int tiles = p.n2 / T;
     const unsigned total = (unsigned)(tiles * p.n_pol);
-    if (threadIdx.x == 0) {
-        unsigned int tk = blockIdx.x;
-        if (SYNC == SYNC_GLOBAL) {
-            tk = atomicAdd(p.ticket, 1u);
+    int blk = blockIdx.x;
+    if (kTicket) {
+        if (threadIdx.x == 0) {
+            const unsigned int tk = atomicAdd(p.ticket, 1u);
             if (tk == gridDim.x - 1) *p.ticket = 0u;          // last CTA to start re-arms the counter
+            s_ticket = tk;
         }
-        s_ticket = tk;
-        Ctrl* c0 = p.ctrl + (tk / tiles) / p.n_pol;
-        s_done = *reinterpret_cast<volatile int*>(&c0->done);
-        s_steps = *reinterpret_cast<volatile int*>(&c0->steps);
-        s_z = *reinterpret_cast<volatile double*>(&c0->z);
-        s_hnext = *reinterpret_cast<volatile double*>(&c0->h);
-        if (SYNC == SYNC_FIXED) { __threadfence(); atomicAdd(&c0->arrived, 1u); }
+        __syncthreads();
+        blk = (int)s_ticket;
     }
-    __syncthreads();
-    const int blk = (int)s_ticket;
     const int tile = blk % tiles, row = blk / tiles;
     const int b = row / p.n_pol;
     Ctrl* ctl = p.ctrl + b;
+    if (threadIdx.x == 0) {
+        s_done = *reinterpret_cast<volatile int*>(&ctl->done);
+        s_steps = *reinterpret_cast<volatile int*>(&ctl->steps);
+        s_z = *reinterpret_cast<volatile double*>(&ctl->z);
+        s_hnext = *reinterpret_cast<volatile double*>(&ctl->h);
+        if (SYNC == SYNC_FIXED) { __threadfence(); atomicAdd(&ctl->arrived, 1u); }
+    }
+
+    const int c = threadIdx.x % T, t = threadIdx.x / T;
+    const int n2 = tile * T + c;
+    load_tables(tw, p.tw_col, fft_plan<M, E>::table_size + SC_N);
+    const C* sct = tw + fft_plan<M, E>::table_size;
+
+    C* __restrict__ rowp = p.field + (size_t)row * p.n;
+    R* __restrict__ strow = p.stash + (size_t)row * p.n;
+    if (p.has_nl) {
+#pragma unroll
+        for (int q = 0; q < E; ++q)
+            cp_async<sizeof(R)>(st_sm + q * NT + threadIdx.x, strow + (size_t)(t + q * (M / E)) * p.n2 + n2);
+        cp_async_commit();
+    }
+    C v[E];
+#pragma unroll
+    for (int q = 0; q < E; ++q) v[q] = rowp[(size_t)(t + q * (M / E)) * p.n2 + n2];
+    apply_fourstep<true, R, E, M>(p, v, n2, t);
+    __syncthreads();
     const int step_before = s_steps;
     const R z_before = (R)s_z, h_before = (R)s_hnext;
-    const bool finished = s_done != 0;
-    if (finished) {                                            // uniform over the waveform (and its cluster)
+    if (s_done) {                                              // uniform over the waveform (and its cluster)
+        cp_async_wait_all();
         if (SYNC == SYNC_FIXED && tile == 0 && (row % p.n_pol) == 0 && threadIdx.x == 0) {
             while (*reinterpret_cast<volatile unsigned int*>(&ctl->arrived) < total) __nanosleep(32);
             ctl->arrived = 0u;
         }
         return;
     }
-    __syncthreads();                                           // s_done / s_hnext are reused after the barrier
+    fft_passes<R, M, +1, ColExchange<T>, E>::run(v, sm + c, tw, t);
 
-    const int c = threadIdx.x % T, t = threadIdx.x / T;
-    const int n2 = tile * T + c;
-    load_tables(tw, p.tw_col, fft_plan<M>::table_size + SC_N);
-    const C* sct = tw + fft_plan<M>::table_size;
-
-    C* __restrict__ rowp = p.field + (size_t)row * p.n;
-    R* __restrict__ strow = p.stash + (size_t)row * p.n;
-    if (p.has_nl) {
+    const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h_before));   // 1/N (exact: N = 2^n) and exp(-alpha/2 h) (real part of D~ h)
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-            cp_async<sizeof(R)>(st_sm + q * NT + threadIdx.x, strow + (size_t)(t + q * (M / 16)) * p.n2 + n2);
-        cp_async_commit();
-    }
-    C v[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const int k1 = t + q * (M / 16);
-        v[q] = cmulc(rowp[(size_t)k1 * p.n2 + n2], fourstep_twiddle<R>(p, n2, k1));
-    }
-    __syncthreads();
-    fft_passes<R, M, +1, ColExchange<T> >::run(v, sm + c, tw, t);
-
-#pragma unroll
-    for (int q = 0; q < 16; ++q) { v[q].x *= p.inv_n; v[q].y *= p.inv_n; }   // numpy ifft scaling (exact: N = 2^n)
+    for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
 
     CtrlNext<R> nx;
     if (SYNC == SYNC_FIXED) {
@@ -525,12 +573,59 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mi
         R pm = 0;
         bool nan = false;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
+        for (int q = 0; q < E; ++q) {
             const R pw = v[q].x * v[q].x + v[q].y * v[q].y;    // the Kerr rotations do not change |A|
             nan |= (pw != pw);
             pm = pw > pm ? pw : pm;
         }
         if (nan) pm = pw_nan<R>();
+        if (SYNC == SYNC_LL) {
+            // block max -> warp 0 publishes it and polls the words of the whole waveform
+            constexpr int NW = sizeof(R) / 4;                  // 64-bit words per slot: {value bits 63..32 | tag}, {bits 31..0 | tag}
+            unsigned long long bits = ord_bits(pm);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (lane == 0) red[warp] = bits;
+            __syncthreads();
+            if (warp == 0) {
+                constexpr int NWARPS = (NT + 31) / 32;
+                bits = lane < NWARPS ? red[lane] : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
+                const unsigned long long tag = (unsigned long long)(unsigned)(step_before + 1);
+                volatile unsigned long long* wf = p.slots + (size_t)b * total * 2;
+                const int me = (row % p.n_pol) * tiles + tile;
+                if (lane < NW) {
+                    const unsigned long long part = (NW == 1) ? (bits & 0xffffffffull) : (lane == 0 ? (bits >> 32) : (bits & 0xffffffffull));
+                    wf[me * 2 + lane] = (part << 32) | tag;
+                }
+                unsigned long long best = 0ull;
+                const int nwords = (int)total * NW;
+                for (int base = 0; base < nwords; base += 32) {
+                    const int idx = base + lane;
+                    const bool have = idx < nwords;
+                    unsigned long long w = tag;
+                    for (;;) {
+                        if (have) w = wf[(idx / NW) * 2 + (idx % NW)];
+                        if (__all_sync(0xffffffffu, !have || (w & 0xffffffffull) == tag)) break;
+                        __nanosleep(20);
+                    }
+                    unsigned long long val = have ? (w >> 32) : 0ull;
+                    if (NW == 2) {
+                        const unsigned long long other = __shfl_xor_sync(0xffffffffu, val, 1);
+                        val = (lane & 1) ? 0ull : ((val << 32) | other);
+                    }
+                    best = val > best ? val : best;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
+                if (lane == 0) red[0] = best;
+            }
+            __syncthreads();
+            nx = controller_next<R>(p, z_before, h_before, step_before, from_bits<R>(red[0]));
+            if (tile == 0 && (row % p.n_pol) == 0 && threadIdx.x == 0) controller_commit<R>(p, b, h_before, step_before, nx);
+        } else {
         pm = block_max_bits<R>(pm, red);
         if (SYNC == SYNC_CLUSTER) {
             const unsigned rank = cluster_ctarank();
@@ -562,13 +657,14 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mi
             __syncthreads();
             nx.done = s_done; nx.h = (R)s_hnext; nx.z = 0;
         }
+        }
     }
     cp_async_wait_all();
 
     if (nx.done) {                                              // last step of this waveform: time domain out
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
+        for (int q = 0; q < E; ++q) {
+            const size_t off = (size_t)(t + q * (M / E)) * p.n2 + n2;
             if (p.has_nl) {
                 R s, co; sincos_r(st_sm[q * NT + threadIdx.x], sct, &s, &co);
                 v[q] = cmul(v[q], mk<R>(co, s));
@@ -578,29 +674,240 @@ __global__ void __launch_bounds__(T * (M / 16), min_ctas(T * (M / 16))) k_col_mi
     } else {
         if (p.has_nl) {
             const R hh = nx.h / (R)2;                           // h_/2 of the NEXT step
+            auto kerr = [&](auto small) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const size_t off = (size_t)(t + q * (M / 16)) * p.n2 + n2;
-                const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
-                const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // first half step of the next step
-                const R tot = st_sm[q * NT + threadIdx.x] + ph; // + second half step of this one
-                strow[off] = ph;
-                R s, co; sincos_r(tot, sct, &s, &co);
-                v[q] = cmul(v[q], mk<R>(co, s));
-            }
+                for (int q = 0; q < E; ++q) {
+                    const size_t off = (size_t)(t + q * (M / E)) * p.n2 + n2;
+                    const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                    const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // first half step of the next step
+                    const R tot = st_sm[q * NT + threadIdx.x] + ph; // + second half step of this one
+                    strow[off] = ph;
+                    R s, co; kerr_sincos<decltype(small)::value>(tot, sct, &s, &co);
+                    v[q] = cmul(v[q], mk<R>(co, s));
+                }
+            };
+            if (sizeof(R) == 8 && p.small_phase) kerr(std::true_type{}); else kerr(std::false_type{});
         }
-        fft_passes<R, M, -1, ColExchange<T> >::run(v, sm + c, tw, t);
+        fft_passes<R, M, -1, ColExchange<T>, E>::run(v, sm + c, tw, t);
+        apply_fourstep<false, R, E, M>(p, v, n2, t);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int k1 = t + q * (M / 16);
-            v[q] = cmul(v[q], fourstep_twiddle<R>(p, n2, k1));
-            rowp[(size_t)k1 * p.n2 + n2] = v[q];
-        }
+        for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
     }
     if (SYNC == SYNC_FIXED && tile == 0 && (row % p.n_pol) == 0 && threadIdx.x == 0) {
         // every tile of the waveform has read the old state by now (or will within microseconds)
         while (*reinterpret_cast<volatile unsigned int*>(&ctl->arrived) < total) __nanosleep(32);
         controller_commit<R>(p, b, h_before, step_before, nx);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_col_pipe: the fused column pass as a PERSISTENT, software-pipelined kernel.
+//
+// k_col_mid is latency-bound (ncu: 28 % of the warp time waits for the tile loads, 28 % at the
+// per-waveform barrier, ~35 % computes).  Here the grid is  G groups x `total` CTAs  (total = tiles of
+// one waveform, all resident); CTA j of group g owns tile j of the waveforms g, g+G, g+2G, ... and runs
+//
+//     iteration i:   B(w[i-1])  ->  cp.async prefetch of w[i+1]  ->  A(w[i])
+//
+//   A(w): tile (already prefetched into shared memory) -> registers, conj twiddle, inverse column
+//         transforms, 1/N, max|A|^2 -> publish the tile maximum (LL words), park the tile in shared memory.
+//   B(w): the maxima of w were published one phase ago -> controller, merged Kerr rotation, new stash,
+//         forward column transforms, twiddle, store.
+//
+// so the tile and stash loads of the next waveform fly during a whole iteration and the barrier of
+// w[i] is polled only after the B phase of w[i-1]... i.e. one phase later.  Tiles are assigned statically
+// (all CTAs resident, no tickets): every sibling a B phase waits for is running and can only be waiting on
+// OLDER waveforms, so there is no deadlock.  Two shared-memory slots per CTA (tile + stash each).
+// ---------------------------------------------------------------------------------------------
+template <typename R, int M, int T, int SYNC>
+__global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), (T * (M / points_per_thread<R>::value)) <= 256 ? 2 : 1)
+k_col_pipe(Params<R> p) {   // two CTAs per SM: shared memory (2 tile slots each) is the limit, so up to 128 registers
+    typedef typename cx_of<R>::type C;
+    constexpr int E = points_per_thread<R>::value;
+    constexpr int NT = T * (M / E);
+    constexpr int NWARPS = (NT + 31) / 32;
+    constexpr int NW = sizeof(R) / 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long red[32];
+    __shared__ int s_done[2], s_steps[2];
+    __shared__ double s_h[2], s_z[2];
+    C* tw = reinterpret_cast<C*>(smem_raw);                              // pass tables + sincos table
+    const C* sct = tw + fft_plan<M, E>::table_size;
+    C* fbuf = tw + fft_plan<M, E>::table_size + SC_N;                     // 2 x [M][T] tile slots
+    R* sbuf = reinterpret_cast<R*>(fbuf + 2 * M * T);                     // 2 x [E][NT] stash slots
+
+    const int tiles = p.n2 / T;
+    const int total = tiles * p.n_pol;
+    const int ngroups = gridDim.x / total;
+    const int grp = blockIdx.x / total, me = blockIdx.x % total;
+    const int pol = me / tiles, tile = me % tiles;
+    const int c = threadIdx.x % T, t = threadIdx.x / T;
+    const int n2 = tile * T + c;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my = (p.batch - grp + ngroups - 1) / ngroups;            // waveforms grp, grp+ngroups, ...
+
+    load_tables(tw, p.tw_col, fft_plan<M, E>::table_size + SC_N);
+
+    auto prefetch = [&](int i) {                                          // waveform i of this CTA -> slot i&1
+        const int w = grp + i * ngroups, slot = i & 1;
+        const size_t row = (size_t)w * p.n_pol + pol;
+        const C* __restrict__ rowp = p.field + row * p.n;
+        const R* __restrict__ strow = p.stash + row * p.n;
+        C* f = fbuf + slot * (M * T);
+        R* st = sbuf + slot * (E * NT);
+        if (threadIdx.x == 0) {                                           // controller state of w, once per CTA
+            const Ctrl* c0 = p.ctrl + w;
+            s_done[slot] = *reinterpret_cast<const volatile int*>(&c0->done);
+            s_steps[slot] = *reinterpret_cast<const volatile int*>(&c0->steps);
+            s_z[slot] = *reinterpret_cast<const volatile double*>(&c0->z);
+            s_h[slot] = *reinterpret_cast<const volatile double*>(&c0->h);
+            if (SYNC == SYNC_FIXED) { __threadfence(); atomicAdd(&p.ctrl[w].arrived, 1u); }
+        }
+#pragma unroll
+        for (int q = 0; q < E; ++q) {
+            const size_t off = (size_t)(t + q * (M / E)) * p.n2 + n2;
+            cp_async<sizeof(C)>(f + (t + q * (M / E)) * T + c, rowp + off);
+            if (p.has_nl) cp_async<sizeof(R)>(st + q * NT + threadIdx.x, strow + off);
+        }
+        cp_async_commit();
+    };
+
+    if (n_my > 0) prefetch(0);
+    // state carried from A(w[i]) to B(w[i]) (uniform over the CTA)
+    int a_valid = 0, a_steps = 0; R a_z = 0, a_h = 0;
+
+    for (int i = 0; i <= n_my; ++i) {
+        // ---------------- B(w[i-1]) -----------------------------------------------------------------
+        if (i > 0 && a_valid) {
+            const int w = grp + (i - 1) * ngroups, slot = (i - 1) & 1;
+            const size_t row = (size_t)w * p.n_pol + pol;
+            C* __restrict__ rowp = p.field + row * p.n;
+            R* __restrict__ strow = p.stash + row * p.n;
+            C* f = fbuf + slot * (M * T);
+            const R* st = sbuf + slot * (E * NT);
+            CtrlNext<R> nx;
+            if (SYNC == SYNC_FIXED) {
+                nx = controller_next<R>(p, a_z, a_h, a_steps, (R)0);
+                if (me == 0 && threadIdx.x == 0) {
+                    while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl[w].arrived) < (unsigned)total) __nanosleep(32);
+                    controller_commit<R>(p, w, a_h, a_steps, nx);
+                }
+            } else {
+                if (warp == 0) {                                          // poll the LL words of waveform w
+                    const unsigned long long tag = (unsigned long long)(unsigned)(a_steps + 1);
+                    volatile unsigned long long* wf = p.slots + (size_t)w * total * 2;
+                    unsigned long long best = 0ull;
+                    const int nwords = total * NW;
+                    for (int base = 0; base < nwords; base += 32) {
+                        const int idx = base + lane;
+                        const bool have = idx < nwords;
+                        unsigned long long x = tag;
+                        for (;;) {
+                            if (have) x = wf[(idx / NW) * 2 + (idx % NW)];
+                            if (__all_sync(0xffffffffu, !have || (x & 0xffffffffull) == tag)) break;
+                            __nanosleep(20);
+                        }
+                        unsigned long long val = have ? (x >> 32) : 0ull;
+                        if (NW == 2) {
+                            const unsigned long long other = __shfl_xor_sync(0xffffffffu, val, 1);
+                            val = (lane & 1) ? 0ull : ((val << 32) | other);
+                        }
+                        best = val > best ? val : best;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
+                    if (lane == 0) red[0] = best;
+                }
+                __syncthreads();
+                nx = controller_next<R>(p, a_z, a_h, a_steps, from_bits<R>(red[0]));
+                if (me == 0 && threadIdx.x == 0) controller_commit<R>(p, w, a_h, a_steps, nx);
+            }
+            C v[E];
+#pragma unroll
+            for (int q = 0; q < E; ++q) v[q] = f[(t + q * (M / E)) * T + c];        // the parked tile (own points)
+            if (nx.done) {                                                        // last step of w: time domain out
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    if (p.has_nl) {
+                        R sn, co; sincos_r(st[q * NT + threadIdx.x], sct, &sn, &co);
+                        v[q] = cmul(v[q], mk<R>(co, sn));
+                    }
+                    rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
+                }
+            } else {
+                if (p.has_nl) {
+                    const R hh = nx.h / (R)2;                                     // h_/2 of the NEXT step
+#pragma unroll
+                    for (int q = 0; q < E; ++q) {
+                        const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                        const R ph = mul_rn(hh, mul_rn(p.gamma, pw));
+                        const R tot = st[q * NT + threadIdx.x] + ph;
+                        strow[(size_t)(t + q * (M / E)) * p.n2 + n2] = ph;
+                        R sn, co; sincos_r(tot, sct, &sn, &co);
+                        v[q] = cmul(v[q], mk<R>(co, sn));
+                    }
+                }
+                fft_passes<R, M, -1, ColExchange<T>, E>::run(v, f + c, tw, t);
+                apply_fourstep<false, R, E, M>(p, v, n2, t);
+#pragma unroll
+                for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
+            }
+            __syncthreads();                                      // slot (i-1)&1 is free for the next prefetch
+        }
+        // ---------------- prefetch w[i+1] into the slot B just released ------------------------------------
+        if (i + 1 < n_my) prefetch(i + 1);
+        // ---------------- A(w[i]) ----------------------------------------------------------------------
+        a_valid = 0;
+        if (i < n_my) {
+            const int w = grp + i * ngroups, slot = i & 1;
+            C* f = fbuf + slot * (M * T);
+            if (i + 1 < n_my) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            else cp_async_wait_all();
+            __syncthreads();                                      // tile landed for every thread; s_* handed over
+            if (!s_done[slot]) {
+                a_valid = 1; a_steps = s_steps[slot]; a_z = (R)s_z[slot]; a_h = (R)s_h[slot];
+                C v[E];
+#pragma unroll
+                for (int q = 0; q < E; ++q) v[q] = f[(t + q * (M / E)) * T + c];
+                apply_fourstep<true, R, E, M>(p, v, n2, t);
+                fft_passes<R, M, +1, ColExchange<T>, E>::run(v, f + c, tw, t);
+                R pm = 0;
+                bool nan = false;
+                const R sc = p.inv_n * exp_r(mul_rn(p.att_half, a_h));
+#pragma unroll
+                for (int q = 0; q < E; ++q) {
+                    v[q].x *= sc; v[q].y *= sc;                    // 1/N and the attenuation of the step
+                    const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                    nan |= (pw != pw);
+                    pm = pw > pm ? pw : pm;
+                }
+                if (nan) pm = pw_nan<R>();
+                unsigned long long bits = ord_bits(pm);
+                if (SYNC != SYNC_FIXED) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
+                    if (lane == 0) red[warp] = bits;
+                }
+                __syncthreads();                                  // all exchange reads done: the slot can take the parked tile
+#pragma unroll
+                for (int q = 0; q < E; ++q) f[(t + q * (M / E)) * T + c] = v[q];
+                if (SYNC != SYNC_FIXED && warp == 0) {
+                    bits = lane < NWARPS ? red[lane] : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
+                    if (lane < NW) {
+                        const unsigned long long tag = (unsigned long long)(unsigned)(a_steps + 1);
+                        const unsigned long long part = (NW == 1) ? (bits & 0xffffffffull) : (lane == 0 ? (bits >> 32) : (bits & 0xffffffffull));
+                        volatile unsigned long long* wf = p.slots + (size_t)w * total * 2;
+                        wf[me * 2 + lane] = (part << 32) | tag;
+                    }
+                }
+            } else if (SYNC == SYNC_FIXED && me == 0 && threadIdx.x == 0) {
+                while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl[w].arrived) < (unsigned)total) __nanosleep(32);
+                p.ctrl[w].arrived = 0u;
+            }
+        }
     }
 }
 
