@@ -69,28 +69,31 @@ def _to_device(a: np.ndarray, tdtype, dev):
 
 # ---- FIBER / DBP --------------------------------------------------------------------------------
 def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
-                precision=None, device=None, want_log=False, chunk_waveforms=None, inplace=False, fused=True):
+                precision=None, device=None, want_log=False, chunk_waveforms=None, inplace=False, fused=True, out=None):
     """Propagate a batch ``field[B, N]`` or ``field[B, P, N]`` (NumPy array or CUDA tensor).
 
     Rows are independent waveforms, each with its own step-size sequence (the global max of
     devices.py:1194 is taken over the P rows of one waveform).  Returns ``(out, StepInfo)``; ``out``
-    is a CUDA tensor when a tensor was given, else a NumPy array.
+    is a CUDA tensor when a CUDA tensor was given, a host tensor for a host tensor (pass a pinned ``out=`` to
+    avoid the allocation) and a NumPy array for a NumPy array.  Host inputs are streamed through the device in
+    chunks so that the PCIe copies overlap the propagation.
     """
     torch = engine._torch()
     tdtype, ndtype = _complex_dtype(precision)
     as_tensor = torch.is_tensor(field)
     on_host = not (as_tensor and field.is_cuda)
-    if not on_host:
-        dev = engine.require_cuda(field.device)
-        x = field.to(dtype=tdtype).contiguous()
-        if not inplace and x.data_ptr() == field.data_ptr():
-            x = x.clone()
-    else:
+    if on_host:
         dev = engine.require_cuda(device)
-        if as_tensor:                                                  # host tensor (pinned => async copy)
-            x = field.to(dev, non_blocking=True).to(tdtype).contiguous()
-        else:
-            x = _to_device(np.asarray(field), tdtype, dev)
+        host = field if as_tensor else torch.from_numpy(np.ascontiguousarray(field))
+        if not host.is_complex():
+            host = host.to(torch.complex128)
+        res, info = _propagate_host_streamed(host.contiguous(), out, tdtype, dev, want_log, chunk_waveforms, fused,
+                                             (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h))
+        return (res if as_tensor else res.numpy()), info
+    dev = engine.require_cuda(field.device)
+    x = field.to(dtype=tdtype).contiguous()
+    if not inplace and x.data_ptr() == field.data_ptr():
+        x = x.clone()
     if x.ndim not in (2, 3):
         raise ValueError("field must have shape [B, N] or [B, P, N]")
     B, P, N = (x.shape[0], 1, x.shape[1]) if x.ndim == 2 else tuple(x.shape)
@@ -98,13 +101,73 @@ def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
     plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
     plan.set_option("fused", 1 if fused else 0)
     info = plan.propagate(x, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
-    if not on_host:
-        return x, info
-    if as_tensor:
-        out = torch.empty(x.shape, dtype=x.dtype, pin_memory=field.is_pinned())
-        out.copy_(x)
-        return out, info
-    return x.cpu().numpy(), info
+    return x, info
+
+
+HOST_LANES = 3                  # concurrent host->device->host pipelines (threads + streams) of the host path
+HOST_CHUNK_BYTES = 256 << 20    # target size of one chunk of rows on the device
+
+
+def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, fused, args):
+    """Host buffers in, host buffers out: rows are cut into chunks and `HOST_LANES` worker threads, each with
+    its own CUDA stream and plan, run  H2D copy -> cast -> split-step loop -> D2H copy  so that the PCIe
+    transfers of one chunk overlap the propagation of another (the C call releases the GIL)."""
+    import threading
+    torch = engine._torch()
+    if host.ndim not in (2, 3):
+        raise ValueError("field must have shape [B, N] or [B, P, N]")
+    B = host.shape[0]
+    P, N = (1, host.shape[1]) if host.ndim == 2 else (host.shape[1], host.shape[2])
+    if out is None:
+        out = torch.empty(host.shape, dtype=tdtype, pin_memory=host.is_pinned())
+    elif out.shape != host.shape or out.dtype != tdtype or out.is_cuda:
+        raise ValueError("out must be a host tensor of shape %s and dtype %s" % (tuple(host.shape), tdtype))
+    row_bytes = P * N * 16
+    rows = max(1, min(B, HOST_CHUNK_BYTES // row_bytes))
+    if B > rows:
+        rows = -(-B // max(HOST_LANES, -(-B // rows)))            # even chunks, at least HOST_LANES of them
+    chunks = [(r0, min(B, r0 + rows)) for r0 in range(0, B, rows)]
+    lanes = min(HOST_LANES, len(chunks))
+    steps = np.zeros(B, np.int32); z = np.zeros(B); hn = np.zeros(B); done = np.zeros(B, bool)
+    logs, errors = {}, []
+
+    def worker(lane):
+        try:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(stream):
+                    for ci in range(lane, len(chunks), lanes):
+                        r0, r1 = chunks[ci]
+                        x = host[r0:r1].to(dev, non_blocking=True).to(tdtype).contiguous()
+                        plan = engine.get_plan(N, P, r1 - r0, tdtype, dev, lane=lane)
+                        plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
+                        plan.set_option("fused", 1 if fused else 0)
+                        info = plan.propagate(x, *args, want_log=want_log)
+                        out[r0:r1].copy_(x, non_blocking=True)
+                        steps[r0:r1], z[r0:r1], hn[r0:r1], done[r0:r1] = info.steps, info.z, info.h_next, info.done
+                        if want_log:
+                            logs[ci] = info.h_log
+                        stream.synchronize()
+        except Exception as e:                                     # surfaced by the caller's thread
+            errors.append(e)
+
+    if lanes == 1:
+        worker(0)
+    else:
+        threads = [threading.Thread(target=worker, args=(l,)) for l in range(lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    h_log = None
+    if want_log:
+        width = max(l.shape[1] for l in logs.values())
+        h_log = np.zeros((B, width))
+        for ci, (r0, r1) in enumerate(chunks):
+            h_log[r0:r1, :logs[ci].shape[1]] = logs[ci]
+    return out, engine.StepInfo(steps, z, hn, done, h_log)
 
 
 def dbp_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, **kw):

@@ -124,16 +124,21 @@ class Plan:
 _PLANS: dict = {}
 
 
-def get_plan(n, n_pol, batch, complex_dtype, device=None) -> Plan:
+_PLANS_LOCK = __import__("threading").Lock()
+
+
+def get_plan(n, n_pol, batch, complex_dtype, device=None, lane=0) -> Plan:
+    """Cached plan.  A plan is not thread-safe: concurrent host pipelines pass distinct ``lane`` ids."""
     torch = _torch()
     dev = require_cuda(device)
     cd = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
-    key = (int(n), int(n_pol), int(batch), cd, dev.index)
-    pl = _PLANS.get(key)
-    if pl is None:
-        if len(_PLANS) >= 8:  # plans own O(B*N) device memory: keep the cache small
-            _PLANS.pop(next(iter(_PLANS))).close()
-        pl = _PLANS[key] = Plan(n, n_pol, batch, cd, dev)
+    key = (int(n), int(n_pol), int(batch), cd, dev.index, int(lane))
+    with _PLANS_LOCK:
+        pl = _PLANS.get(key)
+        if pl is None:
+            if len(_PLANS) >= 12:  # plans own O(B*N) device memory: keep the cache small
+                _PLANS.pop(next(iter(_PLANS))).close()
+            pl = _PLANS[key] = Plan(n, n_pol, batch, cd, dev)
     return pl
 
 
