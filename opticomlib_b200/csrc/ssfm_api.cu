@@ -140,6 +140,7 @@ struct ssfm_plan_s {
     int num_sms = 0;
     int debug = 0;
     int use_tw_full = 1;
+    int l2_ahead = 0;
     int pipe = 0;                // 1: persistent pipelined fused kernel (k_col_pipe) when a waveform fits on the chip
     int n_active = 0;
     double* hlog = nullptr;
@@ -372,6 +373,7 @@ Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed,
     base.has_nl = (g != (R)0) ? 1 : 0;
     base.max_steps = 1 << 30;
     base.debug = pl->debug;
+    base.l2_ahead = pl->l2_ahead;
     base.gamma = g; base.abs_gamma = std::fabs(g); base.phi_max = pm; base.length = L;
     base.att_half = -a_lin / (R)2;
     base.c2 = (R)0.5 * b2;                       // imag(1j/2 * beta_2): exact scaling
@@ -771,6 +773,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "debug") { pl->debug = (int)value; }
     else if (k == "pipe") { pl->pipe = value ? 1 : 0; }
     else if (k == "tw_full") { pl->use_tw_full = value ? 1 : 0; }
+    else if (k == "l2_ahead") { pl->l2_ahead = (int)value; }
     else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
     return SSFM_OK;
 }

@@ -51,6 +51,8 @@ struct Params {
     const C* tw_hi;      // W_N^(i*2^lo_bits)
     const C* tw_full;    // optional full four-step table W_N^{n2*k1} at [k1][n2] (N <= 2^20): one coalesced L2 load
                          // instead of two table look-ups and a complex product
+    int l2_ahead;        // > 0: each CTA of the fused column kernel prefetches into L2 the tile that the CTA
+                         // `l2_ahead` tickets later will load (about one CTA lifetime ahead)
     int small_phase;     // 1: every Kerr phase is <= 0.05 rad (adaptive mode with phi_max <= 0.05): short Taylor sincos
     const C* xfer;       // optional transfer function H[k] in transposed order ([k1][k2], bin k1 + N1*k2):
                          // when set, the row kernel multiplies by it instead of exp(D~ h) (filters, DM)
@@ -209,6 +211,7 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gmem_src), "n"(BYTES));
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -524,6 +527,20 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
     const int tile = blk % tiles, row = blk / tiles;
     const int b = row / p.n_pol;
     Ctrl* ctl = p.ctrl + b;
+    if (p.l2_ahead > 0 && blk + p.l2_ahead < (int)gridDim.x) {   // warm L2 for a CTA that starts one lifetime later
+        const int pb = blk + p.l2_ahead;
+        const int ptile = pb % tiles, prow = pb / tiles;
+        if (!p.ctrl[prow / p.n_pol].done) {
+            const char* fa = reinterpret_cast<const char*>(p.field + (size_t)prow * p.n + (size_t)ptile * T);
+            const char* sa = reinterpret_cast<const char*>(p.stash + (size_t)prow * p.n + (size_t)ptile * T);
+            constexpr int FL = (T * (int)sizeof(C) + 127) / 128, SL = (T * (int)sizeof(R) + 127) / 128;   // 128-B lines per row segment
+            for (int i = threadIdx.x; i < M * FL; i += NT)
+                prefetch_l2(fa + (size_t)(i / FL) * p.n2 * sizeof(C) + (i % FL) * 128);
+            if (p.has_nl)
+                for (int i = threadIdx.x; i < M * SL; i += NT)
+                    prefetch_l2(sa + (size_t)(i / SL) * p.n2 * sizeof(R) + (i % SL) * 128);
+        }
+    }
     if (threadIdx.x == 0) {
         s_done = *reinterpret_cast<volatile int*>(&ctl->done);
         s_steps = *reinterpret_cast<volatile int*>(&ctl->steps);

@@ -123,3 +123,28 @@ def config_input(name: str, shape: str | None = None) -> tuple[np.ndarray, float
         shape = "nrz" if name == "cfg5" else "gaussian"
     field = ook_field(c["order"], c["nbits"], c["sps"], c["p0_dbm"], shape)
     return field, 1.0 / fs, dict(c["fiber"])
+
+
+# ---- BASELINE config #4: received frames for digital back-propagation ------------------------------
+def cfg4_link(frames, fields_fn, spans: int = 10, gain_db: float = 16.0, nf_db: float = 5.0, seed0: int = 2000):
+    """Forward link of config #4: `spans` x [80 km SSMF -> 16 dB gain -> ASE], run by
+    ``fields_fn(block, **fiber_kwargs) -> block`` (the accelerated engine; the CPU reference would need days at
+    full size).  ``frames`` is a complex128 array [B, N] of transmitted frames; row b gets ASE from
+    default_rng(seed0 + b).  Returns the received frames [B, N]."""
+    c = CONFIGS["cfg4"]
+    fs = c["R"] * c["sps"]
+    fwd = dict(length=80.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, h=10.0)
+    G = 10 ** (gain_db / 10)
+    p_ase = 10 ** (nf_db / 10) * PLANCK * (C_LIGHT / 1550e-9) * (G - 1) * fs
+    x = np.array(frames, dtype=np.complex128, copy=True)
+    rngs = [np.random.default_rng(seed0 + b) for b in range(x.shape[0])]
+    for _ in range(spans):
+        x = np.asarray(fields_fn(x, **fwd)) * np.sqrt(G)
+        for b, rng in enumerate(rngs):
+            n = rng.standard_normal((2, x.shape[1]))
+            x[b] += np.sqrt(p_ase / 4) * (n[0] + 1j * n[1])
+    return x
+
+
+CFG4_RX = dict(bpf_bw=40e9, lpf_bw=7.5e9, span_loss_db=16.0, spans=10,
+               dbp=dict(length=80.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, h=10.0))
