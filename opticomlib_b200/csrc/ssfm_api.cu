@@ -43,7 +43,7 @@ constexpr int col_tile(int M, int E) { return clampi(clampi(256 * E / M, 2, 32),
 constexpr int row_group(int M, int E) { return clampi(256 * E / M, 1, M / 2); }
 template <typename R> constexpr int col_tile_of(int M) { return col_tile(M, points_per_thread<R>::value); }
 template <typename R> constexpr int row_group_of(int M) { return row_group(M, points_per_thread<R>::value); }
-int col_tile_rt(int M, int dtype) { return dtype == SSFM_C64 ? col_tile(M, 16) : col_tile(M, 8); }
+int col_tile_rt(int M, int dtype) { return dtype == SSFM_C64 ? col_tile_of<float>(M) : col_tile_of<double>(M); }
 
 // twiddle tables, built on the device in double and rounded once to R ---------------------------
 template <typename R>
@@ -187,7 +187,8 @@ size_t col_mid_smem() {
     typedef typename cx_of<R>::type C;
     constexpr int T = col_tile_of<R>(M);
     constexpr int E = points_per_thread<R>::value;
-    return sizeof(C) * (size_t)(M * T + fft_plan<M, E>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
+    return sizeof(C) * (size_t)(M * T + (col_mid_tables_in_smem(M) ? fft_plan<M, E>::table_size : 0) + SC_N) +
+           sizeof(R) * (size_t)(M * T);
 }
 template <typename R, int M, int SYNC>
 int launch_col_mid(const Params<R>& p, int nblocks, int cluster, cudaStream_t st) {
@@ -282,6 +283,7 @@ int col_mid_sync_mode(int num_sms, long long group, int want, int* mode) {
         CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC_LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_col_mid<R, M, T, SYNC_LL>, T * (M / E), smem));
         if (group <= (long long)per_sm * num_sms) *mode = SYNC_LL;
+        if (getenv("SSFM_DEBUG")) fprintf(stderr, "[ssfm] col_mid LL: M=%d T=%d smem=%zu per_sm=%d group=%lld mode=%d\n", M, T, smem, per_sm, group, *mode);
     }
     return SSFM_OK;
 }

@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
 //                (SYNC_LL uses the same tickets.)
 // ---------------------------------------------------------------------------------------------
 enum { SYNC_FIXED = 0, SYNC_CLUSTER = 1, SYNC_GLOBAL = 2, SYNC_LL = 3 };
+__host__ __device__ constexpr bool col_mid_tables_in_smem(int M) { return M < 1024; }
 
 __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -503,9 +504,16 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
     __shared__ unsigned int s_ticket;
     __shared__ int s_done, s_steps;
     __shared__ double s_hnext, s_z;
+    // Pass tables live in shared memory for M < 1024; for longer transforms they are read through L1 from
+    // global memory instead, which keeps the CTA under half of the SM's shared memory (two resident CTAs,
+    // so that the 256 tiles of a single 2^20-sample waveform fit on the chip for the in-kernel barrier).
+    constexpr bool kTabSmem = col_mid_tables_in_smem(M);
+    constexpr int kTabCount = (kTabSmem ? fft_plan<M, E>::table_size : 0) + SC_N;
     C* sm = reinterpret_cast<C*>(smem_raw);
-    C* tw = sm + M * T;
-    R* st_sm = reinterpret_cast<R*>(tw + fft_plan<M, E>::table_size + SC_N);   // [E][threads] stash prefetch
+    C* tws = sm + M * T;                                                      // [pass tables][sincos table]
+    R* st_sm = reinterpret_cast<R*>(tws + kTabCount);                          // [E][threads] stash prefetch
+    const C* tw = kTabSmem ? tws : p.tw_col;
+    const C* sct = tws + (kTabSmem ? fft_plan<M, E>::table_size : 0);
 
     // Thread 0 takes the ticket (SYNC_GLOBAL / SYNC_LL) and reads the controller state ONCE for the whole
     // CTA (only then does it report "state read" in SYNC_FIXED), so no thread can see a state committed by
@@ -551,8 +559,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
 
     const int c = threadIdx.x % T, t = threadIdx.x / T;
     const int n2 = tile * T + c;
-    load_tables(tw, p.tw_col, fft_plan<M, E>::table_size + SC_N);
-    const C* sct = tw + fft_plan<M, E>::table_size;
+    load_tables(tws, p.tw_col + (kTabSmem ? 0 : fft_plan<M, E>::table_size), kTabCount);
 
     C* __restrict__ rowp = p.field + (size_t)row * p.n;
     R* __restrict__ strow = p.stash + (size_t)row * p.n;
