@@ -71,8 +71,11 @@ SSFM_API int ssfm_plan_create(ssfm_plan_t* plan, int64_t n_samples, int32_t n_po
                      int32_t dtype, int32_t device);
 SSFM_API int ssfm_plan_destroy(ssfm_plan_t plan);
 
-/* Tunables: "chunk_waveforms" (waveforms propagated together so that field + stash stay in L2;
- * 0 = all), "hlog_cap" (step sizes logged per waveform), "burst_steps". */
+/* Tunables: "persistent" (1 = run the whole propagation as one persistent kernel whose teams of CTAs keep
+ * the waveforms in flight resident in L2 -- the default whenever a waveform's team fits on the chip;
+ * 0 = multi-launch schedule), "teams" (cap on concurrent waveforms of the persistent kernel, 0 = auto),
+ * "chunk_waveforms" (multi-launch schedule: waveforms propagated together, 0 = all), "burst_steps",
+ * "fused" (multi-launch schedule: 0 three kernels per step, 1..3 two kernels per step). */
 SSFM_API int ssfm_plan_set_option(ssfm_plan_t plan, const char* name, int64_t value);
 
 /* FIBER hot loop, devices.py:1155-1196, in place on field_dev[n_waveforms][n_pol][n_samples].
@@ -89,6 +92,10 @@ SSFM_API int ssfm_propagate(ssfm_plan_t plan, void* field_dev, const ssfm_fiber_
  * 1 if z >= length. */
 SSFM_API int ssfm_get_state(ssfm_plan_t plan, int32_t* steps_host, double* z_host, double* h_next_host,
                    int32_t* done_host);
+/* Schedule used by the last ssfm_propagate on this plan: *kind = 1 multi-launch, 2 persistent kernel
+ * (then *teams = waveforms in flight and *kernel_ms = device time of that one launch, CUDA events on the
+ * launching stream).  Any pointer may be NULL.  Measurement hook for bench.py's roofline object. */
+SSFM_API int ssfm_get_last_timing(ssfm_plan_t plan, int32_t* kind, int32_t* teams, float* kernel_ms);
 /* Step sizes taken, hlog_host[n_waveforms][cap] (rows are filled up to min(steps, cap)). */
 SSFM_API int ssfm_get_step_log(ssfm_plan_t plan, double* hlog_host, int64_t cap);
 

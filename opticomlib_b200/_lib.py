@@ -38,6 +38,8 @@ PROTOTYPES = {
     "ssfm_get_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_void_p]),
     "ssfm_get_step_log": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    "ssfm_get_last_timing": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                            ctypes.POINTER(ctypes.c_float)]),
     "ssfm_launch_count": (ctypes.c_int64, []),
     "ssfm_time_step_kernels": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FiberParams),
                                               ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),

@@ -10,6 +10,7 @@
 #include "../../include/ssfm_b200.h"
 #include "ssfm_kernels.cuh"
 #include "ssfm_internal.h"
+#include "ssfm_wf.h"
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -142,6 +143,12 @@ struct ssfm_plan_s {
     int use_tw_full = 1;
     int l2_ahead = 0;
     int pipe = 0;                // 1: persistent pipelined fused kernel (k_col_pipe) when a waveform fits on the chip
+    int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
+    int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
+    void* wf_sync = nullptr;     // k_wf barriers / mailboxes / max words
+    cudaEvent_t wf_ev[2] = {nullptr, nullptr};
+    int last_kind = 0;           // schedule of the last propagate: 0 none, 1 multi-launch, 2 k_wf
+    int last_teams = 0;
     int n_active = 0;
     double* hlog = nullptr;
     int hlog_cap = 0;
@@ -407,6 +414,27 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         if (rc) return rc;
         if (sync < 0) use_fused = false;
     }
+    if (pl->persistent && pl->wf_sync) {
+        // One cooperative launch carries every waveform through all of its steps (ssfm_wf.cuh).
+        Params<R> p = base;
+        p.field = (C*)field; p.stash = nullptr; p.ctrl = pl->ctrl; p.active = pl->active;
+        p.ticket = pl->ticket; p.slots = pl->slots; p.hlog = pl->hlog; p.batch = (int)B;
+        WfLaunch l{};
+        l.sync_buf = pl->wf_sync; l.num_sms = pl->num_sms;
+        l.fixed = fixed ? 1 : 0; l.single = single ? 1 : 0; l.resume = resume ? 1 : 0;
+        l.h_fixed = fixed ? prm.h_km : 0.0;
+        l.budget = budget; l.teams_cap = pl->teams_cap;
+        l.ev0 = pl->wf_ev[0]; l.ev1 = pl->wf_ev[1];
+        int teams = 0;
+        const int rc = wf_propagate<R>(p, l, &teams, st);
+        if (rc == SSFM_OK) {
+            CU_TRY(cudaStreamSynchronize(st));
+            pl->have_state = true; pl->last = prm; pl->last_kind = 2; pl->last_teams = teams;
+            return SSFM_OK;
+        }
+        if (rc != SSFM_ERR_UNSUPPORTED) return rc;
+    }
+    pl->last_kind = 1;
     int ci = 0;
     for (long long b0 = 0; b0 < B; b0 += chunk, ++ci) {
         const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
@@ -720,6 +748,9 @@ static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t 
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&pl->active_host, 2 * sizeof(int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[1], cudaEventDisableTiming);
+    if (e == cudaSuccess && with_stash) e = cudaMalloc(&pl->wf_sync, WF_SYNC_BYTES);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[1]);
     if (e != cudaSuccess) {
         ssfm_plan_destroy(pl);
         return fail(e == cudaErrorMemoryAllocation ? SSFM_ERR_NOMEM : SSFM_ERR_CUDA,
@@ -762,6 +793,9 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (pl->active_host) cudaFreeHost(pl->active_host);
     if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
     if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
+    cudaFree(pl->wf_sync);
+    if (pl->wf_ev[0]) cudaEventDestroy(pl->wf_ev[0]);
+    if (pl->wf_ev[1]) cudaEventDestroy(pl->wf_ev[1]);
     delete pl;
     return SSFM_OK;
 }
@@ -774,6 +808,8 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "fused") { pl->fused = (int)value; }   // 0 unfused, 1 fused (LL barrier), 2 fused (atomic barrier), 3 fused (cluster barrier when possible)
     else if (k == "debug") { pl->debug = (int)value; }
     else if (k == "pipe") { pl->pipe = value ? 1 : 0; }
+    else if (k == "persistent") { pl->persistent = value ? 1 : 0; }
+    else if (k == "teams") { if (value < 0) return fail(SSFM_ERR_INVALID, "teams < 0"); pl->teams_cap = (int)value; }
     else if (k == "tw_full") { pl->use_tw_full = value ? 1 : 0; }
     else if (k == "l2_ahead") { pl->l2_ahead = (int)value; }
     else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
@@ -803,6 +839,21 @@ int ssfm_get_state(ssfm_plan_t pl, int32_t* steps, double* z, double* h_next, in
         if (z) z[i] = h[i].z;
         if (h_next) h_next[i] = h[i].h;
         if (done) done[i] = h[i].done;
+    }
+    return SSFM_OK;
+}
+
+int ssfm_get_last_timing(ssfm_plan_t pl, int32_t* kind, int32_t* teams, float* kernel_ms) {
+    if (!pl) return fail(SSFM_ERR_INVALID, "null plan");
+    if (kind) *kind = pl->last_kind;
+    if (teams) *teams = pl->last_kind == 2 ? pl->last_teams : 0;
+    if (kernel_ms) {
+        *kernel_ms = 0.0f;
+        if (pl->last_kind == 2) {
+            CU_TRY(cudaSetDevice(pl->device));
+            CU_TRY(cudaEventSynchronize(pl->wf_ev[1]));
+            CU_TRY(cudaEventElapsedTime(kernel_ms, pl->wf_ev[0], pl->wf_ev[1]));
+        }
     }
     return SSFM_OK;
 }

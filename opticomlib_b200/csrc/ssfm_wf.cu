@@ -1,0 +1,93 @@
+// Launch side of the persistent whole-propagation kernel k_wf (ssfm_wf.cuh).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/ssfm_b200.h"
+#include "ssfm_wf.cuh"
+#include "ssfm_wf.h"
+#include "ssfm_internal.h"
+
+extern long long ssfm_launches;
+
+namespace ssfm {
+namespace {
+
+int wf_fail(int code, const std::string& msg) { ssfm_err_slot = msg; return code; }
+
+#define WF_TRY(expr)                                                                            \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return wf_fail(SSFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+template <typename R, int M1, int M2, bool SMALL>
+int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
+    typedef wf_geom<R, M1, M2> GEO;
+    auto kern = k_wf<R, M1, M2, SMALL>;
+    static int per_sm = -1;                                     // per instantiation; one device kind per process
+    if (per_sm < 0) {
+        WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
+        int v = 0;
+        WF_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, GEO::NT, GEO::smem));
+        per_sm = v;
+    }
+    const long long total = (long long)p.n_pol * (p.n2 / GEO::T);       // CTAs of one team
+    long long teams = (long long)per_sm * l.num_sms / total;
+    if (teams > p.batch) teams = p.batch;
+    if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
+    if (teams < 1) return SSFM_ERR_UNSUPPORTED;                          // one waveform does not fit on the chip
+    if (getenv("SSFM_DEBUG"))
+        fprintf(stderr, "[ssfm] k_wf<%d,%d,%d,%d>: smem %zu, %d CTAs/SM, team %lld CTAs, %lld teams\n", (int)sizeof(R), M1, M2,
+                (int)SMALL, (size_t)GEO::smem, per_sm, total, teams);
+
+    // sync scratch: [bar: teams x 128 B][mail: teams x 128 B][next_wf: 128 B][slots: teams x 2 x total x 16 B]
+    const size_t need = (size_t)teams * 256 + 128 + (size_t)teams * 2 * total * 16;
+    if (need > WF_SYNC_BYTES) return SSFM_ERR_UNSUPPORTED;
+    WF_TRY(cudaMemsetAsync(l.sync_buf, 0, need, st));
+    WfArgs<R> a;
+    char* sb = (char*)l.sync_buf;
+    a.bar = (unsigned int*)sb;
+    a.mail = (unsigned long long*)(sb + (size_t)teams * 128);
+    a.next_wf = (unsigned int*)(sb + (size_t)teams * 256);
+    a.slots = (unsigned long long*)(sb + (size_t)teams * 256 + 128);
+    a.budget = l.budget;
+    a.n_teams = (int)teams;
+    a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
+    a.h_fixed = (R)l.h_fixed;
+    Params<R> pp = p;
+    void* args[2] = {(void*)&pp, (void*)&a};
+    if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
+    WF_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(teams * total)), dim3(GEO::NT), args, GEO::smem, st));
+    if (l.ev1) WF_TRY(cudaEventRecord(l.ev1, st));
+    ++ssfm_launches;
+    if (teams_out) *teams_out = (int)teams;
+    return SSFM_OK;
+}
+
+template <typename R, int M1, int M2>
+int wf_launch_small(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
+    if (sizeof(R) == 8 && p.small_phase) return wf_launch<R, M1, M2, (sizeof(R) == 8)>(p, l, teams_out, st);
+    return wf_launch<R, M1, M2, false>(p, l, teams_out, st);
+}
+
+}  // namespace
+
+template <typename R>
+int wf_propagate(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
+    if (p.xfer) return SSFM_ERR_UNSUPPORTED;
+#define WF_CASE(A, B) if (p.n1 == A && p.n2 == B) return wf_launch_small<R, A, B>(p, l, teams_out, st);
+    WF_CASE(128, 128) WF_CASE(128, 256) WF_CASE(256, 256) WF_CASE(256, 512) WF_CASE(512, 512) WF_CASE(512, 1024)
+    WF_CASE(1024, 1024)
+#undef WF_CASE
+    return SSFM_ERR_UNSUPPORTED;
+}
+
+template int wf_propagate<float>(const Params<float>&, const WfLaunch&, int*, cudaStream_t);
+template int wf_propagate<double>(const Params<double>&, const WfLaunch&, int*, cudaStream_t);
+
+}  // namespace ssfm

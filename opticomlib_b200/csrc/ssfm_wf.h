@@ -1,0 +1,24 @@
+// Host-side interface of the persistent whole-propagation kernel (ssfm_wf.cuh / ssfm_wf.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "ssfm_kernels.cuh"
+
+namespace ssfm {
+
+struct WfLaunch {
+    void* sync_buf;          // plan-owned scratch for barriers, mailboxes and max words (WF_SYNC_BYTES)
+    int num_sms;
+    int fixed, single, resume;
+    double h_fixed;
+    long long budget;        // steps per waveform in this call (> 0)
+    int teams_cap;           // 0 = as many teams as fit on the chip
+    cudaEvent_t ev0, ev1;    // recorded around the launch on the stream (may be null)
+};
+constexpr size_t WF_SYNC_BYTES = 1u << 20;
+
+// Runs the whole propagation of p.batch waveforms as one cooperative launch of k_wf.
+// Returns SSFM_ERR_UNSUPPORTED (no error text) when the geometry has no k_wf instantiation or one
+// waveform's team does not fit on the chip; the caller then uses the multi-launch schedule.
+template <typename R> int wf_propagate(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st);
+
+}  // namespace ssfm

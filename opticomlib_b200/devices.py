@@ -69,7 +69,8 @@ def _to_device(a: np.ndarray, tdtype, dev):
 
 # ---- FIBER / DBP --------------------------------------------------------------------------------
 def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
-                precision=None, device=None, want_log=False, chunk_waveforms=None, inplace=False, fused=True, out=None):
+                precision=None, device=None, want_log=False, chunk_waveforms=None, inplace=False, fused=True,
+                persistent=None, out=None):
     """Propagate a batch ``field[B, N]`` or ``field[B, P, N]`` (NumPy array or CUDA tensor).
 
     Rows are independent waveforms, each with its own step-size sequence (the global max of
@@ -77,6 +78,10 @@ def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
     is a CUDA tensor when a CUDA tensor was given, a host tensor for a host tensor (pass a pinned ``out=`` to
     avoid the allocation) and a NumPy array for a NumPy array.  Host inputs are streamed through the device in
     chunks so that the PCIe copies overlap the propagation.
+
+    Scheduling knobs (results agree to rounding): ``persistent`` (default on: the whole propagation is one
+    persistent kernel that keeps the waveforms in flight L2-resident; off = two launches per step),
+    ``fused`` / ``chunk_waveforms`` (multi-launch schedule only).
     """
     torch = engine._torch()
     tdtype, ndtype = _complex_dtype(precision)
@@ -88,7 +93,7 @@ def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
         if not host.is_complex():
             host = host.to(torch.complex128)
         res, info = _propagate_host_streamed(host.contiguous(), out, tdtype, dev, want_log, chunk_waveforms, fused,
-                                             (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h))
+                                             persistent, (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h))
         return (res if as_tensor else res.numpy()), info
     dev = engine.require_cuda(field.device)
     x = field.to(dtype=tdtype).contiguous()
@@ -99,16 +104,21 @@ def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
     B, P, N = (x.shape[0], 1, x.shape[1]) if x.ndim == 2 else tuple(x.shape)
     plan = engine.get_plan(N, P, B, tdtype, dev)
     plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
-    plan.set_option("fused", 1 if fused else 0)
+    _set_schedule(plan, fused, persistent)
     info = plan.propagate(x, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
     return x, info
+
+
+def _set_schedule(plan, fused=True, persistent=None):
+    plan.set_option("fused", 1 if fused else 0)
+    plan.set_option("persistent", int(bool(fused)) if persistent is None else int(bool(persistent)))
 
 
 HOST_LANES = 3                  # concurrent host->device->host pipelines (threads + streams) of the host path
 HOST_CHUNK_BYTES = 256 << 20    # target size of one chunk of rows on the device
 
 
-def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, fused, args):
+def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, fused, persistent, args):
     """Host buffers in, host buffers out: rows are cut into chunks and `HOST_LANES` worker threads, each with
     its own CUDA stream and plan, run  H2D copy -> cast -> split-step loop -> D2H copy  so that the PCIe
     transfers of one chunk overlap the propagation of another (the C call releases the GIL)."""
@@ -141,7 +151,7 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
                         x = host[r0:r1].to(dev, non_blocking=True).to(tdtype).contiguous()
                         plan = engine.get_plan(N, P, r1 - r0, tdtype, dev, lane=lane)
                         plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
-                        plan.set_option("fused", 1 if fused else 0)
+                        _set_schedule(plan, fused, persistent)
                         info = plan.propagate(x, *args, want_log=want_log)
                         out[r0:r1].copy_(x, non_blocking=True)
                         steps[r0:r1], z[r0:r1], hn[r0:r1], done[r0:r1] = info.steps, info.z, info.h_next, info.done
@@ -196,7 +206,7 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
     x = _to_device(a.reshape(1, n_pol, n), tdtype, dev)    # cast to the compute dtype on the device
     plan = engine.get_plan(n, n_pol, 1, tdtype, dev)
     plan.set_option("chunk_waveforms", 0)
-    plan.set_option("fused", 1)
+    _set_schedule(plan, True, None)
     args = (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h)
 
     bar = None

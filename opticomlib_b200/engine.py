@@ -107,6 +107,13 @@ class Plan:
                                                        ms, ctypes.c_void_p(stream)))
         return [float(v) for v in ms]
 
+    def last_timing(self):
+        """(kind, teams, kernel_ms) of the last propagate: kind 2 = persistent kernel (one launch, timed with
+        CUDA events on the launching stream), kind 1 = multi-launch schedule (kernel_ms = 0)."""
+        kind, teams, ms = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_float(0.0)
+        _lib.check(self.lib.ssfm_get_last_timing(self.handle, ctypes.byref(kind), ctypes.byref(teams), ctypes.byref(ms)))
+        return int(kind.value), int(teams.value), float(ms.value)
+
     def state(self, want_log=False) -> StepInfo:
         B = self.batch
         steps = np.empty(B, np.int32); z = np.empty(B, np.float64); hn = np.empty(B, np.float64)

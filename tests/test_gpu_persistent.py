@@ -1,0 +1,161 @@
+"""GPU parity tests of the persistent whole-propagation kernel k_wf (opticomlib_b200/csrc/ssfm_wf.cuh).
+
+The golden fixtures of the reference are 1024..4096 samples long and therefore run on the multi-launch
+schedule; k_wf adopts waveforms of 2^14 .. 2^20 samples.  Every case here is checked against the CPU oracle
+(oracle/ssfm_oracle.py, pinned to the reference) and against the multi-launch schedule on the same input.
+Tolerances are BASELINE.json's: rel-L2 <= 1e-4 (fp32), <= 1e-10 (fp64), identical step counts.
+"""
+import numpy as np
+import pytest
+
+from oracle.ssfm_oracle import oracle_fiber, oracle_dbp, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "fp64": 1e-10}
+REAL = {"fp32": np.float32, "fp64": np.float64}
+DT = 1 / 640e9
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import opticomlib_b200 as ob
+    return ob
+
+
+def _wave(n, seed, power=2e-3, n_pol=1):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / n
+    rows = []
+    for p in range(n_pol):
+        env = np.sqrt(power) * (0.55 + 0.45 * np.sign(np.sin(2 * np.pi * (37 + 5 * p) * t + 0.3)))   # OOK-like envelope
+        env = np.convolve(env, np.ones(9) / 9, mode="same")
+        rows.append(env * np.exp(2j * np.pi * 3 * t) + 2e-3 * np.sqrt(power) * (rng.standard_normal(n) + 1j * rng.standard_normal(n)))
+    return rows[0] if n_pol == 1 else np.stack(rows)
+
+
+def _kind(ob, n, n_pol, rows, precision):
+    import torch
+    from opticomlib_b200 import engine
+    td = torch.complex64 if precision == "fp32" else torch.complex128
+    return engine.get_plan(n, n_pol, rows, td, torch.device("cuda", 0)).last_timing()
+
+
+CASES = [
+    # name, log2n, kwargs
+    ("adaptive_b3", 14, dict(length=12.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.01)),
+    ("adaptive_odd", 15, dict(length=10.0, alpha=0.2, beta_2=-20.0, beta_3=0.0, gamma=2.0, phi_max=0.02)),
+    ("adaptive_16", 16, dict(length=25.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.01)),
+    ("fixed_h", 16, dict(length=3.05, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, h=0.3)),
+    ("large_phase", 14, dict(length=20.0, alpha=0.1, beta_2=-20.0, gamma=30.0, phi_max=0.3)),
+    ("gamma0", 14, dict(length=40.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=0.0)),
+    ("nodisp", 15, dict(length=30.0, alpha=0.2, gamma=2.0)),
+    ("alpha_only", 14, dict(length=10.0, alpha=0.2)),
+    ("adaptive_17", 17, dict(length=6.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.02)),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name,log2n,kw", CASES, ids=[c[0] for c in CASES])
+def test_persistent_matches_oracle_and_multilaunch(ob, name, log2n, kw, precision):
+    n = 1 << log2n
+    x = _wave(n, log2n)
+    with np.errstate(all="ignore"):
+        ref = oracle_fiber(x, DT, real=REAL[precision], **kw)
+    out, info = ob.fiber_batch(x[None, :], DT, precision=precision, persistent=True, want_log=True, **kw)
+    assert _kind(ob, n, 1, 1, precision)[0] == 2, "the persistent kernel did not run"
+    assert int(info.steps[0]) == ref["steps"]
+    assert rel_l2(out[0], ref["out"]) <= TOL[precision]
+    np.testing.assert_allclose(info.z[0], ref["z"][-1], rtol=1e-6 if precision == "fp32" else 1e-12)
+    np.testing.assert_allclose(info.h_log[0, :ref["steps"]], ref["h"], rtol=1e-3 if precision == "fp32" else 1e-10)
+    out_m, info_m = ob.fiber_batch(x[None, :], DT, precision=precision, persistent=False, **kw)
+    assert _kind(ob, n, 1, 1, precision)[0] == 1
+    assert int(info_m.steps[0]) == int(info.steps[0])
+    assert rel_l2(out[0], out_m[0]) <= (2e-6 if precision == "fp32" else 1e-13)
+    if kw.get("h") is not None:
+        assert info.z[0] == info_m.z[0]                                    # fixed-h bookkeeping is bit exact
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_persistent_dbp_two_polarisations(ob, precision):
+    n = 1 << 14
+    x = _wave(n, 5, n_pol=2)
+    kw = dict(length=15.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.01)
+    with np.errstate(all="ignore"):
+        ref = oracle_dbp(x, DT, real=REAL[precision], **kw)
+    out, info = ob.dbp_batch(x[None], DT, precision=precision, persistent=True, **kw)
+    assert _kind(ob, n, 2, 1, precision)[0] == 2
+    assert int(info.steps[0]) == ref["steps"]
+    assert rel_l2(out[0], ref["out"]) <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_more_waveforms_than_teams_with_diverging_step_counts(ob, precision):
+    """2^16 samples: 18 (fp64) teams of 16 CTAs are in flight; 45 waveforms of different power are handed out
+    dynamically and finish after different numbers of steps."""
+    n, rows = 1 << 16, 45
+    base = _wave(n, 11)
+    scales = 0.2 + 2.3 * np.random.default_rng(3).random(rows)
+    x = np.stack([np.sqrt(s) * np.roll(base, 997 * i) for i, s in enumerate(scales)])
+    kw = dict(length=8.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.01)
+    out, info = ob.fiber_batch(x, DT, precision=precision, persistent=True, **kw)
+    kind, teams, ms = _kind(ob, n, 1, rows, precision)
+    assert kind == 2 and 1 <= teams < rows and ms > 0
+    out_m, info_m = ob.fiber_batch(x, DT, precision=precision, persistent=False, **kw)
+    assert np.array_equal(info.steps, info_m.steps) and info.done.all()
+    assert len(set(info.steps.tolist())) > 5
+    assert rel_l2(out, out_m) <= (2e-6 if precision == "fp32" else 1e-13)
+    for i in (0, 7, 44):
+        with np.errstate(all="ignore"):
+            ref = oracle_fiber(x[i], DT, real=REAL[precision], **kw)
+        assert int(info.steps[i]) == ref["steps"]
+        assert rel_l2(out[i], ref["out"]) <= TOL[precision]
+    # capping the number of teams changes the schedule, not the numbers
+    from opticomlib_b200 import engine
+    import torch
+    td = torch.complex64 if precision == "fp32" else torch.complex128
+    plan = engine.get_plan(n, 1, rows, td, torch.device("cuda", 0))
+    plan.set_option("teams", 3)
+    try:
+        out_3, info_3 = ob.fiber_batch(x, DT, precision=precision, persistent=True, **kw)
+        assert plan.last_timing()[1] == 3
+    finally:
+        plan.set_option("teams", 0)
+    assert np.array_equal(out_3, out) and np.array_equal(info_3.steps, info.steps)
+
+
+def test_persistent_step_budget_and_resume(ob):
+    """return_steps=True drives the kernel one step per call (max_steps=1, resume): the trajectory must equal
+    the oracle's snapshots, and the final field the uninterrupted run."""
+    n = 1 << 14
+    x = _wave(n, 21)
+    kw = dict(length=5.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.02)
+    ob.gv.dt = DT; ob.gv.fs = 1 / DT
+    for precision in ("fp64", "fp32"):
+        z, traj = ob.FIBER(ob.optical_signal(x), return_steps=True, precision=precision, **kw)
+        assert _kind(ob, n, 1, 1, precision)[0] == 2
+        with np.errstate(all="ignore"):
+            ref = oracle_fiber(x, DT, real=REAL[precision], return_steps=True, **kw)
+        assert len(z) == ref["steps"] + 1 and traj.shape == (len(z), n) and z[0] == 0.0
+        np.testing.assert_allclose(z[1:], ref["z"], rtol=1e-3 if precision == "fp32" else 1e-10)
+        for k in (1, len(z) // 2, len(z) - 1):
+            assert rel_l2(traj[k], ref["traj"][k]) <= TOL[precision]
+        full = ob.FIBER(ob.optical_signal(x), precision=precision, **kw)
+        assert rel_l2(traj[-1], full.signal) <= (2e-6 if precision == "fp32" else 1e-13)
+
+
+def test_single_waveform_2_20(ob):
+    """BASELINE config #2 geometry (one 2^20-sample waveform = one team of 256 CTAs), a few adaptive steps."""
+    n = 1 << 20
+    x = _wave(n, 9, power=20e-3)
+    kw = dict(length=1.2, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.01)
+    for precision in ("fp64", "fp32"):
+        with np.errstate(all="ignore"):
+            ref = oracle_fiber(x, DT, real=REAL[precision], **kw)
+        out, info = ob.fiber_batch(x[None, :], DT, precision=precision, persistent=True, **kw)
+        assert _kind(ob, n, 1, 1, precision)[0] == 2
+        assert int(info.steps[0]) == ref["steps"] and ref["steps"] >= 3
+        assert rel_l2(out[0], ref["out"]) <= TOL[precision]
