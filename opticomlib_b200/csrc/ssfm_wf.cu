@@ -37,24 +37,38 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
         per_sm = v;
     }
     const long long total = (long long)p.n_pol * (p.n2 / GEO::T);       // CTAs of one team
-    long long teams = (long long)per_sm * l.num_sms / total;
+    // placement of k_wf: teams no larger than the SM count share groups of `total` SMs (one CTA of each per SM)
+    long long teams = total <= l.num_sms ? (l.num_sms / total) * per_sm : (long long)per_sm * l.num_sms / total;
     if (teams > p.batch) teams = p.batch;
     if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
     if (teams < 1) return SSFM_ERR_UNSUPPORTED;                          // one waveform does not fit on the chip
+    // waveforms multiplexed per team: enough to hide the barrier latency, few enough to stay L2-resident
+    const size_t wf_bytes = (size_t)p.n_pol * (size_t)p.n * (sizeof(typename cx_of<R>::type) + sizeof(R));
+    long long nslots = l.slots > 0 ? l.slots : 1;   // measured: one slot (stash in shared memory) is fastest
+    if (nslots > WF_MAX_SLOTS) nslots = WF_MAX_SLOTS;
+    while (nslots > 1 && ((size_t)teams * nslots * wf_bytes > ((size_t)72 << 20) || teams * (nslots - 1) >= p.batch)) --nslots;
     if (getenv("SSFM_DEBUG"))
-        fprintf(stderr, "[ssfm] k_wf<%d,%d,%d,%d>: smem %zu, %d CTAs/SM, team %lld CTAs, %lld teams\n", (int)sizeof(R), M1, M2,
-                (int)SMALL, (size_t)GEO::smem, per_sm, total, teams);
+        fprintf(stderr, "[ssfm] k_wf<%d,%d,%d,%d>: smem %zu, %d CTAs/SM, team %lld CTAs, %lld teams x %lld slots\n", (int)sizeof(R),
+                M1, M2, (int)SMALL, (size_t)GEO::smem, per_sm, total, teams, nslots);
 
-    // sync scratch: [bar: teams x 128 B][mail: teams x 128 B][next_wf: 128 B][slots: teams x 2 x total x 16 B]
-    const size_t need = (size_t)teams * 256 + 128 + (size_t)teams * 2 * total * 16;
+    // sync scratch: [sm_cnt: 4 KB][grid_bar: 128 B][next_wf: 128 B][bar: ts x 128 B][mail: ts x 128 B]
+    //               [max words: ts x 2 x total x 16 B],  ts = teams x slots
+    const size_t head = 4096 + 256;
+    const size_t ts = (size_t)teams * nslots;
+    const size_t need = head + ts * 256 + ts * 2 * total * 16;
     if (need > WF_SYNC_BYTES) return SSFM_ERR_UNSUPPORTED;
     WF_TRY(cudaMemsetAsync(l.sync_buf, 0, need, st));
     WfArgs<R> a;
     char* sb = (char*)l.sync_buf;
-    a.bar = (unsigned int*)sb;
-    a.mail = (unsigned long long*)(sb + (size_t)teams * 128);
-    a.next_wf = (unsigned int*)(sb + (size_t)teams * 256);
-    a.slots = (unsigned long long*)(sb + (size_t)teams * 256 + 128);
+    a.sm_cnt = (unsigned int*)sb;
+    a.grid_bar = (unsigned int*)(sb + 4096);
+    a.next_wf = (unsigned int*)(sb + 4096 + 128);
+    a.bar = (unsigned int*)(sb + head);
+    a.mail = (unsigned long long*)(sb + head + ts * 128);
+    a.slots = (unsigned long long*)(sb + head + ts * 256);
+    a.n_slots = (int)nslots;
+    a.occ = per_sm;
+    a.placement = l.placement;
     a.budget = l.budget;
     a.n_teams = (int)teams;
     a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
@@ -62,10 +76,11 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     Params<R> pp = p;
     void* args[2] = {(void*)&pp, (void*)&a};
     if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
-    WF_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(teams * total)), dim3(GEO::NT), args, GEO::smem, st));
+    // the grid fills every CTA slot of the chip (co-residency is what the cooperative launch guarantees)
+    WF_TRY(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)(per_sm * l.num_sms)), dim3(GEO::NT), args, GEO::smem, st));
     if (l.ev1) WF_TRY(cudaEventRecord(l.ev1, st));
     ++ssfm_launches;
-    if (teams_out) *teams_out = (int)teams;
+    if (teams_out) *teams_out = (int)(teams * nslots);
     return SSFM_OK;
 }
 

@@ -2,36 +2,49 @@
 //
 // Reference loop: opticomlib/devices.py:1155-1196.  The multi-launch schedule of ssfm_kernels.cuh streams
 // every waveform through HBM twice per step (k_row, k_col_mid).  Here a TEAM of `total` co-resident CTAs
-// (total = n_pol * N/4096) adopts one waveform and carries it through ALL of its steps before it takes
-// the next one, so that
-//   * the field of the waveforms in flight (teams x N samples: a few MiB .. 37 MiB) never leaves the
-//     126 MB L2 -- HBM sees one read and one write of the field per PROPAGATION, not four per step;
-//   * the Kerr-phase stash of a tile lives in the shared memory of the CTA that owns the tile (the same
-//     CTA visits the same tile every step): the stash traffic of the multi-launch schedule is gone;
+// (total = n_pol * N/4096) adopts waveforms and carries each through ALL of its steps, so that
+//   * the field of the waveforms in flight (teams x slots x N samples: a few MiB .. ~50 MiB) never leaves
+//     the 126 MB L2 -- HBM sees one read and one write of the field per PROPAGATION, not four per step;
 //   * pass tables and the sincos table are loaded once per CTA; there are no launches, tickets or host
 //     polls inside a propagation, and the step-size controller runs redundantly in every CTA.
 //
 // Per step each CTA runs a ROW phase (G rows of the N1 x N2 matrix: forward transform, exp(D~ h),
 // inverse transform) and a COLUMN phase (T columns: inverse transform, 1/N, max|A|^2 -> team exchange
 // -> controller -> merged Kerr rotation of the second half step of step s and the first half step of
-// step s+1 -> forward transform), separated by team barriers (a monotonic arrival counter in L2).
-// Loads of the field bypass L1 (ld.global.cg): the data was written by other SMs one phase earlier.
+// step s+1 -> forward transform).  The phases of one waveform are separated by team barriers (a monotonic
+// arrival counter in L2, release-arrive / acquire-wait).
+//
+// Slots.  A team can multiplex `n_slots` waveforms ("slots", each with its own barrier counter): at a barrier
+// a CTA holds no live registers, so it can arrive for slot A, run the next phase of slot B and come back.
+// With n_slots == 1 (the default) the Kerr-phase stash of a tile never leaves the shared memory of the CTA
+// that owns the tile; with more slots it travels through L2 (cp.async prefetch at the start of the column
+// phase).  Measured on B200 (profiles/): multiplexing removes the barrier waits (5 k -> 2 k cycles) but the
+// time moves into the max|A|^2 exchange in the middle of the column phase, where the registers ARE live, and
+// the extra stash traffic costs more than is gained -- one slot with the stash in shared memory is fastest.
 //
 // Everything here is FP64/FP32 FMA-pipe arithmetic on L2-resident data; no tensor cores (no dense
-// contraction on this path).
+// contraction on this path).  Loads of the field bypass L1 (ld.global.cg): the data was written by other
+// SMs one phase earlier.
 #pragma once
 #include "ssfm_kernels.cuh"
 
 namespace ssfm {
 
+constexpr int WF_MAX_SLOTS = 4;
+
 template <typename R>
 struct WfArgs {
-    unsigned int* bar;            // [n_teams][32]  monotonic arrival counter of the team barrier (one 128-B line each)
-    unsigned long long* mail;     // [n_teams][16]  (sequence << 32 | waveform) handed out by CTA 0 of the team
-    unsigned long long* slots;    // [n_teams][2][total][2]  self-validating max words, double-buffered by exchange parity
+    unsigned int* bar;            // [n_teams][slots][32]  monotonic arrival counters (one 128-B line each)
+    unsigned long long* mail;     // [n_teams][slots][16]  (sequence << 32 | waveform) handed out by CTA 0 of the team
+    unsigned long long* slots;    // [n_teams][slots][2][total][2]  self-validating max words, double-buffered by parity
     unsigned int* next_wf;        // next waveform to hand out (dynamic assignment: step counts differ per waveform)
+    unsigned int* sm_cnt;         // [1024] CTAs of this launch that registered on each SM (team placement)
+    unsigned int* grid_bar;       // arrival counter of the one grid-wide barrier that ends the registration
     long long budget;             // stop every waveform after this many steps in this call (max_steps of the C-ABI)
+    int occ;                      // CTAs per SM (the grid is occ x num_sms, all co-resident)
+    int placement;                // 1 = SM-aware team placement (default), 0 = by blockIdx (experiments)
     int n_teams;
+    int n_slots;                  // waveforms multiplexed by one team (1..WF_MAX_SLOTS)
     int fixed, single, resume;
     R h_fixed;
 };
@@ -54,9 +67,32 @@ struct wf_geom {
     static constexpr size_t smem = TABS ? smem_full : smem_full - sizeof(C) * (size_t)(TAB1 + TAB2);
 };
 
-__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
-    return *reinterpret_cast<const volatile unsigned int*>(p);
+// release-arrive / relaxed poll + acquire fence (PTX memory model, gpu scope).  The release is cumulative: it also
+// covers the stores of the other threads of the CTA that were ordered before it by the preceding bar.sync -- the
+// same reasoning cooperative-groups grid synchronisation rests on, without the sequentially-consistent fence.
+__device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
+enum { WF_GRAB = 0, WF_ROW = 1, WF_COL = 2, WF_END = 3 };
+
+template <typename R>
+struct WfSlot {                   // per-slot state of a team (uniform over the CTA and over the team)
+    unsigned int w, bar_target, xchg, seq;
+    int state, steps;
+    long long taken;
+    R z, h;
+};
 
 template <typename R, int M1, int M2, bool SMALL>
 __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> p, WfArgs<R> a) {
@@ -64,6 +100,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     typedef wf_geom<R, M1, M2> GEO;
     constexpr int E = GEO::E, NT = GEO::NT, T = GEO::T, G = GEO::G, PM = GEO::PM;
     static_assert(points_per_thread<R>::value == 16, "k_wf assumes 16 points per thread");
+    static_assert((T * sizeof(R)) % 16 == 0, "stash rows of a tile are copied in 16-byte pieces");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
     __shared__ unsigned int s_w;
@@ -72,14 +109,56 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     C* tw1s = xb + GEO::XB;                                    // pass tables of the N1-point (column) transforms
     C* tw2s = tw1s + (TABS ? GEO::TAB1 : 0);                   // ... of the N2-point (row) transforms when N2 != N1
     C* sct = tw2s + (TABS ? GEO::TAB2 : 0);                    // sincos table
-    R* st_sm = reinterpret_cast<R*>(sct + SC_N);               // [E][NT] Kerr phase of the current step of MY tile
+    R* st_sm = reinterpret_cast<R*>(sct + SC_N);               // [M1][T] staging of the Kerr-phase stash of the tile
     const C* tw1 = TABS ? tw1s : p.tw_col;
     const C* tw2 = TABS ? ((M1 == M2) ? tw1s : tw2s) : p.tw_row;
 
     const int tid = threadIdx.x;
-    const int team = blockIdx.x % a.n_teams, me = blockIdx.x / a.n_teams;
     const int tiles = p.n2 / T;                                // column tiles (= row groups) per polarisation
     const unsigned total = (unsigned)(tiles * p.n_pol);        // CTAs per team
+
+    // ---- team placement.  A team is bulk-synchronous, so its CTAs should run at the same speed, and a CTA's
+    // speed depends on what the OTHER CTAs of its SM are doing.  The grid fills every CTA slot of the chip; each
+    // CTA registers on its SM, and once all have, teams are laid out so that the `occ` CTAs of an SM belong to
+    // `occ` different teams that share the same group of `total` SMs: every CTA of a team then has exactly the
+    // same neighbours (the lock-stepped CTAs of the sibling teams).  Teams larger than the chip's SM count take
+    // consecutive slots instead (all CTAs of an SM in the same team).
+    __shared__ unsigned int s_slot, s_rank;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (tid == 0) {
+        s_rank = 0u;
+        s_slot = atomicAdd(a.sm_cnt + smid, 1u);
+        __threadfence();
+        atomicAdd(a.grid_bar, 1u);
+        while (ld_relaxed_u32(a.grid_bar) < gridDim.x) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+    {
+        unsigned int lower = 0;                                // SMs with a smaller id that host CTAs of this launch
+        for (unsigned int i = tid; i < smid; i += NT) lower += (ld_relaxed_u32(a.sm_cnt + i) != 0u) ? 1u : 0u;
+        if (lower) atomicAdd(&s_rank, lower);
+    }
+    __syncthreads();
+    const unsigned int n_sm = gridDim.x / (unsigned)a.occ;
+    int team, me;
+    if (!a.placement) {
+        team = (int)(blockIdx.x % (unsigned)a.n_teams);
+        me = (int)(blockIdx.x / (unsigned)a.n_teams);
+        if (me >= (int)total) team = a.n_teams;
+    } else if (total <= n_sm) {
+        const unsigned int grp = s_rank / total;
+        team = (int)(grp * (unsigned)a.occ + s_slot);
+        me = (int)(s_rank % total);
+        if (grp >= n_sm / total) team = a.n_teams;             // SMs beyond the last full group stay idle
+    } else {
+        const unsigned int vid = s_rank * (unsigned)a.occ + s_slot;
+        team = (int)(vid / total);
+        me = (int)(vid % total);
+    }
+    if (team >= a.n_teams) return;
+
     const int pol = me / tiles, tile = me % tiles;
     const int c = tid % T, t = tid / T;                        // column phase: column c of the tile, thread t of its transform
     const int n2 = tile * T + c;
@@ -92,162 +171,232 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     }
     for (int i = tid; i < SC_N; i += NT) sct[i] = p.tw_col[GEO::TAB1 + i];
 
-    unsigned int bar_target = 0, xchg = 0, seq = 0;
-    unsigned int* bar = a.bar + team * 32;
+#ifdef SSFM_WF_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pn = 0;
+#define WF_T0(name) const long long name = clock64()
+#define WF_ACC(i, name) prof[i] += clock64() - name
+#else
+#define WF_T0(name) do { } while (0)
+#define WF_ACC(i, name) do { } while (0)
+#endif
 
-    auto team_barrier = [&]() {
-        __syncthreads();
+    // split team barrier of slot s: arrive after the phase's stores, wait before the next phase's loads
+    auto bar_arrive = [&](WfSlot<R>& S, int s) {
+        __syncthreads();                                        // every thread's stores are ordered before the release
+        S.bar_target += total;
+        if (tid == 0) red_release_add_u32(a.bar + (size_t)(team * a.n_slots + s) * 32, 1u);
+    };
+    auto bar_wait = [&](const WfSlot<R>& S, int s) {
         if (tid == 0) {
-            bar_target += total;
-            __threadfence();
-            atomicAdd(bar, 1u);
-            while ((int)(ld_volatile_u32(bar) - bar_target) < 0) __nanosleep(20);
-            __threadfence();
+            const unsigned int* b = a.bar + (size_t)(team * a.n_slots + s) * 32;
+            while ((int)(ld_relaxed_u32(b) - S.bar_target) < 0) { }
+            fence_acq_rel_gpu();
         }
         __syncthreads();
     };
 
     // max over the team of a per-thread value (NaN wins, like numpy's max): block reduction, one self-validating
     // word (two for double) per CTA -- {32 value bits | 32-bit exchange tag}: the flag travels with the data, so no
-    // fence and no atomic is needed -- and every thread polls a share of the team's words.
-    auto team_max = [&](R pm) -> R {
+    // fence and no atomic is needed -- and the first warps poll the team's words.
+    auto team_max = [&](WfSlot<R>& S, int s, R pm) -> R {
         constexpr int NW = sizeof(R) / 4;
-        ++xchg;
-        const unsigned long long tag = (unsigned long long)xchg;
-        volatile unsigned long long* wf = a.slots + ((size_t)(team * 2 + (xchg & 1u)) * total) * 2;
-        const R mine = block_max_bits<R>(pm, red);
-        const unsigned long long bits = ord_bits(mine);
-        if (tid < NW) {
-            const unsigned long long part = (NW == 1) ? (bits & 0xffffffffull) : (tid == 0 ? (bits >> 32) : (bits & 0xffffffffull));
-            wf[me * 2 + tid] = (part << 32) | tag;
-        }
-        unsigned long long best = 0ull;
+        ++S.xchg;
+        const unsigned long long tag = (unsigned long long)S.xchg;
+        volatile unsigned long long* wf = a.slots + ((size_t)((team * a.n_slots + s) * 2 + (S.xchg & 1u)) * total) * 2;
+        const int warp = tid >> 5, lane = tid & 31;
+        unsigned long long bits = ord_bits(pm);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
+        if (lane == 0) red[warp] = bits;
+        __syncthreads();
         const int nwords = (int)total * NW;
-        for (int base = 0; base < nwords; base += NT) {         // uniform trip count; lanes pair up (hi, lo) for double
-            const int idx = base + tid;
-            const bool have = idx < nwords;
-            unsigned long long x = tag;
-            if (have) {
-                for (;;) {
-                    x = wf[(idx / NW) * 2 + (idx % NW)];
-                    if ((x & 0xffffffffull) == tag) break;
-                    __nanosleep(20);
+        unsigned long long best = 0ull;
+        if (warp * 32 < nwords) {                               // the first warps publish (warp 0) and poll
+            if (warp == 0) {
+                bits = lane < NT / 32 ? red[lane] : 0ull;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
+                bits = __shfl_sync(0xffffffffu, bits, 0);
+                if (lane < NW) {
+                    const unsigned long long part = (NW == 1) ? (bits & 0xffffffffull) : (lane == 0 ? (bits >> 32) : (bits & 0xffffffffull));
+                    wf[me * 2 + lane] = (part << 32) | tag;
                 }
             }
-            unsigned long long val = have ? (x >> 32) : 0ull;
-            if (NW == 2) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, val, 1);
-                val = (tid & 1) ? 0ull : ((val << 32) | other);
+            for (int base = 0; base < nwords; base += NT) {     // lanes pair up (hi, lo) for double
+                const int idx = base + tid;
+                const bool have = idx < nwords;
+                unsigned long long x = tag;
+                if (have) {
+                    for (;;) {
+                        x = wf[(idx / NW) * 2 + (idx % NW)];
+                        if ((x & 0xffffffffull) == tag) break;
+                    }
+                }
+                unsigned long long val = have ? (x >> 32) : 0ull;
+                if (NW == 2) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, val, 1);
+                    val = (tid & 1) ? 0ull : ((val << 32) | other);
+                }
+                best = val > best ? val : best;
             }
-            best = val > best ? val : best;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
         }
-        __syncthreads();                                        // red[0] of the first reduction has been read by everyone
-        return block_max_bits<R>(from_bits<R>(best), red);
+        __syncthreads();                                        // red[] of the block reduction has been consumed
+        if (lane == 0) red[warp] = best;
+        __syncthreads();
+        best = red[0];
+#pragma unroll
+        for (int i = 1; i < NT / 32; ++i) best = red[i] > best ? red[i] : best;
+        __syncthreads();                                        // red[] is free for the next exchange
+        return from_bits<R>(best);
     };
 
-    for (;;) {
-        // ------------------------------------------------------------------ next waveform of this team
-        ++seq;
-        if (tid == 0) {
-            volatile unsigned long long* mb = a.mail + team * 16;
-            unsigned int wn;
-            if (me == 0) {
-                wn = atomicAdd(a.next_wf, 1u);
-                *mb = ((unsigned long long)seq << 32) | (unsigned long long)wn;
-            } else {
-                unsigned long long m;
-                for (;;) { m = *mb; if ((unsigned int)(m >> 32) == seq) break; __nanosleep(40); }
-                wn = (unsigned int)m;
-            }
-            s_w = wn;
-        }
-        __syncthreads();
-        const unsigned int w = s_w;
-        __syncthreads();
-        if (w >= (unsigned int)p.batch) break;
-
-        C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + pol) * p.n;
-        C* __restrict__ rbase = rowp + (size_t)k1 * p.n2;
-        C v[E];
-        R z, h;
-        int steps;
-        long long taken = 0;
-
-        // ------------------------------------------------------------------ prologue: first step size, first Kerr
-        // half step (devices.py:1155-1161, 1175-1177), forward column transforms, four-step twiddle
+    const bool keep = a.n_slots == 1;                           // the stash of my tile stays in shared memory
+    WfSlot<R> sl[WF_MAX_SLOTS];
 #pragma unroll
-        for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * p.n2 + n2);
-        if (a.resume) {
-            const Ctrl cs = p.ctrl[w];
-            if (cs.done) continue;
-            z = (R)cs.z; h = (R)cs.h; steps = cs.steps;
-        } else {
-            R h0;
-            if (a.fixed) h0 = a.h_fixed;
-            else if (a.single) h0 = p.length;                   // no dispersion or no Kerr effect: one step
-            else {
-                R pm = 0;
-                bool nan = false;
-#pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
-                    nan |= (pw != pw);
-                    pm = pw > pm ? pw : pm;
+    for (int s = 0; s < WF_MAX_SLOTS; ++s) {
+        sl[s].w = 0u; sl[s].bar_target = 0u; sl[s].xchg = 0u; sl[s].seq = 0u;
+        sl[s].state = s < a.n_slots ? WF_GRAB : WF_END; sl[s].steps = 0; sl[s].taken = 0; sl[s].z = 0; sl[s].h = 0;
+    }
+    int live = a.n_slots;
+
+    while (live > 0) {
+        for (int s = 0; s < a.n_slots; ++s) {
+            WfSlot<R>& S = sl[s];
+            if (S.state == WF_END) continue;
+
+            if (S.state == WF_GRAB) {
+                // ---------------------------------------------------------- next waveform of this slot
+                ++S.seq;
+                if (tid == 0) {
+                    volatile unsigned long long* mb = a.mail + (size_t)(team * a.n_slots + s) * 16;
+                    unsigned int wn;
+                    if (me == 0) {
+                        wn = atomicAdd(a.next_wf, 1u);
+                        *mb = ((unsigned long long)S.seq << 32) | (unsigned long long)wn;
+                    } else {
+                        unsigned long long m;
+                        for (;;) { m = *mb; if ((unsigned int)(m >> 32) == S.seq) break; __nanosleep(40); }
+                        wn = (unsigned int)m;
+                    }
+                    s_w = wn;
                 }
-                if (nan) pm = pw_nan<R>();
-                h0 = p.phi_max / mul_rn(p.abs_gamma, team_max(pm));
-            }
-            h = (p.length < h0) ? p.length : h0;                // python min(h_, length)
-            z = 0; steps = 0;
-            const int done0 = !((R)0 < p.length) || a.budget <= 0;
-            if (me == 0 && tid == 0) {
-                Ctrl& cs = p.ctrl[w];
-                cs.z = 0.0; cs.h = (double)h; cs.pmax = 0ull; cs.steps = 0; cs.arrived = 0u; cs.done = !((R)0 < p.length);
-            }
-            if (done0) continue;
-        }
-        if (p.has_nl) {
-            const R hh = h / (R)2;                              // h_/2
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                const R pw = v[q].x * v[q].x + v[q].y * v[q].y; // |A|^2
-                const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // (h_/2) * (gamma |A|^2)
-                st_sm[q * NT + tid] = ph;
-                R s, co; kerr_sincos<SMALL>(ph, sct, &s, &co);
-                v[q] = cmul(v[q], mk<R>(co, s));
-            }
-        }
-        fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
-        apply_fourstep<false, R, E, M1>(p, v, n2, t);
-#pragma unroll
-        for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
-        team_barrier();
+                __syncthreads();
+                const unsigned int w = s_w;
+                __syncthreads();
+                if (w >= (unsigned int)p.batch) { S.state = WF_END; --live; continue; }
+                S.w = w; S.taken = 0;
 
-        for (;;) {
-            // -------------------------------------------------------------- row phase (devices.py:1178-1180)
+                // ---------------------------------------------------------- prologue: first step size, first Kerr
+                // half step (devices.py:1155-1161, 1175-1177), forward column transforms, four-step twiddle
+                C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + pol) * p.n;
+                R* __restrict__ strow = p.stash + ((size_t)w * p.n_pol + pol) * p.n;
+                C v[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
-            fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
-            {
-                const int half = p.n >> 1;
+                for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * p.n2 + n2);
+                if (a.resume) {
+                    const Ctrl cs = p.ctrl[w];
+                    if (cs.done) continue;                      // stays in WF_GRAB: next waveform
+                    S.z = (R)cs.z; S.h = (R)cs.h; S.steps = cs.steps;
+                } else {
+                    R h0;
+                    if (a.fixed) h0 = a.h_fixed;
+                    else if (a.single) h0 = p.length;           // no dispersion or no Kerr effect: one step
+                    else {
+                        R pm = 0;
+                        bool nan = false;
 #pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    const int k2 = tr + q * (M2 / E);
-                    int k = k1 + p.n1 * k2;                     // transposed-order bin index
-                    k = (k < half) ? k : k - p.n;               // fftfreq ordering
-                    const R wk = (R)((double)k * p.wscale);     // rad/ps (see Params::wscale)
-                    const R dim = add_rn(mul_rn(p.c2, mul_rn(wk, wk)), mul_rn(p.c3, cube_r(wk)));
-                    const R ph = mul_rn(dim, h);
-                    R s, co; sincos_r(ph, sct, &s, &co);
-                    v[q] = cmul(v[q], mk<R>(co, s));
+                        for (int q = 0; q < E; ++q) {
+                            const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                            nan |= (pw != pw);
+                            pm = pw > pm ? pw : pm;
+                        }
+                        if (nan) pm = pw_nan<R>();
+                        h0 = p.phi_max / mul_rn(p.abs_gamma, team_max(S, s, pm));
+                    }
+                    S.h = (p.length < h0) ? p.length : h0;      // python min(h_, length)
+                    S.z = 0; S.steps = 0;
+                    const int done0 = !((R)0 < p.length) || a.budget <= 0;
+                    if (me == 0 && tid == 0) {
+                        Ctrl& cs = p.ctrl[w];
+                        cs.z = 0.0; cs.h = (double)S.h; cs.pmax = 0ull; cs.steps = 0; cs.arrived = 0u; cs.done = !((R)0 < p.length);
+                    }
+                    if (done0) continue;
                 }
-            }
-            fft_passes<R, M2, +1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+                if (p.has_nl) {
+                    const R hh = S.h / (R)2;                    // h_/2
 #pragma unroll
-            for (int q = 0; q < E; ++q) rbase[tr + q * (M2 / E)] = v[q];
-            team_barrier();
+                    for (int q = 0; q < E; ++q) {
+                        const R pw = v[q].x * v[q].x + v[q].y * v[q].y; // |A|^2
+                        const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // (h_/2) * (gamma |A|^2)
+                        if (keep) st_sm[(t + q * (M1 / E)) * T + c] = ph;
+                        else strow[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = ph;
+                        R sn, co; kerr_sincos<SMALL>(ph, sct, &sn, &co);
+                        v[q] = cmul(v[q], mk<R>(co, sn));
+                    }
+                }
+                fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                apply_fourstep<false, R, E, M1>(p, v, n2, t);
+#pragma unroll
+                for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
+                bar_arrive(S, s);
+                S.state = WF_ROW;
+                continue;
+            }
 
-            // -------------------------------------------------------------- column phase: end of step s
+            C* __restrict__ rowp = p.field + ((size_t)S.w * p.n_pol + pol) * p.n;
+            if (S.state == WF_ROW) {
+                // ---------------------------------------------------------- row phase (devices.py:1178-1180)
+                WF_T0(t_r0);
+                bar_wait(S, s);
+                WF_ACC(0, t_r0);
+                C* __restrict__ rbase = rowp + (size_t)k1 * p.n2;
+                const R h = S.h;
+                C v[E];
+#pragma unroll
+                for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
+                fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+                {
+                    const int half = p.n >> 1;
+#pragma unroll
+                    for (int q = 0; q < E; ++q) {
+                        const int k2 = tr + q * (M2 / E);
+                        int k = k1 + p.n1 * k2;                 // transposed-order bin index
+                        k = (k < half) ? k : k - p.n;           // fftfreq ordering
+                        const R wk = (R)((double)k * p.wscale); // rad/ps (see Params::wscale)
+                        const R dim = add_rn(mul_rn(p.c2, mul_rn(wk, wk)), mul_rn(p.c3, cube_r(wk)));
+                        const R ph = mul_rn(dim, h);
+                        R sn, co; sincos_r(ph, sct, &sn, &co);
+                        v[q] = cmul(v[q], mk<R>(co, sn));
+                    }
+                }
+                fft_passes<R, M2, +1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+#pragma unroll
+                for (int q = 0; q < E; ++q) rbase[tr + q * (M2 / E)] = v[q];
+                bar_arrive(S, s);
+                S.state = WF_COL;
+                WF_ACC(1, t_r0);
+                continue;
+            }
+
+            // -------------------------------------------------------------- column phase: end of step s ...
+            WF_T0(t_c0);
+            bar_wait(S, s);
+            WF_ACC(2, t_c0);
+            R* __restrict__ strow = p.stash + ((size_t)S.w * p.n_pol + pol) * p.n;
+            if (p.has_nl && !keep) {                            // Kerr phase of this tile: L2 -> shared memory, in flight
+                constexpr int PIECES = (int)(T * sizeof(R) / 16);       // 16-byte pieces per tile row
+                constexpr int PER = 16 / (int)sizeof(R);
+                for (int i = tid; i < M1 * PIECES; i += NT) {
+                    const int r = i / PIECES, pc = i % PIECES;
+                    cp_async_cg16(st_sm + r * T + pc * PER, strow + (size_t)r * p.n2 + tile * T + pc * PER);
+                }
+                cp_async_commit();
+            }
+            const R z = S.z, h = S.h;
+            const int steps = S.steps;
+            C v[E];
 #pragma unroll
             for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * p.n2 + n2);
             apply_fourstep<true, R, E, M1>(p, v, n2, t);
@@ -266,26 +415,38 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                     pm = pw > pm ? pw : pm;
                 }
                 if (nan) pm = pw_nan<R>();
-                pmax = team_max(pm);
+                WF_T0(t_x0);
+                pmax = team_max(S, s, pm);
+                WF_ACC(3, t_x0);
             }
             const CtrlNext<R> nx = controller_next<R>(p, z, h, steps, pmax);
-            ++taken;
-            const bool stop = nx.done || taken >= a.budget;
+            ++S.taken;
+#ifdef SSFM_WF_PROFILE
+            ++pn;
+#endif
+            const bool stop = nx.done || S.taken >= a.budget;
             if (me == 0 && tid == 0) {
-                Ctrl& cs = p.ctrl[w];
-                if (p.hlog && steps < p.hlog_cap) p.hlog[(size_t)w * p.hlog_cap + steps] = (double)h;
+                Ctrl& cs = p.ctrl[S.w];
+                if (p.hlog && steps < p.hlog_cap) p.hlog[(size_t)S.w * p.hlog_cap + steps] = (double)h;
                 cs.z = (double)nx.z; cs.h = (double)nx.h; cs.steps = steps + 1; cs.done = nx.done;
+            }
+            if (!keep) {
+                cp_async_wait_all();
+                __syncthreads();                                // the staged stash was copied by other threads
             }
             if (stop) {                                         // second Kerr half step, time domain out
 #pragma unroll
                 for (int q = 0; q < E; ++q) {
                     if (p.has_nl) {
-                        R s, co; kerr_sincos<SMALL>(st_sm[q * NT + tid], sct, &s, &co);
-                        v[q] = cmul(v[q], mk<R>(co, s));
+                        R sn, co; kerr_sincos<SMALL>(st_sm[(t + q * (M1 / E)) * T + c], sct, &sn, &co);
+                        v[q] = cmul(v[q], mk<R>(co, sn));
                     }
                     rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
                 }
-                break;
+                S.state = WF_GRAB;
+                __syncthreads();                                // st_sm / xb are free for the next phase
+                WF_ACC(4, t_c0);
+                continue;
             }
             // -------------------------------------------------------------- ... and start of step s+1
             if (p.has_nl) {
@@ -294,20 +455,28 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 for (int q = 0; q < E; ++q) {
                     const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
                     const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // first half step of the next step
-                    const R tot = st_sm[q * NT + tid] + ph;         // + second half step of this one
-                    st_sm[q * NT + tid] = ph;
-                    R s, co; kerr_sincos<SMALL>(tot, sct, &s, &co);
-                    v[q] = cmul(v[q], mk<R>(co, s));
+                    const R tot = st_sm[(t + q * (M1 / E)) * T + c] + ph;   // + second half step of this one
+                    if (keep) st_sm[(t + q * (M1 / E)) * T + c] = ph;   // each thread re-reads only what it wrote itself
+                    else strow[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = ph;
+                    R sn, co; kerr_sincos<SMALL>(tot, sct, &sn, &co);
+                    v[q] = cmul(v[q], mk<R>(co, sn));
                 }
             }
             fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
             apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
             for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
-            z = nx.z; h = nx.h; ++steps;
-            team_barrier();
+            S.z = nx.z; S.h = nx.h; S.steps = steps + 1;
+            bar_arrive(S, s);
+            S.state = WF_ROW;
+            WF_ACC(4, t_c0);
         }
     }
+#ifdef SSFM_WF_PROFILE
+    if (tid == 0 && me == 1 && team < 2 && pn > 0)
+        printf("[k_wf profile] team %d steps %lld cycles/step: row wait %lld | row phase %lld | col wait %lld | exchange %lld | col phase %lld\n",
+               team, pn, prof[0] / pn, (prof[1] - prof[0]) / pn, prof[2] / pn, prof[3] / pn, (prof[4] - prof[2]) / pn);
+#endif
 }
 
 }  // namespace ssfm
