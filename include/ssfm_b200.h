@@ -73,8 +73,7 @@ SSFM_API int ssfm_plan_destroy(ssfm_plan_t plan);
 
 /* Tunables: "persistent" (1 = run the whole propagation as one persistent kernel whose teams of CTAs keep
  * the waveforms in flight resident in L2 -- the default whenever a waveform's team fits on the chip;
- * 0 = multi-launch schedule), "teams" (cap on the teams of CTAs of the persistent kernel, 0 = auto), "slots" (waveforms multiplexed per
- * team to hide barrier latency, 0 = auto),
+ * 0 = multi-launch schedule), "teams" (cap on the teams of CTAs = waveforms in flight of the persistent kernel, 0 = auto),
  * "chunk_waveforms" (multi-launch schedule: waveforms propagated together, 0 = all), "burst_steps",
  * "fused" (multi-launch schedule: 0 three kernels per step, 1..3 two kernels per step). */
 SSFM_API int ssfm_plan_set_option(ssfm_plan_t plan, const char* name, int64_t value);

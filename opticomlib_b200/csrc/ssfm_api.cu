@@ -145,8 +145,7 @@ struct ssfm_plan_s {
     int pipe = 0;                // 1: persistent pipelined fused kernel (k_col_pipe) when a waveform fits on the chip
     int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
-    int placement = 1;           // k_wf: SM-aware team placement
-    int wf_slots = 0;            // k_wf: waveforms multiplexed per team (0 = auto)
+    int placement = -1;          // k_wf: SM-aware team placement (-1 = auto)
     void* wf_sync = nullptr;     // k_wf barriers / mailboxes / max words
     cudaEvent_t wf_ev[2] = {nullptr, nullptr};
     int last_kind = 0;           // schedule of the last propagate: 0 none, 1 multi-launch, 2 k_wf
@@ -425,7 +424,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         l.sync_buf = pl->wf_sync; l.num_sms = pl->num_sms;
         l.fixed = fixed ? 1 : 0; l.single = single ? 1 : 0; l.resume = resume ? 1 : 0;
         l.h_fixed = fixed ? prm.h_km : 0.0;
-        l.budget = budget; l.teams_cap = pl->teams_cap; l.placement = pl->placement; l.slots = pl->wf_slots;
+        l.budget = budget; l.teams_cap = pl->teams_cap; l.placement = pl->placement;
         l.ev0 = pl->wf_ev[0]; l.ev1 = pl->wf_ev[1];
         int teams = 0;
         const int rc = wf_propagate<R>(p, l, &teams, st);
@@ -811,8 +810,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "debug") { pl->debug = (int)value; }
     else if (k == "pipe") { pl->pipe = value ? 1 : 0; }
     else if (k == "persistent") { pl->persistent = value ? 1 : 0; }
-    else if (k == "placement") { pl->placement = value ? 1 : 0; }
-    else if (k == "slots") { if (value < 0 || value > 4) return fail(SSFM_ERR_INVALID, "slots out of range"); pl->wf_slots = (int)value; }
+    else if (k == "placement") { pl->placement = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "teams") { if (value < 0) return fail(SSFM_ERR_INVALID, "teams < 0"); pl->teams_cap = (int)value; }
     else if (k == "tw_full") { pl->use_tw_full = value ? 1 : 0; }
     else if (k == "l2_ahead") { pl->l2_ahead = (int)value; }

@@ -38,15 +38,12 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     }
     const long long total = (long long)p.n_pol * (p.n2 / GEO::T);       // CTAs of one team
     // placement of k_wf: teams no larger than the SM count share groups of `total` SMs (one CTA of each per SM)
-    long long teams = total <= l.num_sms ? (l.num_sms / total) * per_sm : (long long)per_sm * l.num_sms / total;
+    const int placement = l.placement >= 0 ? l.placement : (sizeof(R) == 4 ? 1 : 0);
+    long long teams = (placement && total <= l.num_sms) ? (l.num_sms / total) * per_sm : (long long)per_sm * l.num_sms / total;
     if (teams > p.batch) teams = p.batch;
     if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
     if (teams < 1) return SSFM_ERR_UNSUPPORTED;                          // one waveform does not fit on the chip
-    // waveforms multiplexed per team: enough to hide the barrier latency, few enough to stay L2-resident
-    const size_t wf_bytes = (size_t)p.n_pol * (size_t)p.n * (sizeof(typename cx_of<R>::type) + sizeof(R));
-    long long nslots = l.slots > 0 ? l.slots : 1;   // measured: one slot (stash in shared memory) is fastest
-    if (nslots > WF_MAX_SLOTS) nslots = WF_MAX_SLOTS;
-    while (nslots > 1 && ((size_t)teams * nslots * wf_bytes > ((size_t)72 << 20) || teams * (nslots - 1) >= p.batch)) --nslots;
+    const long long nslots = 1;
     if (getenv("SSFM_DEBUG"))
         fprintf(stderr, "[ssfm] k_wf<%d,%d,%d,%d>: smem %zu, %d CTAs/SM, team %lld CTAs, %lld teams x %lld slots\n", (int)sizeof(R),
                 M1, M2, (int)SMALL, (size_t)GEO::smem, per_sm, total, teams, nslots);
@@ -66,9 +63,9 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     a.bar = (unsigned int*)(sb + head);
     a.mail = (unsigned long long*)(sb + head + ts * 128);
     a.slots = (unsigned long long*)(sb + head + ts * 256);
-    a.n_slots = (int)nslots;
+
     a.occ = per_sm;
-    a.placement = l.placement;
+    a.placement = placement;
     a.budget = l.budget;
     a.n_teams = (int)teams;
     a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;

@@ -14,13 +14,14 @@
 // step s+1 -> forward transform).  The phases of one waveform are separated by team barriers (a monotonic
 // arrival counter in L2, release-arrive / acquire-wait).
 //
-// Slots.  A team can multiplex `n_slots` waveforms ("slots", each with its own barrier counter): at a barrier
-// a CTA holds no live registers, so it can arrive for slot A, run the next phase of slot B and come back.
-// With n_slots == 1 (the default) the Kerr-phase stash of a tile never leaves the shared memory of the CTA
-// that owns the tile; with more slots it travels through L2 (cp.async prefetch at the start of the column
-// phase).  Measured on B200 (profiles/): multiplexing removes the barrier waits (5 k -> 2 k cycles) but the
-// time moves into the max|A|^2 exchange in the middle of the column phase, where the registers ARE live, and
-// the extra stash traffic costs more than is gained -- one slot with the stash in shared memory is fastest.
+//   * the Kerr-phase stash of a tile lives in the shared memory of the CTA that owns the tile (the same CTA
+//     visits the same tile every step): the stash traffic of the multi-launch schedule is gone.
+//
+// Tried and dropped (measured on B200): letting a team multiplex two or three waveforms
+// ("slots") so that it runs a phase of waveform B while the barrier of waveform A completes.  The barrier waits
+// shrank from ~5 k to ~2 k cycles per phase but the time moved into the max|A|^2 exchange in the middle of the
+// column phase (where the registers ARE live and the CTA cannot switch), and the stash had to travel through
+// L2: 4.2e10 instead of 4.6e10 sample*steps/s.
 //
 // Everything here is FP64/FP32 FMA-pipe arithmetic on L2-resident data; no tensor cores (no dense
 // contraction on this path).  Loads of the field bypass L1 (ld.global.cg): the data was written by other
@@ -30,13 +31,11 @@
 
 namespace ssfm {
 
-constexpr int WF_MAX_SLOTS = 4;
-
 template <typename R>
 struct WfArgs {
-    unsigned int* bar;            // [n_teams][slots][32]  monotonic arrival counters (one 128-B line each)
-    unsigned long long* mail;     // [n_teams][slots][16]  (sequence << 32 | waveform) handed out by CTA 0 of the team
-    unsigned long long* slots;    // [n_teams][slots][2][total][2]  self-validating max words, double-buffered by parity
+    unsigned int* bar;            // [n_teams][32]  monotonic arrival counter of the team barrier (one 128-B line each)
+    unsigned long long* mail;     // [n_teams][16]  (sequence << 32 | waveform) handed out by CTA 0 of the team
+    unsigned long long* slots;    // [n_teams][2][total][2]  self-validating max words, double-buffered by parity
     unsigned int* next_wf;        // next waveform to hand out (dynamic assignment: step counts differ per waveform)
     unsigned int* sm_cnt;         // [1024] CTAs of this launch that registered on each SM (team placement)
     unsigned int* grid_bar;       // arrival counter of the one grid-wide barrier that ends the registration
@@ -44,7 +43,6 @@ struct WfArgs {
     int occ;                      // CTAs per SM (the grid is occ x num_sms, all co-resident)
     int placement;                // 1 = SM-aware team placement (default), 0 = by blockIdx (experiments)
     int n_teams;
-    int n_slots;                  // waveforms multiplexed by one team (1..WF_MAX_SLOTS)
     int fixed, single, resume;
     R h_fixed;
 };
@@ -79,15 +77,11 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
     return v;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
-}
 
 enum { WF_GRAB = 0, WF_ROW = 1, WF_COL = 2, WF_END = 3 };
 
 template <typename R>
-struct WfSlot {                   // per-slot state of a team (uniform over the CTA and over the team)
+struct WfSlot {                   // state of the team's current waveform (uniform over the CTA and over the team)
     unsigned int w, bar_target, xchg, seq;
     int state, steps;
     long long taken;
@@ -100,7 +94,6 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     typedef wf_geom<R, M1, M2> GEO;
     constexpr int E = GEO::E, NT = GEO::NT, T = GEO::T, G = GEO::G, PM = GEO::PM;
     static_assert(points_per_thread<R>::value == 16, "k_wf assumes 16 points per thread");
-    static_assert((T * sizeof(R)) % 16 == 0, "stash rows of a tile are copied in 16-byte pieces");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
     __shared__ unsigned int s_w;
@@ -109,7 +102,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     C* tw1s = xb + GEO::XB;                                    // pass tables of the N1-point (column) transforms
     C* tw2s = tw1s + (TABS ? GEO::TAB1 : 0);                   // ... of the N2-point (row) transforms when N2 != N1
     C* sct = tw2s + (TABS ? GEO::TAB2 : 0);                    // sincos table
-    R* st_sm = reinterpret_cast<R*>(sct + SC_N);               // [M1][T] staging of the Kerr-phase stash of the tile
+    R* st_sm = reinterpret_cast<R*>(sct + SC_N);               // [E][NT] Kerr phase of the current step of MY tile
     const C* tw1 = TABS ? tw1s : p.tw_col;
     const C* tw2 = TABS ? ((M1 == M2) ? tw1s : tw2s) : p.tw_row;
 
@@ -121,8 +114,9 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     // speed depends on what the OTHER CTAs of its SM are doing.  The grid fills every CTA slot of the chip; each
     // CTA registers on its SM, and once all have, teams are laid out so that the `occ` CTAs of an SM belong to
     // `occ` different teams that share the same group of `total` SMs: every CTA of a team then has exactly the
-    // same neighbours (the lock-stepped CTAs of the sibling teams).  Teams larger than the chip's SM count take
-    // consecutive slots instead (all CTAs of an SM in the same team).
+    // same neighbours (the lock-stepped CTAs of the sibling teams).  Measured: +16 % in fp32 (three CTAs per SM),
+    // -3 % in fp64 (two per SM), so the host enables it for fp32 only; teams larger than the SM count are
+    // spread by blockIdx.
     __shared__ unsigned int s_slot, s_rank;
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -143,19 +137,15 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     __syncthreads();
     const unsigned int n_sm = gridDim.x / (unsigned)a.occ;
     int team, me;
-    if (!a.placement) {
+    if (!a.placement || total > n_sm) {                        // by blockIdx: consecutive CTAs spread over the SMs
         team = (int)(blockIdx.x % (unsigned)a.n_teams);
         me = (int)(blockIdx.x / (unsigned)a.n_teams);
         if (me >= (int)total) team = a.n_teams;
-    } else if (total <= n_sm) {
+    } else {
         const unsigned int grp = s_rank / total;
         team = (int)(grp * (unsigned)a.occ + s_slot);
         me = (int)(s_rank % total);
         if (grp >= n_sm / total) team = a.n_teams;             // SMs beyond the last full group stay idle
-    } else {
-        const unsigned int vid = s_rank * (unsigned)a.occ + s_slot;
-        team = (int)(vid / total);
-        me = (int)(vid % total);
     }
     if (team >= a.n_teams) return;
 
@@ -180,16 +170,16 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
 #define WF_ACC(i, name) do { } while (0)
 #endif
 
-    // split team barrier of slot s: arrive after the phase's stores, wait before the next phase's loads
-    auto bar_arrive = [&](WfSlot<R>& S, int s) {
+    // team barrier, split: arrive after the phase's stores, wait before the next phase's loads
+    unsigned int* const bar = a.bar + (size_t)team * 32;
+    auto bar_arrive = [&](WfSlot<R>& S) {
         __syncthreads();                                        // every thread's stores are ordered before the release
         S.bar_target += total;
-        if (tid == 0) red_release_add_u32(a.bar + (size_t)(team * a.n_slots + s) * 32, 1u);
+        if (tid == 0) red_release_add_u32(bar, 1u);
     };
-    auto bar_wait = [&](const WfSlot<R>& S, int s) {
+    auto bar_wait = [&](const WfSlot<R>& S) {
         if (tid == 0) {
-            const unsigned int* b = a.bar + (size_t)(team * a.n_slots + s) * 32;
-            while ((int)(ld_relaxed_u32(b) - S.bar_target) < 0) { }
+            while ((int)(ld_relaxed_u32(bar) - S.bar_target) < 0) { }
             fence_acq_rel_gpu();
         }
         __syncthreads();
@@ -198,11 +188,11 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     // max over the team of a per-thread value (NaN wins, like numpy's max): block reduction, one self-validating
     // word (two for double) per CTA -- {32 value bits | 32-bit exchange tag}: the flag travels with the data, so no
     // fence and no atomic is needed -- and the first warps poll the team's words.
-    auto team_max = [&](WfSlot<R>& S, int s, R pm) -> R {
+    auto team_max = [&](WfSlot<R>& S, R pm) -> R {
         constexpr int NW = sizeof(R) / 4;
         ++S.xchg;
         const unsigned long long tag = (unsigned long long)S.xchg;
-        volatile unsigned long long* wf = a.slots + ((size_t)((team * a.n_slots + s) * 2 + (S.xchg & 1u)) * total) * 2;
+        volatile unsigned long long* wf = a.slots + ((size_t)(team * 2 + (S.xchg & 1u)) * total) * 2;
         const int warp = tid >> 5, lane = tid & 31;
         unsigned long long bits = ord_bits(pm);
 #pragma unroll
@@ -252,25 +242,16 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
         return from_bits<R>(best);
     };
 
-    const bool keep = a.n_slots == 1;                           // the stash of my tile stays in shared memory
-    WfSlot<R> sl[WF_MAX_SLOTS];
-#pragma unroll
-    for (int s = 0; s < WF_MAX_SLOTS; ++s) {
-        sl[s].w = 0u; sl[s].bar_target = 0u; sl[s].xchg = 0u; sl[s].seq = 0u;
-        sl[s].state = s < a.n_slots ? WF_GRAB : WF_END; sl[s].steps = 0; sl[s].taken = 0; sl[s].z = 0; sl[s].h = 0;
-    }
-    int live = a.n_slots;
+    WfSlot<R> S;
+    S.w = 0u; S.bar_target = 0u; S.xchg = 0u; S.seq = 0u; S.state = WF_GRAB; S.steps = 0; S.taken = 0; S.z = 0; S.h = 0;
 
-    while (live > 0) {
-        for (int s = 0; s < a.n_slots; ++s) {
-            WfSlot<R>& S = sl[s];
-            if (S.state == WF_END) continue;
-
+    while (S.state != WF_END) {
+        {
             if (S.state == WF_GRAB) {
                 // ---------------------------------------------------------- next waveform of this slot
                 ++S.seq;
                 if (tid == 0) {
-                    volatile unsigned long long* mb = a.mail + (size_t)(team * a.n_slots + s) * 16;
+                    volatile unsigned long long* mb = a.mail + (size_t)team * 16;
                     unsigned int wn;
                     if (me == 0) {
                         wn = atomicAdd(a.next_wf, 1u);
@@ -285,13 +266,12 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 __syncthreads();
                 const unsigned int w = s_w;
                 __syncthreads();
-                if (w >= (unsigned int)p.batch) { S.state = WF_END; --live; continue; }
+                if (w >= (unsigned int)p.batch) { S.state = WF_END; continue; }
                 S.w = w; S.taken = 0;
 
                 // ---------------------------------------------------------- prologue: first step size, first Kerr
                 // half step (devices.py:1155-1161, 1175-1177), forward column transforms, four-step twiddle
                 C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + pol) * p.n;
-                R* __restrict__ strow = p.stash + ((size_t)w * p.n_pol + pol) * p.n;
                 C v[E];
 #pragma unroll
                 for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * p.n2 + n2);
@@ -313,7 +293,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                             pm = pw > pm ? pw : pm;
                         }
                         if (nan) pm = pw_nan<R>();
-                        h0 = p.phi_max / mul_rn(p.abs_gamma, team_max(S, s, pm));
+                        h0 = p.phi_max / mul_rn(p.abs_gamma, team_max(S, pm));
                     }
                     S.h = (p.length < h0) ? p.length : h0;      // python min(h_, length)
                     S.z = 0; S.steps = 0;
@@ -330,8 +310,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                     for (int q = 0; q < E; ++q) {
                         const R pw = v[q].x * v[q].x + v[q].y * v[q].y; // |A|^2
                         const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // (h_/2) * (gamma |A|^2)
-                        if (keep) st_sm[(t + q * (M1 / E)) * T + c] = ph;
-                        else strow[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = ph;
+                        st_sm[q * NT + tid] = ph;
                         R sn, co; kerr_sincos<SMALL>(ph, sct, &sn, &co);
                         v[q] = cmul(v[q], mk<R>(co, sn));
                     }
@@ -340,7 +319,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
                 for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
-                bar_arrive(S, s);
+                bar_arrive(S);
                 S.state = WF_ROW;
                 continue;
             }
@@ -349,7 +328,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
             if (S.state == WF_ROW) {
                 // ---------------------------------------------------------- row phase (devices.py:1178-1180)
                 WF_T0(t_r0);
-                bar_wait(S, s);
+                bar_wait(S);
                 WF_ACC(0, t_r0);
                 C* __restrict__ rbase = rowp + (size_t)k1 * p.n2;
                 const R h = S.h;
@@ -374,7 +353,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 fft_passes<R, M2, +1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
 #pragma unroll
                 for (int q = 0; q < E; ++q) rbase[tr + q * (M2 / E)] = v[q];
-                bar_arrive(S, s);
+                bar_arrive(S);
                 S.state = WF_COL;
                 WF_ACC(1, t_r0);
                 continue;
@@ -382,18 +361,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
 
             // -------------------------------------------------------------- column phase: end of step s ...
             WF_T0(t_c0);
-            bar_wait(S, s);
+            bar_wait(S);
             WF_ACC(2, t_c0);
-            R* __restrict__ strow = p.stash + ((size_t)S.w * p.n_pol + pol) * p.n;
-            if (p.has_nl && !keep) {                            // Kerr phase of this tile: L2 -> shared memory, in flight
-                constexpr int PIECES = (int)(T * sizeof(R) / 16);       // 16-byte pieces per tile row
-                constexpr int PER = 16 / (int)sizeof(R);
-                for (int i = tid; i < M1 * PIECES; i += NT) {
-                    const int r = i / PIECES, pc = i % PIECES;
-                    cp_async_cg16(st_sm + r * T + pc * PER, strow + (size_t)r * p.n2 + tile * T + pc * PER);
-                }
-                cp_async_commit();
-            }
             const R z = S.z, h = S.h;
             const int steps = S.steps;
             C v[E];
@@ -416,7 +385,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 }
                 if (nan) pm = pw_nan<R>();
                 WF_T0(t_x0);
-                pmax = team_max(S, s, pm);
+                pmax = team_max(S, pm);
                 WF_ACC(3, t_x0);
             }
             const CtrlNext<R> nx = controller_next<R>(p, z, h, steps, pmax);
@@ -430,21 +399,16 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 if (p.hlog && steps < p.hlog_cap) p.hlog[(size_t)S.w * p.hlog_cap + steps] = (double)h;
                 cs.z = (double)nx.z; cs.h = (double)nx.h; cs.steps = steps + 1; cs.done = nx.done;
             }
-            if (!keep) {
-                cp_async_wait_all();
-                __syncthreads();                                // the staged stash was copied by other threads
-            }
             if (stop) {                                         // second Kerr half step, time domain out
 #pragma unroll
                 for (int q = 0; q < E; ++q) {
                     if (p.has_nl) {
-                        R sn, co; kerr_sincos<SMALL>(st_sm[(t + q * (M1 / E)) * T + c], sct, &sn, &co);
+                        R sn, co; kerr_sincos<SMALL>(st_sm[q * NT + tid], sct, &sn, &co);
                         v[q] = cmul(v[q], mk<R>(co, sn));
                     }
                     rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
                 }
                 S.state = WF_GRAB;
-                __syncthreads();                                // st_sm / xb are free for the next phase
                 WF_ACC(4, t_c0);
                 continue;
             }
@@ -455,9 +419,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 for (int q = 0; q < E; ++q) {
                     const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
                     const R ph = mul_rn(hh, mul_rn(p.gamma, pw));   // first half step of the next step
-                    const R tot = st_sm[(t + q * (M1 / E)) * T + c] + ph;   // + second half step of this one
-                    if (keep) st_sm[(t + q * (M1 / E)) * T + c] = ph;   // each thread re-reads only what it wrote itself
-                    else strow[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = ph;
+                    const R tot = st_sm[q * NT + tid] + ph;         // + second half step of this one
+                    st_sm[q * NT + tid] = ph;                       // (each thread re-reads only what it wrote itself)
                     R sn, co; kerr_sincos<SMALL>(tot, sct, &sn, &co);
                     v[q] = cmul(v[q], mk<R>(co, sn));
                 }
@@ -467,7 +430,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
 #pragma unroll
             for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
             S.z = nx.z; S.h = nx.h; S.steps = steps + 1;
-            bar_arrive(S, s);
+            bar_arrive(S);
             S.state = WF_ROW;
             WF_ACC(4, t_c0);
         }

@@ -12,8 +12,8 @@ struct WfLaunch {
     double h_fixed;
     long long budget;        // steps per waveform in this call (> 0)
     int teams_cap;           // 0 = as many teams as fit on the chip
-    int placement;           // 1 = SM-aware team placement, 0 = by blockIdx
-    int slots;               // waveforms multiplexed per team (0 = auto)
+    int placement;           // 1 = SM-aware team placement, 0 = by blockIdx, -1 = auto (measured: on for fp32 with three
+                             // CTAs per SM, +16 %; off for fp64 with two, where it costs 3 %)
     cudaEvent_t ev0, ev1;    // recorded around the launch on the stream (may be null)
 };
 constexpr size_t WF_SYNC_BYTES = 1u << 20;
@@ -21,7 +21,7 @@ constexpr size_t WF_SYNC_BYTES = 1u << 20;
 // Runs the whole propagation of p.batch waveforms as one cooperative launch of k_wf.
 // Returns SSFM_ERR_UNSUPPORTED (no error text) when the geometry has no k_wf instantiation or one
 // waveform's team does not fit on the chip; the caller then uses the multi-launch schedule.
-// *in_flight = waveforms in flight (teams x slots).
+// *in_flight = waveforms in flight (= teams).
 template <typename R> int wf_propagate(const Params<R>& p, const WfLaunch& l, int* in_flight, cudaStream_t st);
 
 }  // namespace ssfm

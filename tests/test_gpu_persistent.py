@@ -103,7 +103,7 @@ def test_more_waveforms_than_teams_with_diverging_step_counts(ob, precision):
     kw = dict(length=8.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.01)
     out, info = ob.fiber_batch(x, DT, precision=precision, persistent=True, **kw)
     kind, teams, ms = _kind(ob, n, 1, rows, precision)
-    assert kind == 2 and 1 <= teams <= rows and ms > 0
+    assert kind == 2 and 1 <= teams < rows and ms > 0
     out_m, info_m = ob.fiber_batch(x, DT, precision=precision, persistent=False, **kw)
     assert np.array_equal(info.steps, info_m.steps) and info.done.all()
     assert len(set(info.steps.tolist())) > 5
@@ -118,14 +118,14 @@ def test_more_waveforms_than_teams_with_diverging_step_counts(ob, precision):
     import torch
     td = torch.complex64 if precision == "fp32" else torch.complex128
     plan = engine.get_plan(n, 1, rows, td, torch.device("cuda", 0))
-    for teams_cap, slots in ((3, 1), (3, 2), (0, 1), (5, 3)):
-        plan.set_option("teams", teams_cap); plan.set_option("slots", slots)
+    for teams_cap, placement in ((3, -1), (5, 0), (5, 1), (0, 0), (0, 1)):
+        plan.set_option("teams", teams_cap); plan.set_option("placement", placement)
         try:
             out_3, info_3 = ob.fiber_batch(x, DT, precision=precision, persistent=True, **kw)
             if teams_cap:
-                assert plan.last_timing()[1] == teams_cap * slots       # waveforms in flight
+                assert plan.last_timing()[1] == teams_cap               # waveforms in flight
         finally:
-            plan.set_option("teams", 0); plan.set_option("slots", 0)
+            plan.set_option("teams", 0); plan.set_option("placement", -1)
         assert np.array_equal(out_3, out) and np.array_equal(info_3.steps, info.steps)
 
 
