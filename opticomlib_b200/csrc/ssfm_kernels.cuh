@@ -85,7 +85,23 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 // to |r| <= pi/256 + degree-5/6 Taylor polynomials: 17 FP64 instructions instead of ~40 for
 // sincos(), absolute error < 3e-16 for |x| < 1e7 rad (the linear-operator phase is O(1e3) rad).
 constexpr int SC_N = 256;
-__device__ __forceinline__ void sincos_r(float x, const float2*, float* s, float* c) { sincosf(x, s, c); }
+// float: the argument is the float32 phase the reference feeds to exp() (O(1e3) rad for the linear operator), so the
+// reduction must be exact for THAT value: it is done in double (two FMAs), the rest in float32 -- 256-entry table +
+// degree-3/4 Taylor on |r| <= pi/256 (truncation < 3e-12), about 16 instructions instead of ~45 for sincosf's
+// slow path; absolute error < 1.5e-7.
+__device__ __forceinline__ void sincos_r(float x, const float2* tab, float* s, float* c) {
+    const double magic = 6755399441055744.0;                       // 1.5 * 2^52
+    const double xd = (double)x;
+    const double m = fma(xd, 40.74366543152521, magic);            // x * 256/(2 pi), integer part in the low bits
+    const int idx = __double2loint(m) & (SC_N - 1);
+    const float r = (float)fma(-(m - magic), 0.02454369260617026, xd);   // x - k * 2 pi/256
+    const float r2 = r * r;
+    const float sr = fmaf(r * r2, -1.6666667e-1f, r);
+    const float cr = fmaf(r2, fmaf(r2, 4.1666668e-2f, -0.5f), 1.0f);
+    const float2 e = tab[idx];                                     // (cos, sin) of 2 pi idx/256
+    *c = fmaf(e.x, cr, -(e.y * sr));
+    *s = fmaf(e.y, cr, e.x * sr);
+}
 __device__ __forceinline__ void sincos_r(double x, const double2* tab, double* s, double* c) {
     const double magic = 6755399441055744.0;                       // 1.5 * 2^52
     const double m = fma(x, 40.74366543152521, magic);             // x * 256/(2 pi), integer part in the low bits

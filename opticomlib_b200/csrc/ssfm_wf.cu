@@ -83,7 +83,7 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
 
 template <typename R, int M1, int M2>
 int wf_launch_small(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
-    if (sizeof(R) == 8 && p.small_phase) return wf_launch<R, M1, M2, (sizeof(R) == 8)>(p, l, teams_out, st);
+    if (p.small_phase) return wf_launch<R, M1, M2, true>(p, l, teams_out, st);   // |Kerr phase| <= 0.05 rad: short Taylor sincos
     return wf_launch<R, M1, M2, false>(p, l, teams_out, st);
 }
 

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     };
     auto bar_wait = [&](const WfSlot<R>& S) {
         if (tid == 0) {
-            while ((int)(ld_relaxed_u32(bar) - S.bar_target) < 0) { }
+            while ((int)(ld_relaxed_u32(bar) - S.bar_target) < 0) { if (total > 32u) __nanosleep(20); }   // big teams: ease off L2
             fence_acq_rel_gpu();
         }
         __syncthreads();
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                     for (;;) {
                         x = wf[(idx / NW) * 2 + (idx % NW)];
                         if ((x & 0xffffffffull) == tag) break;
+                        if (total > 32u) __nanosleep(20);
                     }
                 }
                 unsigned long long val = have ? (x >> 32) : 0ull;
