@@ -119,6 +119,28 @@ SSFM_API int ssfm_fiber_host(ssfm_plan_t plan, const void* field_in_host, void* 
  * the zero-phase filters use it internally with H = |H_sos|^2. */
 SSFM_API int ssfm_apply_transfer(ssfm_plan_t plan, void* field_dev, const void* h_dev, void* stream);
 
+/* ---- long waveforms: N = N0 x N_l beyond one two-pass transform (N > 2^22) and/or one waveform spread over
+ * `n_ranks` GPUs (BASELINE config #5).  The same statements of devices.py:1155-1196; only the transform is split:
+ * rank g holds columns [g N_l/G, (g+1) N_l/G) of the N0 x N_l sample matrix (local [N0][N_l/G], sample n = na N_l + nb)
+ * in the time domain and rows [g N0/G, (g+1) N0/G) (local [N0/G][N_l]) in the frequency domain.  The caller moves
+ * the data between the two layouts (an all-to-all between the ranks; nothing for one rank) -- the library itself has
+ * no NCCL dependency -- and drives one split step as
+ *     ssfm_long_outer(stage)  ->  exchange  ->  ssfm_long_inner  ->  exchange back  ->  ssfm_long_outer(stage) ...
+ * stage 0 "open": first Kerr half step + forward outer transform; stage 2 "close": inverse outer transform + second
+ * Kerr half step + local max|A|^2 into the controller (then ssfm_long_pmax get / all-reduce MAX / set when n_ranks > 1,
+ * and ssfm_long_ctrl(0) runs the step-size controller); stage 1 "mid" (fixed step only): close + open in one pass,
+ * the device controller advances by itself and the last "mid" leaves the field in the time domain.
+ * ssfm_get_state / ssfm_get_step_log report z, h, steps, done as for ordinary plans. */
+SSFM_API int ssfm_long_plan_create(ssfm_plan_t* plan, int64_t n_samples_global, int32_t n_outer, int32_t n_ranks,
+                          int32_t rank, int32_t dtype, int32_t device);
+/* Reset the controller for a new propagation; adaptive mode: local max|A|^2 of field_local -> ssfm_long_pmax.
+ * Follow with ssfm_long_ctrl(plan, 1, ...) (first step size, devices.py:1155-1161). */
+SSFM_API int ssfm_long_begin(ssfm_plan_t plan, void* field_local_dev, const ssfm_fiber_params* prm, void* stream);
+SSFM_API int ssfm_long_pmax(ssfm_plan_t plan, double* value_host, int32_t set, void* stream);
+SSFM_API int ssfm_long_ctrl(ssfm_plan_t plan, int32_t init, void* stream);
+SSFM_API int ssfm_long_outer(ssfm_plan_t plan, void* field_local_dev, int32_t stage, void* stream);
+SSFM_API int ssfm_long_inner(ssfm_plan_t plan, void* rows_local_dev, void* stream);
+
 /* Zero-phase cascaded-biquad filtering (scipy.signal.sosfiltfilt as called at devices.py:820-823 and
  * 1365-1368): x_dev[n_rows][n_samples] complex128 -> y_dev (may alias x_dev).
  * sos_host[n_sections][6] = b0 b1 b2 a0 a1 a2 (a0 == 1) from scipy.signal.bessel(..., output='sos').

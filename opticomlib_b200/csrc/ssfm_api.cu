@@ -142,7 +142,6 @@ struct ssfm_plan_s {
     int debug = 0;
     int use_tw_full = 1;
     int l2_ahead = 0;
-    int pipe = 0;                // 1: persistent pipelined fused kernel (k_col_pipe) when a waveform fits on the chip
     int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
     int placement = -1;          // k_wf: SM-aware team placement (-1 = auto)
@@ -150,6 +149,11 @@ struct ssfm_plan_s {
     cudaEvent_t wf_ev[2] = {nullptr, nullptr};
     int last_kind = 0;           // schedule of the last propagate: 0 none, 1 multi-launch, 2 k_wf
     int last_teams = 0;
+    int lo_bits = 0;             // split of the four-step twiddle tables (0 = log2 n2)
+    // long waveforms (ssfm_long_*): this plan is the OUTER N0-point stage over this rank's column slice
+    long long long_n = 0;        // global transform length N = N0 x N_l (0 = ordinary plan)
+    int long_ranks = 1, long_rank = 0;
+    ssfm_plan_t inner = nullptr; // N_l-point transforms of the N0 / ranks rows this rank owns after the exchange
     int n_active = 0;
     double* hlog = nullptr;
     int hlog_cap = 0;
@@ -225,39 +229,6 @@ int launch_col_mid(const Params<R>& p, int nblocks, int cluster, cudaStream_t st
     ++ssfm_launches;
     return SSFM_OK;
 }
-template <typename R, int M>
-size_t col_pipe_smem() {
-    typedef typename cx_of<R>::type C;
-    constexpr int T = col_tile_of<R>(M);
-    constexpr int E = points_per_thread<R>::value;
-    return sizeof(C) * (size_t)(fft_plan<M, E>::table_size + SC_N + 2 * M * T) + sizeof(R) * (size_t)(2 * M * T);
-}
-// persistent pipelined fused kernel: grid = groups x (tiles of one waveform), every CTA resident.
-// Returns SSFM_ERR_UNSUPPORTED (without setting an error text) when one waveform does not fit on the chip.
-template <typename R, int M, int SYNC>
-int launch_col_pipe(const Params<R>& p, int num_sms, cudaStream_t st) {
-    constexpr int T = col_tile_of<R>(M);
-    constexpr int E = points_per_thread<R>::value;
-    const size_t smem = col_pipe_smem<R, M>();
-    static int per_sm = -1;
-    if (per_sm < 0) {
-        if (smem > 227 * 1024) { per_sm = 0; }
-        else {
-            CU_TRY(cudaFuncSetAttribute(k_col_pipe<R, M, T, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int v = 0;
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_col_pipe<R, M, T, SYNC>, T * (M / E), smem));
-            per_sm = v;
-        }
-    }
-    const long long total = (long long)p.n_pol * (p.n2 / T);
-    long long groups = (long long)per_sm * num_sms / total;
-    if (groups > p.batch) groups = p.batch;
-    if (groups < 1) return SSFM_ERR_UNSUPPORTED;
-    k_col_pipe<R, M, T, SYNC><<<(unsigned)(groups * total), T * (M / E), smem, st>>>(p);
-    ++ssfm_launches;
-    return SSFM_OK;
-}
-
 // How can the fused kernel synchronise the `group` tiles of one waveform on this device?
 //   want = SYNC_CLUSTER : a cluster of `group` CTAs if it can be scheduled (group <= 16)
 //   want = SYNC_GLOBAL / SYNC_LL : that protocol if `group` CTAs are resident at once
@@ -314,8 +285,7 @@ int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
 enum ColKind { COL_FWD, COL_INV, COL_MID };
 
 template <typename R>
-int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st, int sync = SYNC_GLOBAL, bool pipe = false,
-                int num_sms = 0) {
+int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st, int sync = SYNC_GLOBAL) {
     const long long rows = (long long)p.batch * p.n_pol;
     switch (p.n1) {
 #define X(M) case M: {                                                             \
@@ -323,11 +293,6 @@ int enqueue_col(const Params<R>& p, ColKind kind, cudaStream_t st, int sync = SY
             const int nb = (int)(rows * tiles);                                    \
             if (kind == COL_FWD) return launch_col_fwd<R, M>(p, nb, st);           \
             if (kind == COL_INV) return launch_col_inv<R, M>(p, nb, st);           \
-            if (pipe && (sync == SYNC_FIXED || sync == SYNC_LL)) {                                      \
-                const int rp = sync == SYNC_FIXED ? launch_col_pipe<R, M, SYNC_FIXED>(p, num_sms, st)   \
-                                                  : launch_col_pipe<R, M, SYNC_LL>(p, num_sms, st);     \
-                if (rp != SSFM_ERR_UNSUPPORTED) return rp;                                              \
-            }                                                                                           \
             if (sync == SYNC_FIXED) return launch_col_mid<R, M, SYNC_FIXED>(p, nb, 1, st);              \
             if (sync == SYNC_CLUSTER) return launch_col_mid<R, M, SYNC_CLUSTER>(p, nb, tiles * p.n_pol, st); \
             if (sync == SYNC_LL) return launch_col_mid<R, M, SYNC_LL>(p, nb, 1, st);                    \
@@ -375,8 +340,9 @@ Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed,
     base.tw_lo = (const C*)pl->tw_lo;   base.tw_hi = (const C*)pl->tw_hi;
     base.tw_full = pl->use_tw_full ? (const C*)pl->tw_full : nullptr;
     base.small_phase = (!fixed && !single && pm <= (R)0.05 && pm >= (R)0) ? 1 : 0;   // |Kerr phase| <= phi_max in adaptive mode
-    base.lo_bits = ilog2(pl->n2);
+    base.lo_bits = pl->lo_bits ? pl->lo_bits : ilog2(pl->n2);
     base.n = (int)pl->n; base.n1 = pl->n1; base.n2 = pl->n2; base.log2_n2 = ilog2(pl->n2);
+    base.n_glob = (int)pl->n; base.bin_mul = 1;
     base.n_pol = pl->n_pol;
     base.hlog_cap = pl->hlog_cap;
     base.adaptive = fixed ? 0 : 1;
@@ -492,7 +458,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
                 int rc = SSFM_OK;
                 if (use_fused) {
                     rc = enqueue_row<R>(p, st);
-                    if (!rc) rc = enqueue_col<R>(p, (enq + s + 1 == budget) ? COL_INV : COL_MID, st, sync, pl->pipe != 0, pl->num_sms);
+                    if (!rc) rc = enqueue_col<R>(p, (enq + s + 1 == budget) ? COL_INV : COL_MID, st, sync);
                 } else {
                     rc = enqueue_col<R>(p, COL_FWD, st);
                     if (!rc) rc = enqueue_row<R>(p, st);
@@ -569,7 +535,7 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
         CU_TRY(cudaEventRecord(ev[1], st));
         if (!rc) rc = enqueue_row<R>(p, st);
         CU_TRY(cudaEventRecord(ev[2], st));
-        if (!rc) rc = enqueue_col<R>(p, use_fused ? COL_MID : COL_INV, st, sync, pl->pipe != 0, pl->num_sms);
+        if (!rc) rc = enqueue_col<R>(p, use_fused ? COL_MID : COL_INV, st, sync);
         CU_TRY(cudaEventRecord(ev[3], st));
         CU_TRY(cudaEventSynchronize(ev[3]));
         if (r >= 0)
@@ -795,6 +761,7 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
     if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
     cudaFree(pl->wf_sync);
+    if (pl->inner) ssfm_plan_destroy(pl->inner);
     if (pl->wf_ev[0]) cudaEventDestroy(pl->wf_ev[0]);
     if (pl->wf_ev[1]) cudaEventDestroy(pl->wf_ev[1]);
     delete pl;
@@ -808,7 +775,6 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "burst_steps") { if (value < 1 || value > 4096) return fail(SSFM_ERR_INVALID, "burst_steps out of range"); pl->burst = (int)value; }
     else if (k == "fused") { pl->fused = (int)value; }   // 0 unfused, 1 fused (LL barrier), 2 fused (atomic barrier), 3 fused (cluster barrier when possible)
     else if (k == "debug") { pl->debug = (int)value; }
-    else if (k == "pipe") { pl->pipe = value ? 1 : 0; }
     else if (k == "persistent") { pl->persistent = value ? 1 : 0; }
     else if (k == "placement") { pl->placement = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "teams") { if (value < 0) return fail(SSFM_ERR_INVALID, "teams < 0"); pl->teams_cap = (int)value; }
@@ -822,6 +788,7 @@ int ssfm_propagate(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, in
                    void* stream) {
     if (!pl || !field || !prm) return fail(SSFM_ERR_INVALID, "null plan, field or params");
     if (!pl->stash) return fail(SSFM_ERR_INVALID, "this plan was created for transfer functions only");
+    if (pl->long_n) return fail(SSFM_ERR_INVALID, "long-waveform plans are driven through ssfm_long_*");
     if (!(prm->dt_s > 0)) return fail(SSFM_ERR_INVALID, "dt_s must be > 0");
     if (max_steps < 0) return fail(SSFM_ERR_INVALID, "max_steps < 0");
     if (resume && !pl->have_state) return fail(SSFM_ERR_INVALID, "resume requested but the plan holds no controller state");
@@ -886,6 +853,232 @@ int ssfm_fiber_host(ssfm_plan_t pl, const void* in, void* outp, const ssfm_fiber
         if (e != cudaSuccess) rc = fail(SSFM_ERR_CUDA, std::string("D2H: ") + cudaGetErrorString(e));
     }
     cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Long waveforms: N = N0 x N_l, beyond one two-pass transform (N > 2^22) and/or spread over several
+// GPUs (BASELINE config #5).  Sample n = na N_l + nb, bin k = ka + N0 kb.  In the time domain rank g holds
+// the columns nb in [g N_l/G, (g+1) N_l/G) of the N0 x N_l matrix for every na (local array [N0][N_l/G]);
+// in the frequency domain it holds the rows ka in [g N0/G, (g+1) N0/G) for every nb (local array
+// [N0/G][N_l]).  One split step is
+//   OUTER (this plan; the column kernels of ssfm_kernels.cuh with M = N0 and the global twiddle W_N^{nb ka}):
+//         end of the previous step / Kerr half steps / N0-point column transforms       -- local, 1R + 1W
+//   exchange  [N0][N_l/G] -> [N0/G][N_l]   (all-to-all between the ranks; the identity for one rank)
+//   INNER (pl->inner): N_l-point transforms of the rank's rows by the ordinary two-pass kernels with the
+//         linear operator exp(D~(w_k) h) at global bin k = ka + N0 (k1 + N1 k2) in the middle     -- local, 3R + 3W
+//   exchange back.
+// The exchange itself belongs to the host side (torch.distributed all_to_all_single over NCCL/NVLink,
+// opticomlib_b200/longwave.py): the library has no NCCL dependency.  The spectrum stays in (doubly)
+// transposed order throughout; the linear operator is point-wise, so no transposition pass exists.
+// =================================================================================================
+namespace {
+
+template <typename R>
+Params<R> long_outer_params(ssfm_plan_t pl, void* field) {
+    typedef typename cx_of<R>::type C;
+    bool fixed, single;
+    Params<R> p = base_params<R>(pl, pl->last, fixed, single);
+    p.field = (C*)field; p.stash = (R*)pl->stash; p.ctrl = pl->ctrl; p.active = pl->active;
+    p.ticket = pl->ticket; p.slots = pl->slots; p.hlog = pl->hlog; p.batch = 1;
+    p.tw_full = nullptr;
+    p.n2_off = pl->long_rank * pl->n2;
+    p.n_glob = (int)pl->long_n;
+    p.inv_n = (R)1 / (R)pl->long_n;
+    p.defer_ctrl = 1;
+    return p;
+}
+
+template <typename R>
+Params<R> long_inner_params(ssfm_plan_t pl, void* rows) {
+    typedef typename cx_of<R>::type C;
+    ssfm_plan_t pi = pl->inner;
+    bool fixed, single;
+    Params<R> p = base_params<R>(pi, pl->last, fixed, single);
+    p.field = (C*)rows; p.stash = nullptr; p.ctrl = pl->ctrl; p.active = pl->active;   // controller state of the OUTER plan
+    p.ticket = pi->ticket; p.slots = pi->slots; p.hlog = nullptr; p.batch = (int)pi->batch;
+    p.inner = 1;
+    p.bin_mul = pl->n1;                                        // N0
+    p.bin_off = pl->long_rank * (int)pi->batch;                // first outer bin ka of this rank
+    p.n_glob = (int)pl->long_n;
+    p.wscale = ((1.0 / ((double)pl->long_n * pl->last.dt_s)) * 2.0) * 3.141592653589793 * 1e-12;
+    p.inv_n = (R)1; p.att_half = (R)0;                          // 1/N and the attenuation are applied once, by the outer stage
+    p.has_nl = 0;
+    return p;
+}
+
+template <typename R>
+int long_begin_t(ssfm_plan_t pl, void* field, cudaStream_t st) {
+    bool fixed, single;
+    (void)base_params<R>(pl, pl->last, fixed, single);
+    Params<R> p = long_outer_params<R>(pl, field);
+    const int one = 1;
+    CU_TRY(cudaMemcpyAsync(p.active, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl), st));
+    if (!fixed && !single) {                                    // local max |A|^2 -> ctrl.pmax (combined over the ranks by the host)
+        k_power_max<R><<<64, 256, 0, st>>>(p, 64);
+        ++ssfm_launches;
+    }
+    CU_TRY(cudaGetLastError());
+    return SSFM_OK;
+}
+
+template <typename R>
+int long_ctrl_t(ssfm_plan_t pl, int init, cudaStream_t st) {
+    bool fixed, single;
+    (void)base_params<R>(pl, pl->last, fixed, single);
+    Params<R> p = long_outer_params<R>(pl, nullptr);
+    if (init) k_ctrl_init<R><<<1, 32, 0, st>>>(p, fixed ? 1 : 0, fixed ? (R)pl->last.h_km : (R)0, single ? 1 : 0);
+    else k_ctrl_step<R><<<1, 32, 0, st>>>(p);
+    ++ssfm_launches;
+    CU_TRY(cudaGetLastError());
+    return SSFM_OK;
+}
+
+template <typename R>
+int long_outer_t(ssfm_plan_t pl, void* field, int stage, cudaStream_t st) {
+    Params<R> p = long_outer_params<R>(pl, field);
+    if (stage == 0) return enqueue_col<R>(p, COL_FWD, st);
+    if (stage == 2) return enqueue_col<R>(p, COL_INV, st);
+    return enqueue_col<R>(p, COL_MID, st, SYNC_FIXED);         // fixed step only: no max, the device controller advances alone
+}
+
+template <typename R>
+int long_inner_t(ssfm_plan_t pl, void* rows, cudaStream_t st) {
+    Params<R> p = long_inner_params<R>(pl, rows);
+    int rc = enqueue_col<R>(p, COL_FWD, st);
+    if (!rc) rc = enqueue_row<R>(p, st);
+    if (!rc) rc = enqueue_col<R>(p, COL_INV, st);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ssfm_long_plan_create(ssfm_plan_t* out, int64_t n_global, int32_t n_outer, int32_t n_ranks, int32_t rank,
+                          int32_t dtype, int32_t device) {
+    if (!out) return fail(SSFM_ERR_INVALID, "plan pointer is null");
+    *out = nullptr;
+    if (dtype != SSFM_C64 && dtype != SSFM_C128) return fail(SSFM_ERR_INVALID, "dtype must be SSFM_C64 or SSFM_C128");
+    if (n_global < (1ll << 12) || n_global > (1ll << 30) || (n_global & (n_global - 1)))
+        return fail(SSFM_ERR_UNSUPPORTED, "long waveforms: n_samples must be a power of two in [2^12, 2^30]");
+    if (n_outer < 16 || n_outer > 2048 || (n_outer & (n_outer - 1)))
+        return fail(SSFM_ERR_UNSUPPORTED, "long waveforms: the outer factor must be a power of two in [16, 2048]");
+    if (n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks || n_outer % n_ranks)
+        return fail(SSFM_ERR_INVALID, "long waveforms: ranks must be a power of two dividing the outer factor");
+    const long long nl = n_global / n_outer;
+    if (nl < 256 || nl > (1ll << 22)) return fail(SSFM_ERR_UNSUPPORTED, "long waveforms: inner length out of range [2^8, 2^22]");
+    const long long n2loc = nl / n_ranks;
+    if (n2loc < 32) return fail(SSFM_ERR_UNSUPPORTED, "long waveforms: fewer than 32 columns per rank");
+    CU_TRY(cudaSetDevice(device));
+    ssfm_plan_s* pl = new ssfm_plan_s();
+    pl->device = device; pl->dtype = dtype; pl->n_pol = 1; pl->batch = 1;
+    pl->n1 = n_outer; pl->n2 = (int)n2loc; pl->n = (long long)n_outer * n2loc; pl->log2n = ilog2(pl->n);
+    pl->long_n = n_global; pl->long_ranks = n_ranks; pl->long_rank = rank;
+    pl->lo_bits = (ilog2(n_global) + 1) / 2;
+    pl->hlog_cap = 1 << 16;
+    pl->persistent = 0;
+    const size_t rsz = dtype == SSFM_C64 ? 4 : 8, csz = 2 * rsz;
+    const long long n_lo = 1ll << pl->lo_bits, n_hi = n_global >> pl->lo_bits;
+    cudaError_t e = cudaMalloc(&pl->stash, (size_t)pl->n * rsz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ctrl, sizeof(Ctrl));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->active, sizeof(int));
+    pl->slots_bytes = 64;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->slots, pl->slots_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ticket, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(pl->ticket, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->hlog, sizeof(double) * (size_t)pl->hlog_cap);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->tw_lo, csz * (size_t)n_lo);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->tw_hi, csz * (size_t)n_hi);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&pl->active_host, 2 * sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[1], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[1]);
+    if (e != cudaSuccess) {
+        ssfm_plan_destroy(pl);
+        return fail(e == cudaErrorMemoryAllocation ? SSFM_ERR_NOMEM : SSFM_ERR_CUDA,
+                    std::string("long plan allocation: ") + cudaGetErrorString(e));
+    }
+    CU_TRY(cudaMemset(pl->ctrl, 0, sizeof(Ctrl)));
+    CU_TRY(cudaMemset(pl->hlog, 0, sizeof(double) * (size_t)pl->hlog_cap));
+    int rc;
+    if (dtype == SSFM_C64) {
+        k_build_unit_roots<float><<<(unsigned)((n_lo + 127) / 128), 128>>>((float2*)pl->tw_lo, (int)n_lo, 1, n_global);
+        k_build_unit_roots<float><<<(unsigned)((n_hi + 127) / 128), 128>>>((float2*)pl->tw_hi, (int)n_hi, n_lo, n_global);
+        rc = build_pass_tables<float>(&pl->tw_col, pl->n1, 0);
+    } else {
+        k_build_unit_roots<double><<<(unsigned)((n_lo + 127) / 128), 128>>>((double2*)pl->tw_lo, (int)n_lo, 1, n_global);
+        k_build_unit_roots<double><<<(unsigned)((n_hi + 127) / 128), 128>>>((double2*)pl->tw_hi, (int)n_hi, n_lo, n_global);
+        rc = build_pass_tables<double>(&pl->tw_col, pl->n1, 0);
+    }
+    if (!rc) rc = plan_create_impl(&pl->inner, nl, 1, n_outer / n_ranks, dtype, device, false);
+    if (rc) { ssfm_plan_destroy(pl); return rc; }
+    cudaError_t es = cudaDeviceSynchronize();
+    if (es != cudaSuccess) { ssfm_plan_destroy(pl); return fail(SSFM_ERR_CUDA, std::string("table build: ") + cudaGetErrorString(es)); }
+    *out = pl;
+    return SSFM_OK;
+}
+
+#define LONG_DISPATCH(pl, call_f, call_d) ((pl)->dtype == SSFM_C64 ? (call_f) : (call_d))
+
+int ssfm_long_begin(ssfm_plan_t pl, void* field_local, const ssfm_fiber_params* prm, void* stream) {
+    if (!pl || !pl->long_n || !field_local || !prm) return fail(SSFM_ERR_INVALID, "null argument or not a long-waveform plan");
+    if (!(prm->dt_s > 0)) return fail(SSFM_ERR_INVALID, "dt_s must be > 0");
+    CU_TRY(cudaSetDevice(pl->device));
+    pl->last = *prm;
+    pl->have_state = true;
+    pl->last_kind = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    return LONG_DISPATCH(pl, long_begin_t<float>(pl, field_local, st), long_begin_t<double>(pl, field_local, st));
+}
+
+int ssfm_long_pmax(ssfm_plan_t pl, double* value, int32_t set, void* stream) {
+    if (!pl || !pl->long_n || !value) return fail(SSFM_ERR_INVALID, "null argument or not a long-waveform plan");
+    CU_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long bits = 0;
+    if (set) {                                                   // value holds a number of the compute real type
+        if (pl->dtype == SSFM_C64) { float f = (float)*value; unsigned int u; std::memcpy(&u, &f, 4); bits = u; }
+        else std::memcpy(&bits, value, 8);
+        CU_TRY(cudaMemcpyAsync(&pl->ctrl->pmax, &bits, sizeof(bits), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    } else {
+        CU_TRY(cudaMemcpyAsync(&bits, &pl->ctrl->pmax, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        if (pl->dtype == SSFM_C64) { float f; unsigned int u = (unsigned int)bits; std::memcpy(&f, &u, 4); *value = (double)f; }
+        else std::memcpy(value, &bits, 8);
+    }
+    return SSFM_OK;
+}
+
+int ssfm_long_ctrl(ssfm_plan_t pl, int32_t init, void* stream) {
+    if (!pl || !pl->long_n) return fail(SSFM_ERR_INVALID, "null plan or not a long-waveform plan");
+    CU_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    return LONG_DISPATCH(pl, long_ctrl_t<float>(pl, init, st), long_ctrl_t<double>(pl, init, st));
+}
+
+int ssfm_long_outer(ssfm_plan_t pl, void* field_local, int32_t stage, void* stream) {
+    if (!pl || !pl->long_n || !field_local) return fail(SSFM_ERR_INVALID, "null argument or not a long-waveform plan");
+    if (stage < 0 || stage > 2) return fail(SSFM_ERR_INVALID, "stage must be 0 (open), 1 (mid) or 2 (close)");
+    CU_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = LONG_DISPATCH(pl, long_outer_t<float>(pl, field_local, stage, st), long_outer_t<double>(pl, field_local, stage, st));
+    if (!rc) CU_TRY(cudaGetLastError());
+    return rc;
+}
+
+int ssfm_long_inner(ssfm_plan_t pl, void* rows_local, void* stream) {
+    if (!pl || !pl->long_n || !rows_local) return fail(SSFM_ERR_INVALID, "null argument or not a long-waveform plan");
+    CU_TRY(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = LONG_DISPATCH(pl, long_inner_t<float>(pl, rows_local, st), long_inner_t<double>(pl, rows_local, st));
+    if (!rc) CU_TRY(cudaGetLastError());
     return rc;
 }
 

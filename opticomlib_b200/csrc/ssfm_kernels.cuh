@@ -57,6 +57,14 @@ struct Params {
     const C* xfer;       // optional transfer function H[k] in transposed order ([k1][k2], bin k1 + N1*k2):
                          // when set, the row kernel multiplies by it instead of exp(D~ h) (filters, DM)
     int lo_bits;
+    // long waveforms (N = N0 x N_l, ssfm_long.cu): the OUTER launches see one "waveform" of N0 rows x n2 columns (this
+    // rank's slice of the N_l columns, global column = n2 + n2_off, twiddle tables built for the global N); the INNER
+    // launches (inner = 1) transform the N0/G rows of N_l samples this rank owns after the exchange: every row shares
+    // the controller state of waveform 0 (h, done), the row kernel maps its bins to global bins
+    // k = bin_off + row + bin_mul (k1 + N1 k2) with the fftfreq wrap at n_glob, and k_col_inv leaves the controller alone.
+    int n2_off, inner, bin_mul, bin_off, n_glob;
+    int defer_ctrl;      // 1: k_col_inv only accumulates max|A|^2 in ctrl.pmax; the controller runs later (k_ctrl_step), after
+                         // the maxima of all ranks have been combined
     int n, n1, n2, log2_n2;
     int n_pol;
     int batch;           // waveforms in this launch
@@ -205,6 +213,12 @@ __device__ __forceinline__ void controller_update(const Params<R>& p, int b, R p
     controller_commit<R>(p, b, h, s, n);
 }
 
+// deferred controller step of waveform 0 (long waveforms: ctrl.pmax holds the max over all ranks by now)
+template <typename R>
+__global__ void k_ctrl_step(Params<R> p) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !p.ctrl[0].done) controller_update<R>(p, 0, from_bits<R>(p.ctrl[0].pmax));
+}
+
 // Ask for SSFM_THREADS_PER_SM resident threads per SM (512 -> at most 128 registers per thread):
 // several small CTAs per SM so that one CTA's global loads overlap another's transform.
 #ifndef SSFM_THREADS_PER_SM
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
 
     const int tiles = p.n2 / T;
     const int tile = blockIdx.x % tiles, row = blockIdx.x / tiles;   // row = b*P + pol
-    const int b = row / p.n_pol;
+    const int b = p.inner ? 0 : row / p.n_pol;
     const Ctrl ctl = p.ctrl[b];
     if (ctl.done) return;
 
@@ -342,7 +356,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
         if (sizeof(R) == 8 && p.small_phase) kerr(std::true_type{}); else kerr(std::false_type{});   // fp32: sincosf is cheap
     }
     fft_passes<R, M, -1, ColExchange<T>, E>::run(v, sm + c, tw, t);
-    apply_fourstep<false, R, E, M>(p, v, n2, t);
+    apply_fourstep<false, R, E, M>(p, v, n2 + p.n2_off, t);
 #pragma unroll
     for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
 }
@@ -362,7 +376,7 @@ __global__ void __launch_bounds__(G * (M / points_per_thread<R>::value), min_cta
     const int g = threadIdx.x / (M / E), t = threadIdx.x % (M / E);
     const long long grow = (long long)blockIdx.x * G + g;       // global row index over [B*P][N1]
     const int bp = (int)(grow / p.n1), k1 = (int)(grow % p.n1);
-    const int b = bp / p.n_pol;
+    const int b = p.inner ? 0 : bp / p.n_pol;
     const Ctrl ctl = p.ctrl[b];
     if (ctl.done) return;                                       // G divides N1: uniform per block
 
@@ -381,12 +395,13 @@ __global__ void __launch_bounds__(G * (M / points_per_thread<R>::value), min_cta
         for (int q = 0; q < E; ++q) v[q] = cmul(v[q], __ldg(hrow + t + q * (M / E)));
     } else {        // exp(D~ h): real part -alpha/2*h (attenuation), imaginary part (b2/2 w^2 + b3/6 w^3) h
         const R h = (R)ctl.h;                                   // (the attenuation exp(-alpha/2 h) of D~ is a per-step
-        const int half = p.n >> 1;                              //  scalar: it is folded into the 1/N of the column pass)
+        const int half = p.n_glob >> 1;                         //  scalar: it is folded into the 1/N of the column pass)
+        const int kbase = p.inner ? p.bin_off + bp : 0;         // long waveforms: this row is outer bin ka = bin_off + row
 #pragma unroll
         for (int q = 0; q < E; ++q) {
             const int k2 = t + q * (M / E);
-            int k = k1 + p.n1 * k2;                             // transposed-order bin index
-            k = (k < half) ? k : k - p.n;                       // fftfreq ordering
+            int k = kbase + p.bin_mul * (k1 + p.n1 * k2);       // transposed-order bin index
+            k = (k < half) ? k : k - p.n_glob;                  // fftfreq ordering
             const R w = (R)((double)k * p.wscale);              // rad/ps, = fftfreq*2*pi*1e-12 (see Params::wscale)
             const R dim = add_rn(mul_rn(p.c2, mul_rn(w, w)), mul_rn(p.c3, cube_r(w)));
             const R ph = mul_rn(dim, h);
@@ -414,7 +429,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
 
     const int tiles = p.n2 / T;
     const int tile = blockIdx.x % tiles, row = blockIdx.x / tiles;
-    const int b = row / p.n_pol;
+    const int b = p.inner ? 0 : row / p.n_pol;
     if (p.ctrl[b].done) return;
     const R sc = p.inv_n * exp_r(mul_rn(p.att_half, (R)p.ctrl[b].h));   // 1/N and exp(-alpha/2 h) (real part of D~ h)
 
@@ -434,7 +449,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
     C v[E];
 #pragma unroll
     for (int q = 0; q < E; ++q) v[q] = rowp[(size_t)(t + q * (M / E)) * p.n2 + n2];
-    apply_fourstep<true, R, E, M>(p, v, n2, t);
+    apply_fourstep<true, R, E, M>(p, v, n2 + p.n2_off, t);
     __syncthreads();
     fft_passes<R, M, +1, ColExchange<T>, E>::run(v, sm + c, tw, t);
 
@@ -456,10 +471,12 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
         rowp[off] = a;
     }
     if (nan) pm = pw_nan<R>();
+    if (p.inner) return;                                        // inner transform of a long waveform: no controller
     pm = block_max_bits<R>(pm, red);
 
     if (threadIdx.x == 0) {
         atomicMax(&p.ctrl[b].pmax, ord_bits(pm));
+        if (p.defer_ctrl) return;
         __threadfence();
         const unsigned total = (unsigned)(tiles * p.n_pol);
         const unsigned prev = atomicAdd(&p.ctrl[b].arrived, 1u);
@@ -588,7 +605,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
     C v[E];
 #pragma unroll
     for (int q = 0; q < E; ++q) v[q] = rowp[(size_t)(t + q * (M / E)) * p.n2 + n2];
-    apply_fourstep<true, R, E, M>(p, v, n2, t);
+    apply_fourstep<true, R, E, M>(p, v, n2 + p.n2_off, t);
     __syncthreads();
     const int step_before = s_steps;
     const R z_before = (R)s_z, h_before = (R)s_hnext;
@@ -729,7 +746,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
             if (sizeof(R) == 8 && p.small_phase) kerr(std::true_type{}); else kerr(std::false_type{});
         }
         fft_passes<R, M, -1, ColExchange<T>, E>::run(v, sm + c, tw, t);
-        apply_fourstep<false, R, E, M>(p, v, n2, t);
+        apply_fourstep<false, R, E, M>(p, v, n2 + p.n2_off, t);
 #pragma unroll
         for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
     }
@@ -740,215 +757,5 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// k_col_pipe: the fused column pass as a PERSISTENT, software-pipelined kernel.
-//
-// k_col_mid is latency-bound (ncu: 28 % of the warp time waits for the tile loads, 28 % at the
-// per-waveform barrier, ~35 % computes).  Here the grid is  G groups x `total` CTAs  (total = tiles of
-// one waveform, all resident); CTA j of group g owns tile j of the waveforms g, g+G, g+2G, ... and runs
-//
-//     iteration i:   B(w[i-1])  ->  cp.async prefetch of w[i+1]  ->  A(w[i])
-//
-//   A(w): tile (already prefetched into shared memory) -> registers, conj twiddle, inverse column
-//         transforms, 1/N, max|A|^2 -> publish the tile maximum (LL words), park the tile in shared memory.
-//   B(w): the maxima of w were published one phase ago -> controller, merged Kerr rotation, new stash,
-//         forward column transforms, twiddle, store.
-//
-// so the tile and stash loads of the next waveform fly during a whole iteration and the barrier of
-// w[i] is polled only after the B phase of w[i-1]... i.e. one phase later.  Tiles are assigned statically
-// (all CTAs resident, no tickets): every sibling a B phase waits for is running and can only be waiting on
-// OLDER waveforms, so there is no deadlock.  Two shared-memory slots per CTA (tile + stash each).
-// ---------------------------------------------------------------------------------------------
-template <typename R, int M, int T, int SYNC>
-__global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), (T * (M / points_per_thread<R>::value)) <= 256 ? 2 : 1)
-k_col_pipe(Params<R> p) {   // two CTAs per SM: shared memory (2 tile slots each) is the limit, so up to 128 registers
-    typedef typename cx_of<R>::type C;
-    constexpr int E = points_per_thread<R>::value;
-    constexpr int NT = T * (M / E);
-    constexpr int NWARPS = (NT + 31) / 32;
-    constexpr int NW = sizeof(R) / 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long red[32];
-    __shared__ int s_done[2], s_steps[2];
-    __shared__ double s_h[2], s_z[2];
-    C* tw = reinterpret_cast<C*>(smem_raw);                              // pass tables + sincos table
-    const C* sct = tw + fft_plan<M, E>::table_size;
-    C* fbuf = tw + fft_plan<M, E>::table_size + SC_N;                     // 2 x [M][T] tile slots
-    R* sbuf = reinterpret_cast<R*>(fbuf + 2 * M * T);                     // 2 x [E][NT] stash slots
-
-    const int tiles = p.n2 / T;
-    const int total = tiles * p.n_pol;
-    const int ngroups = gridDim.x / total;
-    const int grp = blockIdx.x / total, me = blockIdx.x % total;
-    const int pol = me / tiles, tile = me % tiles;
-    const int c = threadIdx.x % T, t = threadIdx.x / T;
-    const int n2 = tile * T + c;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_my = (p.batch - grp + ngroups - 1) / ngroups;            // waveforms grp, grp+ngroups, ...
-
-    load_tables(tw, p.tw_col, fft_plan<M, E>::table_size + SC_N);
-
-    auto prefetch = [&](int i) {                                          // waveform i of this CTA -> slot i&1
-        const int w = grp + i * ngroups, slot = i & 1;
-        const size_t row = (size_t)w * p.n_pol + pol;
-        const C* __restrict__ rowp = p.field + row * p.n;
-        const R* __restrict__ strow = p.stash + row * p.n;
-        C* f = fbuf + slot * (M * T);
-        R* st = sbuf + slot * (E * NT);
-        if (threadIdx.x == 0) {                                           // controller state of w, once per CTA
-            const Ctrl* c0 = p.ctrl + w;
-            s_done[slot] = *reinterpret_cast<const volatile int*>(&c0->done);
-            s_steps[slot] = *reinterpret_cast<const volatile int*>(&c0->steps);
-            s_z[slot] = *reinterpret_cast<const volatile double*>(&c0->z);
-            s_h[slot] = *reinterpret_cast<const volatile double*>(&c0->h);
-            if (SYNC == SYNC_FIXED) { __threadfence(); atomicAdd(&p.ctrl[w].arrived, 1u); }
-        }
-#pragma unroll
-        for (int q = 0; q < E; ++q) {
-            const size_t off = (size_t)(t + q * (M / E)) * p.n2 + n2;
-            cp_async<sizeof(C)>(f + (t + q * (M / E)) * T + c, rowp + off);
-            if (p.has_nl) cp_async<sizeof(R)>(st + q * NT + threadIdx.x, strow + off);
-        }
-        cp_async_commit();
-    };
-
-    if (n_my > 0) prefetch(0);
-    // state carried from A(w[i]) to B(w[i]) (uniform over the CTA)
-    int a_valid = 0, a_steps = 0; R a_z = 0, a_h = 0;
-
-    for (int i = 0; i <= n_my; ++i) {
-        // ---------------- B(w[i-1]) -----------------------------------------------------------------
-        if (i > 0 && a_valid) {
-            const int w = grp + (i - 1) * ngroups, slot = (i - 1) & 1;
-            const size_t row = (size_t)w * p.n_pol + pol;
-            C* __restrict__ rowp = p.field + row * p.n;
-            R* __restrict__ strow = p.stash + row * p.n;
-            C* f = fbuf + slot * (M * T);
-            const R* st = sbuf + slot * (E * NT);
-            CtrlNext<R> nx;
-            if (SYNC == SYNC_FIXED) {
-                nx = controller_next<R>(p, a_z, a_h, a_steps, (R)0);
-                if (me == 0 && threadIdx.x == 0) {
-                    while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl[w].arrived) < (unsigned)total) __nanosleep(32);
-                    controller_commit<R>(p, w, a_h, a_steps, nx);
-                }
-            } else {
-                if (warp == 0) {                                          // poll the LL words of waveform w
-                    const unsigned long long tag = (unsigned long long)(unsigned)(a_steps + 1);
-                    volatile unsigned long long* wf = p.slots + (size_t)w * total * 2;
-                    unsigned long long best = 0ull;
-                    const int nwords = total * NW;
-                    for (int base = 0; base < nwords; base += 32) {
-                        const int idx = base + lane;
-                        const bool have = idx < nwords;
-                        unsigned long long x = tag;
-                        for (;;) {
-                            if (have) x = wf[(idx / NW) * 2 + (idx % NW)];
-                            if (__all_sync(0xffffffffu, !have || (x & 0xffffffffull) == tag)) break;
-                            __nanosleep(20);
-                        }
-                        unsigned long long val = have ? (x >> 32) : 0ull;
-                        if (NW == 2) {
-                            const unsigned long long other = __shfl_xor_sync(0xffffffffu, val, 1);
-                            val = (lane & 1) ? 0ull : ((val << 32) | other);
-                        }
-                        best = val > best ? val : best;
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
-                    if (lane == 0) red[0] = best;
-                }
-                __syncthreads();
-                nx = controller_next<R>(p, a_z, a_h, a_steps, from_bits<R>(red[0]));
-                if (me == 0 && threadIdx.x == 0) controller_commit<R>(p, w, a_h, a_steps, nx);
-            }
-            C v[E];
-#pragma unroll
-            for (int q = 0; q < E; ++q) v[q] = f[(t + q * (M / E)) * T + c];        // the parked tile (own points)
-            if (nx.done) {                                                        // last step of w: time domain out
-#pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    if (p.has_nl) {
-                        R sn, co; sincos_r(st[q * NT + threadIdx.x], sct, &sn, &co);
-                        v[q] = cmul(v[q], mk<R>(co, sn));
-                    }
-                    rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
-                }
-            } else {
-                if (p.has_nl) {
-                    const R hh = nx.h / (R)2;                                     // h_/2 of the NEXT step
-#pragma unroll
-                    for (int q = 0; q < E; ++q) {
-                        const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
-                        const R ph = mul_rn(hh, mul_rn(p.gamma, pw));
-                        const R tot = st[q * NT + threadIdx.x] + ph;
-                        strow[(size_t)(t + q * (M / E)) * p.n2 + n2] = ph;
-                        R sn, co; sincos_r(tot, sct, &sn, &co);
-                        v[q] = cmul(v[q], mk<R>(co, sn));
-                    }
-                }
-                fft_passes<R, M, -1, ColExchange<T>, E>::run(v, f + c, tw, t);
-                apply_fourstep<false, R, E, M>(p, v, n2, t);
-#pragma unroll
-                for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
-            }
-            __syncthreads();                                      // slot (i-1)&1 is free for the next prefetch
-        }
-        // ---------------- prefetch w[i+1] into the slot B just released ------------------------------------
-        if (i + 1 < n_my) prefetch(i + 1);
-        // ---------------- A(w[i]) ----------------------------------------------------------------------
-        a_valid = 0;
-        if (i < n_my) {
-            const int w = grp + i * ngroups, slot = i & 1;
-            C* f = fbuf + slot * (M * T);
-            if (i + 1 < n_my) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-            else cp_async_wait_all();
-            __syncthreads();                                      // tile landed for every thread; s_* handed over
-            if (!s_done[slot]) {
-                a_valid = 1; a_steps = s_steps[slot]; a_z = (R)s_z[slot]; a_h = (R)s_h[slot];
-                C v[E];
-#pragma unroll
-                for (int q = 0; q < E; ++q) v[q] = f[(t + q * (M / E)) * T + c];
-                apply_fourstep<true, R, E, M>(p, v, n2, t);
-                fft_passes<R, M, +1, ColExchange<T>, E>::run(v, f + c, tw, t);
-                R pm = 0;
-                bool nan = false;
-                const R sc = p.inv_n * exp_r(mul_rn(p.att_half, a_h));
-#pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    v[q].x *= sc; v[q].y *= sc;                    // 1/N and the attenuation of the step
-                    const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
-                    nan |= (pw != pw);
-                    pm = pw > pm ? pw : pm;
-                }
-                if (nan) pm = pw_nan<R>();
-                unsigned long long bits = ord_bits(pm);
-                if (SYNC != SYNC_FIXED) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
-                    if (lane == 0) red[warp] = bits;
-                }
-                __syncthreads();                                  // all exchange reads done: the slot can take the parked tile
-#pragma unroll
-                for (int q = 0; q < E; ++q) f[(t + q * (M / E)) * T + c] = v[q];
-                if (SYNC != SYNC_FIXED && warp == 0) {
-                    bits = lane < NWARPS ? red[lane] : 0ull;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
-                    if (lane < NW) {
-                        const unsigned long long tag = (unsigned long long)(unsigned)(a_steps + 1);
-                        const unsigned long long part = (NW == 1) ? (bits & 0xffffffffull) : (lane == 0 ? (bits >> 32) : (bits & 0xffffffffull));
-                        volatile unsigned long long* wf = p.slots + (size_t)w * total * 2;
-                        wf[me * 2 + lane] = (part << 32) | tag;
-                    }
-                }
-            } else if (SYNC == SYNC_FIXED && me == 0 && threadIdx.x == 0) {
-                while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl[w].arrived) < (unsigned)total) __nanosleep(32);
-                p.ctrl[w].arrived = 0u;
-            }
-        }
-    }
-}
 
 }  // namespace ssfm

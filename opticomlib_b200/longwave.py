@@ -1,0 +1,315 @@
+"""Long waveforms: one FIBER / DBP propagation whose transform is split as N = N0 x N_l.
+
+Two uses, one code path (BASELINE config #5):
+
+* a single GPU and N > 2^22 samples (up to 2^30): the outer N0-point stage and the inner N_l-point stage
+  both run on the same device and no data moves between them;
+* one waveform spread over the G GPUs of a process group: rank g keeps columns [g N_l/G, (g+1) N_l/G) of the
+  N0 x N_l sample matrix in the time domain and rows [g N0/G, (g+1) N0/G) of the (transposed-order) spectrum;
+  the two layouts are exchanged with ``torch.distributed.all_to_all_single`` (NCCL over NVLink on the GPU
+  box, gloo in the CPU tests of the index logic) -- twice per split step -- plus one scalar all-reduce (MAX)
+  per step in adaptive mode.  Every arithmetic operation stays in the CUDA kernels behind the C-ABI
+  (``ssfm_long_*`` in include/ssfm_b200.h); this module only sequences stages and moves bytes.
+
+The statements reproduced are the same as for short waveforms (opticomlib/devices.py:1155-1196); the
+reference itself has no multi-device path.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib, engine
+
+INNER_LOG2 = 18          # preferred inner transform length N_l = 2^18 (512 x 512 two-pass kernels)
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def split_sizes(n_global: int, n_ranks: int = 1, n_outer: int | None = None):
+    """(N0, N_l) for a waveform of ``n_global`` samples on ``n_ranks`` devices."""
+    if n_global & (n_global - 1) or n_global < (1 << 12):
+        raise ValueError("long waveforms need a power-of-two length >= 2^12, got %d" % n_global)
+    m = n_global.bit_length() - 1
+    if n_outer is None:
+        lo = max(4, m - 22, int(math.log2(max(n_ranks, 1))))
+        hi = min(11, m - 8)
+        n_outer = 1 << min(max(m - INNER_LOG2, lo), hi)
+    n_inner = n_global // n_outer
+    if n_outer % n_ranks or n_inner % n_ranks or n_inner // n_ranks < 32:
+        raise ValueError("cannot split %d samples as %d x %d over %d ranks" % (n_global, n_outer, n_inner, n_ranks))
+    return n_outer, n_inner
+
+
+def fixed_step_count(length, h, real) -> int:
+    """Number of steps of the fixed-h controller (devices.py:1159-1162, 1173, 1195-1196) in the compute real type."""
+    R = np.float32 if real in (np.float32, "fp32") else np.float64
+    L, hk, z = R(length), R(h), R(0)
+    hk = L if L < hk else hk
+    steps = 0
+    while z < L:
+        z = R(z + hk)
+        steps += 1
+        rem = R(L - z)
+        hk = rem if rem < hk else hk
+    return steps
+
+
+def local_columns(x_full, n_outer: int, n_ranks: int, rank: int):
+    """This rank's time-domain share of a full waveform x[N]: columns of the N0 x N_l matrix, as [N0, N_l/G]."""
+    n = x_full.shape[-1]
+    n_inner = n // n_outer
+    w = n_inner // n_ranks
+    return x_full.reshape(n_outer, n_inner)[:, rank * w:(rank + 1) * w]
+
+
+class CudaStages:
+    """The stage kernels of one rank behind the C-ABI (``ssfm_long_*``): outer tables, stash, controller, inner plan."""
+
+    def __init__(self, n_global, n_outer, ranks, rank, cdtype, device):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.device = device
+        code = _lib.SSFM_C64 if cdtype == torch.complex64 else _lib.SSFM_C128
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.ssfm_long_plan_create(ctypes.byref(h), n_global, n_outer, ranks, rank, code, device.index))
+        self.handle = h
+
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def begin(self, field, prm):
+        _lib.check(self.lib.ssfm_long_begin(self.handle, field.data_ptr(), ctypes.byref(prm), self._stream()))
+
+    def pmax(self, value=None):
+        v = ctypes.c_double(0.0 if value is None else value)
+        _lib.check(self.lib.ssfm_long_pmax(self.handle, ctypes.byref(v), 0 if value is None else 1, self._stream()))
+        return v.value
+
+    def ctrl(self, init):
+        _lib.check(self.lib.ssfm_long_ctrl(self.handle, 1 if init else 0, self._stream()))
+
+    def outer(self, field, stage):
+        _lib.check(self.lib.ssfm_long_outer(self.handle, field.data_ptr(), stage, self._stream()))
+
+    def inner(self, rows):
+        _lib.check(self.lib.ssfm_long_inner(self.handle, rows.data_ptr(), self._stream()))
+
+    def sync(self):
+        _torch().cuda.current_stream(self.device).synchronize()
+
+    def state(self, want_log=False):
+        steps = np.empty(1, np.int32); z = np.empty(1, np.float64); hn = np.empty(1, np.float64); done = np.empty(1, np.int32)
+        _lib.check(self.lib.ssfm_get_state(self.handle, steps.ctypes.data, z.ctypes.data, hn.ctypes.data, done.ctypes.data))
+        log = None
+        if want_log:
+            cap = int(max(1, steps.max()))
+            log = np.zeros((1, cap), np.float64)
+            _lib.check(self.lib.ssfm_get_step_log(self.handle, log.ctypes.data, cap))
+        return engine.StepInfo(steps, z, hn, done.astype(bool), log)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ssfm_plan_destroy(self.handle)
+            self.handle = None
+
+
+class LongPlan:
+    """Sequencer of one rank: stages (``CudaStages``; the CPU tests inject a NumPy model of the same stages to check
+    the sequencing and the exchange under gloo) + the two layout exchanges + the scalar max all-reduce."""
+
+    def __init__(self, n_global, complex_dtype, device=None, group=None, n_outer=None, stages=None):
+        torch = _torch()
+        self.group = group
+        self.ranks, self.rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            self.ranks, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n = int(n_global)
+        self.n_outer, self.n_inner = split_sizes(self.n, self.ranks, n_outer)
+        self.cols = self.n_inner // self.ranks            # columns of the sample matrix held in the time domain
+        self.rows = self.n_outer // self.ranks            # rows of the spectrum held in the frequency domain
+        self.cdtype = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
+        self.real = np.float32 if self.cdtype == torch.complex64 else np.float64
+        if stages is None:
+            self.device = engine.require_cuda(device)
+            stages = CudaStages(self.n, self.n_outer, self.ranks, self.rank, self.cdtype, self.device)
+        else:
+            self.device = torch.device("cpu")
+        self.stages = stages
+        self._buf = None                                   # exchange buffers (only with more than one rank)
+
+    def close(self):
+        if getattr(self, "stages", None) is not None:
+            self.stages.close()
+            self.stages = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the exchange between the two layouts --------------------------------------------------
+    def _buffers(self, like):
+        torch = _torch()
+        if self._buf is None:
+            self._buf = (torch.empty_like(like), torch.empty((self.rows, self.n_inner), dtype=like.dtype, device=like.device))
+        return self._buf
+
+    def _to_rows(self, field):
+        """[N0][N_l/G] (time layout, outer transform done) -> [N0/G][N_l] (this rank's rows)."""
+        if self.ranks == 1:
+            return field
+        import torch.distributed as dist
+        torch = _torch()
+        recv, rows = self._buffers(field)
+        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(field), group=self.group)
+        # recv[s] = block of my rows that rank s held: [G][N0/G][N_l/G] -> [N0/G][G][N_l/G]
+        rows.view(self.rows, self.ranks, self.cols).copy_(recv.view(self.ranks, self.rows, self.cols).permute(1, 0, 2))
+        return rows
+
+    def _to_columns(self, rows, field):
+        if self.ranks == 1:
+            return
+        import torch.distributed as dist
+        torch = _torch()
+        send, _ = self._buffers(field)
+        send.view(self.ranks, self.rows, self.cols).copy_(rows.view(self.rows, self.ranks, self.cols).permute(1, 0, 2))
+        dist.all_to_all_single(torch.view_as_real(field), torch.view_as_real(send), group=self.group)
+
+    # ---- one propagation ------------------------------------------------------------------------
+    def propagate(self, field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None,
+                  want_log=False) -> engine.StepInfo:
+        """In place on ``field``: CUDA tensor [N0, N_l/G] (this rank's columns of the sample matrix)."""
+        torch = _torch()
+        on_cuda = isinstance(self.stages, CudaStages)
+        if field.dtype != self.cdtype or field.is_cuda != on_cuda or not field.is_contiguous():
+            raise ValueError("field must be a contiguous %s tensor of dtype %s" % ("CUDA" if on_cuda else "CPU", self.cdtype))
+        if tuple(field.shape) != (self.n_outer, self.cols):
+            raise ValueError("field must have shape (%d, %d), got %s" % (self.n_outer, self.cols, tuple(field.shape)))
+        sg = self.stages
+        prm = _lib.FiberParams(float(dt), float(length), float(alpha), float(beta_2), float(beta_3), float(gamma),
+                               float(phi_max), math.nan if h is None else float(h))
+        R = self.real
+        fixed = h is not None
+        single = (not fixed) and ((R(beta_2) == 0 and R(beta_3) == 0) or R(gamma) == 0)
+
+        def combine_max():
+            if self.ranks == 1:
+                return
+            import torch.distributed as dist
+            t = torch.tensor([sg.pmax()], dtype=torch.float64, device=self.device)
+            t = torch.where(torch.isnan(t), torch.full_like(t, float("inf")), t)     # NaN must win the max, as in numpy
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            val = float(t.item())
+            sg.pmax(float("nan") if math.isinf(val) and val > 0 else val)
+
+        ctx = torch.cuda.device(self.device) if on_cuda else _Null()
+        with ctx:
+            sg.begin(field, prm)
+            if not fixed and not single:
+                combine_max()
+            sg.ctrl(True)
+            if sg.state().done[0]:
+                return sg.state(want_log)
+            sg.outer(field, 0)
+            n_fixed = fixed_step_count(length, h, R) if fixed else 0
+            done_steps = 0
+            while True:
+                rows = self._to_rows(field)
+                sg.inner(rows)
+                self._to_columns(rows, field)
+                done_steps += 1
+                if fixed:
+                    sg.outer(field, 1)                           # end of this step (+ start of the next one)
+                    if done_steps >= n_fixed:
+                        break
+                else:
+                    sg.outer(field, 2)
+                    combine_max()
+                    sg.ctrl(False)
+                    if sg.state().done[0]:
+                        break
+                    sg.outer(field, 0)
+            sg.sync()
+        info = sg.state(want_log)
+        if not info.done[0]:
+            raise RuntimeError("long-waveform propagation ended before z reached the fibre length (controller out of step)")
+        return info
+
+    def state(self, want_log=False) -> engine.StepInfo:
+        return self.stages.state(want_log)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_PLANS: dict = {}
+
+
+def get_long_plan(n_global, complex_dtype, device=None, group=None, n_outer=None) -> LongPlan:
+    torch = _torch()
+    dev = engine.require_cuda(device)
+    cd = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
+    key = (int(n_global), cd, dev.index, id(group) if group is not None else None, n_outer)
+    pl = _PLANS.get(key)
+    if pl is None:
+        if len(_PLANS) >= 2:                                # long plans own O(N) device memory
+            _PLANS.pop(next(iter(_PLANS))).close()
+        pl = _PLANS[key] = LongPlan(n_global, cd, dev, group, n_outer)
+    return pl
+
+
+def clear_plans():
+    while _PLANS:
+        _PLANS.popitem()[1].close()
+
+
+def fiber_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
+               precision="fp32", device=None, group=None, n_outer=None, want_log=False, gather=True):
+    """Propagate ONE waveform ``field[N]`` (NumPy array or tensor, the same on every rank of ``group``).
+
+    With ``group=None`` the whole waveform lives on this process's GPU (any power-of-two N in [2^12, 2^30]); with a
+    process group its columns are spread over the ranks and the result is gathered back on every rank
+    (``gather=False`` returns this rank's [N0, N_l/G] share instead).  Returns ``(out, StepInfo)``.
+    """
+    torch = _torch()
+    dev = engine.require_cuda(device)
+    tdtype = torch.complex64 if precision in ("fp32", "float32") else torch.complex128
+    as_numpy = not torch.is_tensor(field)
+    x = torch.from_numpy(np.ascontiguousarray(field)) if as_numpy else field
+    if x.ndim != 1:
+        raise ValueError("fiber_long takes one single-polarisation waveform of shape [N]")
+    plan = get_long_plan(x.shape[0], tdtype, dev, group, n_outer)
+    mine = local_columns(x, plan.n_outer, plan.ranks, plan.rank).to(dev).to(tdtype).contiguous()
+    if mine.data_ptr() == x.data_ptr():
+        mine = mine.clone()
+    info = plan.propagate(mine, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
+    if not gather:
+        return mine, info
+    if plan.ranks > 1:
+        import torch.distributed as dist
+        parts = [torch.empty_like(mine) for _ in range(plan.ranks)]
+        dist.all_gather(parts, mine, group=group)
+        out = torch.cat(parts, dim=1).reshape(-1)
+    else:
+        out = mine.reshape(-1)
+    return (out.cpu().numpy() if as_numpy else out), info
+
+
+def dbp_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, **kw):
+    """devices.py:1280-1283 for long waveforms: FIBER with negated parameters."""
+    return fiber_long(field, dt, length, -alpha, -beta_2, -beta_3, -gamma, phi_max, h, **kw)
