@@ -145,8 +145,11 @@ struct ssfm_plan_s {
     int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
     int placement = -1;          // k_wf: SM-aware team placement (-1 = auto)
+    int cluster = -1;            // k_wf: teams as thread-block clusters (-1 = auto, 0 = never, 1 = always when possible)
     void* wf_sync = nullptr;     // k_wf barriers / mailboxes / max words
     cudaEvent_t wf_ev[2] = {nullptr, nullptr};
+    cudaStream_t wf_side = nullptr;   // k_wf: side stream of the launch that fills the slots the clusters leave
+    cudaEvent_t wf_ev_side = nullptr;
     int last_kind = 0;           // schedule of the last propagate: 0 none, 1 multi-launch, 2 k_wf
     int last_teams = 0;
     int lo_bits = 0;             // split of the four-step twiddle tables (0 = log2 n2)
@@ -390,8 +393,9 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         l.sync_buf = pl->wf_sync; l.num_sms = pl->num_sms;
         l.fixed = fixed ? 1 : 0; l.single = single ? 1 : 0; l.resume = resume ? 1 : 0;
         l.h_fixed = fixed ? prm.h_km : 0.0;
-        l.budget = budget; l.teams_cap = pl->teams_cap; l.placement = pl->placement;
+        l.budget = budget; l.teams_cap = pl->teams_cap; l.placement = pl->placement; l.cluster = pl->cluster;
         l.ev0 = pl->wf_ev[0]; l.ev1 = pl->wf_ev[1];
+        l.side = pl->wf_side; l.ev_side = pl->wf_ev_side;
         int teams = 0;
         const int rc = wf_propagate<R>(p, l, &teams, st);
         if (rc == SSFM_OK) {
@@ -716,6 +720,8 @@ static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t 
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[1], cudaEventDisableTiming);
     if (e == cudaSuccess && with_stash) e = cudaMalloc(&pl->wf_sync, WF_SYNC_BYTES);
+    if (e == cudaSuccess && with_stash) e = cudaStreamCreateWithFlags(&pl->wf_side, cudaStreamNonBlocking);
+    if (e == cudaSuccess && with_stash) e = cudaEventCreateWithFlags(&pl->wf_ev_side, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[1]);
     if (e != cudaSuccess) {
@@ -761,6 +767,8 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
     if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
     cudaFree(pl->wf_sync);
+    if (pl->wf_side) cudaStreamDestroy(pl->wf_side);
+    if (pl->wf_ev_side) cudaEventDestroy(pl->wf_ev_side);
     if (pl->inner) ssfm_plan_destroy(pl->inner);
     if (pl->wf_ev[0]) cudaEventDestroy(pl->wf_ev[0]);
     if (pl->wf_ev[1]) cudaEventDestroy(pl->wf_ev[1]);
@@ -776,6 +784,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "fused") { pl->fused = (int)value; }   // 0 unfused, 1 fused (LL barrier), 2 fused (atomic barrier), 3 fused (cluster barrier when possible)
     else if (k == "debug") { pl->debug = (int)value; }
     else if (k == "persistent") { pl->persistent = value ? 1 : 0; }
+    else if (k == "cluster") { pl->cluster = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "placement") { pl->placement = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "teams") { if (value < 0) return fail(SSFM_ERR_INVALID, "teams < 0"); pl->teams_cap = (int)value; }
     else if (k == "tw_full") { pl->use_tw_full = value ? 1 : 0; }

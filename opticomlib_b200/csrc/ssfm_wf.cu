@@ -25,10 +25,84 @@ int wf_fail(int code, const std::string& msg) { ssfm_err_slot = msg; return code
             return wf_fail(SSFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+// cluster variant: one thread-block cluster per team (teams of <= 16 CTAs).  16-CTA clusters must sit inside one GPC, so
+// fewer of them are co-resident than the chip has CTA slots (measured on B200: 14 of 18 possible teams in fp64, 21 of 27 in
+// fp32); the slots they leave are filled by a second launch of the flag-based variant on a side stream, whose teams draw
+// from the SAME waveform counter.  (That launch needs no co-residency guarantee: if some of its CTAs are not scheduled
+// at once its teams simply wait until the cluster kernel frees slots.)
+template <typename R, int M1, int M2, bool SMALL>
+int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st, int coop_ctas) {
+    typedef wf_geom<R, M1, M2> GEO;
+    auto kern = k_wf<R, M1, M2, SMALL, true>;
+    const int total = p.n_pol * (p.n2 / GEO::T);
+    static int max_clusters[17] = {0};                           // per instantiation and cluster size
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(GEO::NT); cfg.dynamicSmemBytes = GEO::smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)total; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (max_clusters[total] == 0) {
+        WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
+        WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cfg.gridDim = dim3((unsigned)(total * 64));
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+        max_clusters[total] = n > 0 ? n : -1;
+    }
+    long long teams = max_clusters[total];
+    if (getenv("SSFM_DEBUG"))
+        fprintf(stderr, "[ssfm] k_wf cluster<%d,%d,%d>: %d CTAs per cluster, %lld clusters fit (cooperative: %d CTAs)\n", (int)sizeof(R),
+                M1, M2, total, teams, coop_ctas);
+    if (teams < 1) return SSFM_ERR_UNSUPPORTED;
+    long long fill = (l.side && l.ev_side && l.ev0) ? (coop_ctas - teams * total) / total : 0;   // flag-based teams in the free slots
+    if (l.cluster < 1 && (teams + fill) * total * 10 < (long long)coop_ctas * 8) return SSFM_ERR_UNSUPPORTED;   // < 80 % of the chip
+    if (teams > p.batch) teams = p.batch;
+    if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
+    if (fill > p.batch - teams) fill = p.batch - teams;
+    if (l.teams_cap > 0 && fill > l.teams_cap - teams) fill = l.teams_cap - teams;
+    const size_t head = 4096 + 256;
+    const size_t need = head + (size_t)fill * 256 + (size_t)fill * 2 * total * 16;
+    if (need > WF_SYNC_BYTES) fill = 0;
+    WF_TRY(cudaMemsetAsync(l.sync_buf, 0, fill > 0 ? need : head, st));
+    WfArgs<R> a;
+    std::memset(&a, 0, sizeof(a));
+    char* sb = (char*)l.sync_buf;
+    a.next_wf = (unsigned int*)(sb + 4096 + 128);
+    a.budget = l.budget;
+    a.n_teams = (int)teams;
+    a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
+    a.h_fixed = (R)l.h_fixed;
+    a.occ = 1; a.placement = 0;
+    cfg.gridDim = dim3((unsigned)(teams * total));
+    if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
+    WF_TRY(cudaLaunchKernelEx(&cfg, kern, p, a));
+    ++ssfm_launches;
+    if (fill > 0) {
+        WfArgs<R> b = a;
+        b.sm_cnt = (unsigned int*)sb;
+        b.grid_bar = (unsigned int*)(sb + 4096);
+        b.bar = (unsigned int*)(sb + head);
+        b.mail = (unsigned long long*)(sb + head + (size_t)fill * 128);
+        b.slots = (unsigned long long*)(sb + head + (size_t)fill * 256);
+        b.n_teams = (int)fill;
+        WF_TRY(cudaStreamWaitEvent(l.side, l.ev0, 0));
+        k_wf<R, M1, M2, SMALL, false><<<(unsigned)(fill * total), GEO::NT, GEO::smem, l.side>>>(p, b);
+        WF_TRY(cudaGetLastError());
+        WF_TRY(cudaEventRecord(l.ev_side, l.side));
+        WF_TRY(cudaStreamWaitEvent(st, l.ev_side, 0));
+        ++ssfm_launches;
+    }
+    if (l.ev1) WF_TRY(cudaEventRecord(l.ev1, st));
+    if (teams_out) *teams_out = (int)(teams + fill);
+    return SSFM_OK;
+}
+
 template <typename R, int M1, int M2, bool SMALL>
 int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
     typedef wf_geom<R, M1, M2> GEO;
-    auto kern = k_wf<R, M1, M2, SMALL>;
+    auto kern = k_wf<R, M1, M2, SMALL, false>;
     static int per_sm = -1;                                     // per instantiation; one device kind per process
     if (per_sm < 0) {
         WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
@@ -43,6 +117,12 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     if (teams > p.batch) teams = p.batch;
     if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
     if (teams < 1) return SSFM_ERR_UNSUPPORTED;                          // one waveform does not fit on the chip
+    if constexpr (M2 <= 256) {                                           // teams of <= 16 CTAs can be thread-block clusters
+        if (l.cluster != 0 && total <= 16 && total >= 2) {
+            const int rc = wf_launch_cluster<R, M1, M2, SMALL>(p, l, teams_out, st, per_sm * l.num_sms);
+            if (rc != SSFM_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const long long nslots = 1;
     if (getenv("SSFM_DEBUG"))
         fprintf(stderr, "[ssfm] k_wf<%d,%d,%d,%d>: smem %zu, %d CTAs/SM, team %lld CTAs, %lld teams x %lld slots\n", (int)sizeof(R),

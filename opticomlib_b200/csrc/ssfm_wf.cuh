@@ -88,7 +88,18 @@ struct WfSlot {                   // state of the team's current waveform (unifo
     R z, h;
 };
 
-template <typename R, int M1, int M2, bool SMALL>
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void st_cluster_u32(void* local_smem, unsigned rank, unsigned v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem);
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+
+// CL = true: the team is one thread-block cluster (teams of <= 16 CTAs): the team barrier is the hardware cluster barrier
+// (arrive.release / wait.acquire, executed by every thread), the per-CTA maxima and the waveform index travel through
+// distributed shared memory, and no cooperative launch, registration or global-memory flag is needed.
+template <typename R, int M1, int M2, bool SMALL, bool CL>
 __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> p, WfArgs<R> a) {
     typedef typename cx_of<R>::type C;
     typedef wf_geom<R, M1, M2> GEO;
@@ -96,7 +107,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     static_assert(points_per_thread<R>::value == 16, "k_wf assumes 16 points per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
-    __shared__ unsigned int s_w;
+    __shared__ unsigned int s_w, s_wcl[2];
+    __shared__ unsigned long long cl_max[16];
     C* xb = reinterpret_cast<C*>(smem_raw);                    // exchange buffer: column tile [M1][T] or G padded rows
     constexpr bool TABS = GEO::TABS;
     C* tw1s = xb + GEO::XB;                                    // pass tables of the N1-point (column) transforms
@@ -118,6 +130,11 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     // -3 % in fp64 (two per SM), so the host enables it for fp32 only; teams larger than the SM count are
     // spread by blockIdx.
     __shared__ unsigned int s_slot, s_rank;
+    int team, me;
+    if (CL) {
+        team = (int)cluster_id_x();
+        me = (int)cluster_ctarank();
+    } else {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     if (tid == 0) {
@@ -136,7 +153,6 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     }
     __syncthreads();
     const unsigned int n_sm = gridDim.x / (unsigned)a.occ;
-    int team, me;
     if (!a.placement || total > n_sm) {                        // by blockIdx: consecutive CTAs spread over the SMs
         team = (int)(blockIdx.x % (unsigned)a.n_teams);
         me = (int)(blockIdx.x / (unsigned)a.n_teams);
@@ -148,6 +164,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
         if (grp >= n_sm / total) team = a.n_teams;             // SMs beyond the last full group stay idle
     }
     if (team >= a.n_teams) return;
+    }
 
     const int pol = me / tiles, tile = me % tiles;
     const int c = tid % T, t = tid / T;                        // column phase: column c of the tile, thread t of its transform
@@ -173,11 +190,13 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     // team barrier, split: arrive after the phase's stores, wait before the next phase's loads
     unsigned int* const bar = a.bar + (size_t)team * 32;
     auto bar_arrive = [&](WfSlot<R>& S) {
+        if (CL) { cluster_arrive_release(); return; }           // every thread releases its own stores
         __syncthreads();                                        // every thread's stores are ordered before the release
         S.bar_target += total;
         if (tid == 0) red_release_add_u32(bar, 1u);
     };
     auto bar_wait = [&](const WfSlot<R>& S) {
+        if (CL) { cluster_wait_acquire(); return; }
         if (tid == 0) {
             while ((int)(ld_relaxed_u32(bar) - S.bar_target) < 0) { if (total > 32u) __nanosleep(20); }   // big teams: ease off L2
             fence_acq_rel_gpu();
@@ -199,6 +218,19 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
         if (lane == 0) red[warp] = bits;
         __syncthreads();
+        if (CL) {                                               // my maximum -> slot [me] of every CTA of the cluster
+            if (tid < (int)total) {
+                unsigned long long b = red[0];
+#pragma unroll
+                for (int i = 1; i < NT / 32; ++i) b = red[i] > b ? red[i] : b;
+                st_cluster_u64(&cl_max[me], (unsigned)tid, b);
+            }
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            unsigned long long m = cl_max[0];
+            for (unsigned i = 1; i < total; ++i) m = cl_max[i] > m ? cl_max[i] : m;
+            return from_bits<R>(m);                             // (the next write to cl_max / red is behind a later cluster barrier)
+        }
         const int nwords = (int)total * NW;
         unsigned long long best = 0ull;
         if (warp * 32 < nwords) {                               // the first warps publish (warp 0) and poll
@@ -251,7 +283,16 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
             if (S.state == WF_GRAB) {
                 // ---------------------------------------------------------- next waveform of this slot
                 ++S.seq;
-                if (tid == 0) {
+                if (CL) {                                       // CTA 0 of the cluster draws the waveform and posts it to every CTA
+                    if (me == 0) {
+                        if (tid == 0) s_w = atomicAdd(a.next_wf, 1u);
+                        __syncthreads();
+                        if (tid < (int)total) st_cluster_u32(&s_wcl[S.seq & 1u], (unsigned)tid, s_w);
+                    }
+                    cluster_arrive_release();
+                    cluster_wait_acquire();
+                    if (tid == 0) s_w = s_wcl[S.seq & 1u];
+                } else if (tid == 0) {
                     volatile unsigned long long* mb = a.mail + (size_t)team * 16;
                     unsigned int wn;
                     if (me == 0) {

@@ -14,6 +14,10 @@ struct WfLaunch {
     int teams_cap;           // 0 = as many teams as fit on the chip
     int placement;           // 1 = SM-aware team placement, 0 = by blockIdx, -1 = auto (measured: on for fp32 with three
                              // CTAs per SM, +16 %; off for fp64 with two, where it costs 3 %)
+    int cluster;             // teams of <= 16 CTAs as thread-block clusters: 1 = always, 0 = never, -1 = when >= 80 % of the
+                             // CTA slots of the cooperative variant can be filled with clusters
+    cudaStream_t side;       // side stream + event for the launch that fills the CTA slots the clusters leave (may be null)
+    cudaEvent_t ev_side;
     cudaEvent_t ev0, ev1;    // recorded around the launch on the stream (may be null)
 };
 constexpr size_t WF_SYNC_BYTES = 1u << 20;

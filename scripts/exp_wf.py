@@ -1,4 +1,4 @@
-"""k_wf experiments: slots / teams / placement on `rows` config-#3-like waveforms."""
+"""k_wf experiments: cluster / cooperative variants on `rows` config-#3-like waveforms."""
 import sys, torch
 sys.path.insert(0, '.')
 from opticomlib_b200 import engine, workloads as wl
@@ -11,12 +11,12 @@ for prec in precs:
     x0 = (torch.from_numpy(x).to(dev) * 10 ** 0.5).to(td).repeat(rows, 1).contiguous()
     x0 = x0 * (1 + 0.01 * torch.rand((rows, 1), device=dev, dtype=torch.float64)).to(td)
     plan = engine.get_plan(x0.shape[1], 1, rows, td, dev)
-    for slots, teams, placement in ((1, 0, 1), (2, 0, 1), (3, 0, 1), (4, 0, 1), (2, 0, 0), (2, 9, 1), (4, 9, 1)):
-        plan.set_option('placement', placement); plan.set_option('slots', slots); plan.set_option('teams', teams)
+    for cluster, teams in ((0, 0), (1, 0), (-1, 0), (1, 8), (0, 8)):
+        plan.set_option('cluster', cluster); plan.set_option('teams', teams)
         best = 1e9
         for i in range(3):
             w = x0.clone()
             info = plan.propagate(w, dt, **kw)
             kind, tm, ms = plan.last_timing()
             best = min(best, ms)
-        print('%s slots %d teams %d placement %d (in flight %d): %.2f ms  %.3e sample*steps/s' % (prec, slots, teams, placement, tm, best, info.sample_steps(x0.shape[1]) / best * 1e3), flush=True)
+        print('%s cluster %d teams %d (in flight %d): %.2f ms  %.3e sample*steps/s' % (prec, cluster, teams, tm, best, info.sample_steps(x0.shape[1]) / best * 1e3), flush=True)

@@ -118,14 +118,15 @@ def test_more_waveforms_than_teams_with_diverging_step_counts(ob, precision):
     import torch
     td = torch.complex64 if precision == "fp32" else torch.complex128
     plan = engine.get_plan(n, 1, rows, td, torch.device("cuda", 0))
-    for teams_cap, placement in ((3, -1), (5, 0), (5, 1), (0, 0), (0, 1)):
-        plan.set_option("teams", teams_cap); plan.set_option("placement", placement)
+    # (cluster = 1: each team is a thread-block cluster with hardware barriers; 0: cooperative launch, barriers through L2)
+    for teams_cap, placement, cluster in ((3, -1, 0), (5, 0, 0), (5, 1, 0), (0, 0, 0), (0, 1, 0), (0, -1, 1), (3, -1, 1)):
+        plan.set_option("teams", teams_cap); plan.set_option("placement", placement); plan.set_option("cluster", cluster)
         try:
             out_3, info_3 = ob.fiber_batch(x, DT, precision=precision, persistent=True, **kw)
             if teams_cap:
                 assert plan.last_timing()[1] == teams_cap               # waveforms in flight
         finally:
-            plan.set_option("teams", 0); plan.set_option("placement", -1)
+            plan.set_option("teams", 0); plan.set_option("placement", -1); plan.set_option("cluster", -1)
         assert np.array_equal(out_3, out) and np.array_equal(info_3.steps, info.steps)
 
 
