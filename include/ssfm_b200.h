@@ -65,8 +65,11 @@ SSFM_API int         ssfm_abi_version(void);
 SSFM_API const char* ssfm_last_error(void);
 
 /* Plan for `n_waveforms` independent waveforms of `n_pol` (1|2) polarisation rows of `n_samples`
- * complex samples each.  n_samples must be a power of two, 2^8 <= n <= 2^22.  Holds the twiddle
- * tables, the Kerr-phase stash and the per-waveform controller state on `device`. */
+ * complex samples each.  Powers of two 2^8 <= n <= 2^22 run on the two-pass transform kernels; any
+ * other length 2 <= n <= 2^21 (the reference accepts any N, numpy.fft) runs the same statements with
+ * chirp-z (Bluestein) transforms built on those kernels -- correct but about an order of magnitude
+ * slower per sample; longer power-of-two waveforms: ssfm_long_plan_create.  Holds the twiddle tables,
+ * the Kerr-phase stash and the per-waveform controller state on `device`. */
 SSFM_API int ssfm_plan_create(ssfm_plan_t* plan, int64_t n_samples, int32_t n_pol, int64_t n_waveforms,
                      int32_t dtype, int32_t device);
 SSFM_API int ssfm_plan_destroy(ssfm_plan_t plan);

@@ -1,6 +1,7 @@
 // C-ABI of the split-step Fourier engine (see include/ssfm_b200.h) and the host-side step loop.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -157,6 +158,10 @@ struct ssfm_plan_s {
     long long long_n = 0;        // global transform length N = N0 x N_l (0 = ordinary plan)
     int long_ranks = 1, long_rank = 0;
     ssfm_plan_t inner = nullptr; // N_l-point transforms of the N0 / ranks rows this rank owns after the exchange
+                                 // (chirp plans: the M-point transforms of the padded rows)
+    // arbitrary lengths (chirp-z / Bluestein): n is not a power of two; rows are padded to chirp_m = 2^ceil(log2(2n-1))
+    long long chirp_m = 0;
+    void *wb = nullptr, *wtab = nullptr, *xf_fwd = nullptr, *xf_inv = nullptr;   // padded work rows, chirp, chirp spectra
     int n_active = 0;
     double* hlog = nullptr;
     int hlog_cap = 0;
@@ -170,6 +175,10 @@ struct ssfm_plan_s {
 
 static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, int32_t dtype, int32_t device,
                             bool with_stash);
+static int chirp_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, int32_t dtype, int32_t device);
+template <typename R>
+static int chirp_propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long long max_steps, int resume,
+                             cudaStream_t st);
 
 namespace {
 
@@ -644,6 +653,7 @@ extern "C" {
 
 int ssfm_apply_transfer(ssfm_plan_t pl, void* field, const void* h_dev, void* stream) {
     if (!pl || !field || !h_dev) return fail(SSFM_ERR_INVALID, "null plan, field or transfer function");
+    if (pl->chirp_m || pl->long_n) return fail(SSFM_ERR_UNSUPPORTED, "transfer functions need a power-of-two plan of at most 2^22 samples");
     CU_TRY(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_xfer(pl);
@@ -668,6 +678,7 @@ int64_t ssfm_launch_count(void) { return ssfm_launches; }
 int ssfm_time_step_kernels(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, int32_t reps, float* ms3,
                            void* stream) {
     if (!pl || !field || !prm || !ms3 || reps < 1) return fail(SSFM_ERR_INVALID, "null argument or reps < 1");
+    if (pl->chirp_m || pl->long_n) return fail(SSFM_ERR_UNSUPPORTED, "per-kernel timing needs a power-of-two plan of at most 2^22 samples");
     CU_TRY(cudaSetDevice(pl->device));
     if (pl->dtype == SSFM_C64) return time_kernels_t<float>(pl, field, *prm, reps, ms3, (cudaStream_t)stream);
     return time_kernels_t<double>(pl, field, *prm, reps, ms3, (cudaStream_t)stream);
@@ -689,8 +700,11 @@ static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t 
     if (n_pol != 1 && n_pol != 2) return fail(SSFM_ERR_INVALID, "n_pol must be either 1 or 2");
     if (batch < 1) return fail(SSFM_ERR_INVALID, "n_waveforms must be >= 1");
     if (dtype != SSFM_C64 && dtype != SSFM_C128) return fail(SSFM_ERR_INVALID, "dtype must be SSFM_C64 or SSFM_C128");
+    if (with_stash && n >= 2 && n <= (1ll << 21) && (n < 256 || (n & (n - 1))))
+        return chirp_plan_create(out, n, n_pol, batch, dtype, device);      // any other length: chirp-z transforms
     if (n < 256 || n > (1ll << 22) || (n & (n - 1)))
-        return fail(SSFM_ERR_UNSUPPORTED, "n_samples must be a power of two in [2^8, 2^22]");
+        return fail(SSFM_ERR_UNSUPPORTED, "n_samples must be in [2, 2^21], or a power of two up to 2^22 "
+                                          "(longer power-of-two waveforms: ssfm_long_plan_create)");
     CU_TRY(cudaSetDevice(device));
     ssfm_plan_s* pl = new ssfm_plan_s();
     pl->device = device; pl->dtype = dtype; pl->n_pol = n_pol; pl->n = n; pl->batch = batch;
@@ -767,6 +781,7 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (pl->ev[0]) cudaEventDestroy(pl->ev[0]);
     if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
     cudaFree(pl->wf_sync);
+    cudaFree(pl->wb); cudaFree(pl->wtab); cudaFree(pl->xf_fwd); cudaFree(pl->xf_inv);
     if (pl->wf_side) cudaStreamDestroy(pl->wf_side);
     if (pl->wf_ev_side) cudaEventDestroy(pl->wf_ev_side);
     if (pl->inner) ssfm_plan_destroy(pl->inner);
@@ -803,6 +818,10 @@ int ssfm_propagate(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, in
     if (resume && !pl->have_state) return fail(SSFM_ERR_INVALID, "resume requested but the plan holds no controller state");
     CU_TRY(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (pl->chirp_m) {
+        if (pl->dtype == SSFM_C64) return chirp_propagate_t<float>(pl, field, *prm, max_steps, resume, st);
+        return chirp_propagate_t<double>(pl, field, *prm, max_steps, resume, st);
+    }
     if (pl->dtype == SSFM_C64) return propagate_t<float>(pl, field, *prm, max_steps, resume, st);
     return propagate_t<double>(pl, field, *prm, max_steps, resume, st);
 }
@@ -1092,3 +1111,148 @@ int ssfm_long_inner(ssfm_plan_t pl, void* rows_local, void* stream) {
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// Arbitrary lengths (chirp-z): see the kernels k_bs_* in ssfm_kernels.cuh.
+// =================================================================================================
+namespace {
+
+// FFT_M -> * xf -> IFFT_M of the padded rows with the power-of-two kernels (xf already in transposed order)
+template <typename R>
+int chirp_transfer(ssfm_plan_t pl, const void* xf, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    ssfm_plan_t pi = pl->inner;
+    ssfm_fiber_params prm{};
+    prm.dt_s = 1.0; prm.length_km = 1e30; prm.phi_max_rad = 0.01; prm.h_km = 1.0;
+    bool fixed, single;
+    Params<R> p = base_params<R>(pi, prm, fixed, single);
+    p.field = (C*)pl->wb; p.stash = nullptr; p.ctrl = pi->ctrl; p.active = pi->active; p.hlog = nullptr;
+    p.ticket = pi->ticket; p.slots = pi->slots; p.batch = (int)pi->batch; p.xfer = (const C*)xf;
+    p.inner = 1; p.has_nl = 0; p.att_half = (R)0;              // dummy controller word (done = 0), no scaling but 1/M
+    int rc = enqueue_col<R>(p, COL_FWD, st);
+    if (!rc) rc = enqueue_row<R>(p, st);
+    if (!rc) rc = enqueue_col<R>(p, COL_INV, st);
+    return rc;
+}
+
+template <typename R>
+int chirp_build_tables(ssfm_plan_t pl) {
+    typedef typename cx_of<R>::type C;
+    ssfm_plan_t pi = pl->inner;
+    const int n = (int)pl->n, m = (int)pl->chirp_m;
+    k_bs_chirp<R><<<(n + 255) / 256, 256>>>((C*)pl->wtab, n);
+    for (int which = 0; which < 2; ++which) {                   // forward: FFT_M(conj w); inverse: FFT_M(w)
+        C* dst = (C*)(which == 0 ? pl->xf_fwd : pl->xf_inv);
+        k_bs_kernel_row<R><<<(m + 255) / 256, 256>>>(dst, (const C*)pl->wtab, n, m, which == 0 ? 1 : 0);
+        ssfm_fiber_params prm{};
+        prm.dt_s = 1.0; prm.length_km = 1e30; prm.phi_max_rad = 0.01; prm.h_km = 1.0;
+        bool fixed, single;
+        Params<R> p = base_params<R>(pi, prm, fixed, single);
+        p.field = dst; p.ctrl = pi->ctrl; p.active = pi->active; p.ticket = pi->ticket; p.slots = pi->slots;
+        p.batch = 1; p.inner = 1; p.has_nl = 0; p.fwd_only = 1;
+        int rc = enqueue_col<R>(p, COL_FWD, 0);
+        if (!rc) rc = enqueue_row<R>(p, 0);                     // spectrum of the chirp, left in transposed order in place
+        if (rc) return rc;
+    }
+    CU_TRY(cudaGetLastError());
+    return SSFM_OK;
+}
+
+}  // namespace
+
+static int chirp_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t batch, int32_t dtype, int32_t device) {
+    CU_TRY(cudaSetDevice(device));
+    long long m = 256;
+    while (m < 2 * n - 1) m <<= 1;
+    ssfm_plan_s* pl = new ssfm_plan_s();
+    pl->device = device; pl->dtype = dtype; pl->n_pol = n_pol; pl->n = n; pl->batch = batch;
+    pl->chirp_m = m; pl->persistent = 0;
+    pl->hlog_cap = 4096;
+    if ((size_t)batch * pl->hlog_cap * sizeof(double) > (256u << 20)) pl->hlog_cap = (int)((256u << 20) / (batch * sizeof(double)));
+    if (pl->hlog_cap < 16) pl->hlog_cap = 16;
+    const size_t rsz = dtype == SSFM_C64 ? 4 : 8, csz = 2 * rsz;
+    const size_t rows = (size_t)batch * n_pol;
+    cudaError_t e = cudaMalloc(&pl->stash, rows * (size_t)n * rsz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ctrl, sizeof(Ctrl) * (size_t)batch);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->active, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->hlog, sizeof(double) * (size_t)batch * pl->hlog_cap);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->wb, rows * (size_t)m * csz);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->wtab, (size_t)n * csz);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->xf_fwd, (size_t)m * csz);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->xf_inv, (size_t)m * csz);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&pl->active_host, 2 * sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[1]);
+    if (e != cudaSuccess) {
+        ssfm_plan_destroy(pl);
+        return fail(e == cudaErrorMemoryAllocation ? SSFM_ERR_NOMEM : SSFM_ERR_CUDA,
+                    std::string("chirp plan allocation: ") + cudaGetErrorString(e));
+    }
+    CU_TRY(cudaMemset(pl->ctrl, 0, sizeof(Ctrl) * (size_t)batch));
+    CU_TRY(cudaMemset(pl->hlog, 0, sizeof(double) * (size_t)batch * pl->hlog_cap));
+    int rc = plan_create_impl(&pl->inner, m, 1, (int64_t)rows, dtype, device, false);
+    if (!rc) rc = dtype == SSFM_C64 ? chirp_build_tables<float>(pl) : chirp_build_tables<double>(pl);
+    if (rc) { ssfm_plan_destroy(pl); return rc; }
+    cudaError_t es = cudaDeviceSynchronize();
+    if (es != cudaSuccess) { ssfm_plan_destroy(pl); return fail(SSFM_ERR_CUDA, std::string("chirp tables: ") + cudaGetErrorString(es)); }
+    *out = pl;
+    return SSFM_OK;
+}
+
+template <typename R>
+static int chirp_propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long long max_steps, int resume,
+                             cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    bool fixed, single;
+    Params<R> p = base_params<R>(pl, prm, fixed, single);
+    ssfm_plan_t pi = pl->inner;
+    const int E = points_per_thread<R>::value;
+    const C* sct = (const C*)pi->tw_col + pass_table_size(pi->n1, E);          // sincos table behind the inner pass tables
+    p.field = (C*)field; p.stash = (R*)pl->stash; p.ctrl = pl->ctrl; p.active = pl->active; p.hlog = pl->hlog;
+    p.batch = (int)pl->batch;
+    p.n_glob = (int)pl->n;
+    p.inv_n = (R)1 / (R)pl->n;
+    const int m = (int)pl->chirp_m;
+    const int rows = (int)(pl->batch * pl->n_pol);
+    const long long budget = max_steps > 0 ? max_steps : (1ll << 40);
+    pl->last_kind = 1;
+    int act = (int)pl->batch;
+    if (!resume) {
+        CU_TRY(cudaMemcpyAsync(p.active, &act, sizeof(int), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)pl->batch, st));
+        if (!fixed && !single) {
+            k_power_max<R><<<(unsigned)(pl->batch * 8), 256, 0, st>>>(p, 8);
+            ++ssfm_launches;
+        }
+        k_ctrl_init<R><<<(unsigned)((pl->batch + 127) / 128), 128, 0, st>>>(p, fixed ? 1 : 0, fixed ? (R)prm.h_km : (R)0, single ? 1 : 0);
+        ++ssfm_launches;
+    } else {
+        std::vector<Ctrl> h((size_t)pl->batch);
+        CU_TRY(cudaMemcpyAsync(h.data(), p.ctrl, sizeof(Ctrl) * h.size(), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        act = 0;
+        for (auto& c : h) act += c.done ? 0 : 1;
+        CU_TRY(cudaMemcpyAsync(p.active, &act, sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(cudaMemcpyAsync(&pl->active_host[0], p.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    const dim3 grid((unsigned)std::min<long long>((m + 255) / 256, 1024), (unsigned)rows);
+    for (long long s = 0; s < budget && pl->active_host[0] > 0; ++s) {
+        k_bs_open<R><<<grid, 256, 0, st>>>(p, (C*)pl->wb, (const C*)pl->wtab, m, sct);
+        int rc = chirp_transfer<R>(pl, pl->xf_fwd, st);
+        if (rc) return rc;
+        k_bs_mid<R><<<grid, 256, 0, st>>>(p, (C*)pl->wb, m, sct);
+        rc = chirp_transfer<R>(pl, pl->xf_inv, st);
+        if (rc) return rc;
+        k_bs_close<R><<<grid, 256, 0, st>>>(p, (const C*)pl->wb, (const C*)pl->wtab, m, sct);
+        k_ctrl_steps<R><<<(unsigned)((pl->batch + 127) / 128), 128, 0, st>>>(p);
+        ssfm_launches += 4;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(&pl->active_host[0], p.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    pl->have_state = true;
+    pl->last = prm;
+    return SSFM_OK;
+}

@@ -63,6 +63,8 @@ struct Params {
     // the controller state of waveform 0 (h, done), the row kernel maps its bins to global bins
     // k = bin_off + row + bin_mul (k1 + N1 k2) with the fftfreq wrap at n_glob, and k_col_inv leaves the controller alone.
     int n2_off, inner, bin_mul, bin_off, n_glob;
+    int fwd_only;        // 1: the row kernel stops after the forward transforms and stores the spectrum (transposed order):
+                         // used once per plan to build the chirp spectra of the arbitrary-length transform
     int defer_ctrl;      // 1: k_col_inv only accumulates max|A|^2 in ctrl.pmax; the controller runs later (k_ctrl_step), after
                          // the maxima of all ranks have been combined
     int n, n1, n2, log2_n2;
@@ -388,6 +390,11 @@ __global__ void __launch_bounds__(G * (M / points_per_thread<R>::value), min_cta
     for (int q = 0; q < E; ++q) v[q] = base[t + q * (M / E)];
     __syncthreads();
     fft_passes<R, M, -1, RowExchange<M, E>, E>::run(v, sm + g * PM, tw, t);
+    if (p.fwd_only) {
+#pragma unroll
+        for (int q = 0; q < E; ++q) base[t + q * (M / E)] = v[q];
+        return;
+    }
 
     if (p.xfer) {   // arbitrary transfer function (zero-phase filters: |H|^2; DM: exp(j w^2 D/2))
         const C* __restrict__ hrow = p.xfer + (size_t)k1 * p.n2;
@@ -757,5 +764,118 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Arbitrary (non power-of-two) lengths: the reference accepts any N (numpy.fft).  The N-point transforms of
+// devices.py:1178-1180 are evaluated as chirp-z (Bluestein) convolutions of length M = 2^ceil(log2(2N-1)) with the
+// power-of-two kernels above:   DFT_N(x)[k] = w[k] * sum_n (x[n] w[n]) conj(w)[k-n],   w[n] = exp(-j pi n^2 / N).
+// Per split step:  k_bs_open  (first Kerr half step, * w, zero padding)  ->  FFT_M, * FFT_M(conj w), IFFT_M
+//   ->  k_bs_mid  (* exp(j imag(D~) h); the post-chirp of the forward and the pre-chirp of the inverse transform cancel)
+//   ->  FFT_M, * FFT_M(w), IFFT_M  ->  k_bs_close (* conj(w)/N, attenuation, second Kerr half step, max |A|^2)
+//   ->  k_ctrl_steps (controller of every waveform).  About ten passes over 2-4 N samples: a completeness path.
+// ---------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void k_bs_chirp(typename cx_of<R>::type* wtab, int n) {      // w[i] = exp(-j pi i^2 / n), i^2 reduced mod 2n exactly
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long r = ((long long)i * i) % (2ll * n);
+    double s, c;
+    sincospi((double)r / (double)n, &s, &c);
+    wtab[i] = mk<R>((R)c, (R)(-s));
+}
+template <typename R>
+__global__ void k_bs_kernel_row(typename cx_of<R>::type* row, const typename cx_of<R>::type* wtab, int n, int m, int conj_w) {
+    // b[i] = conj(w)[i] (or w[i]) at circular index i and m - i, zero elsewhere
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    typename cx_of<R>::type v = mk<R>((R)0, (R)0);
+    int d = -1;
+    if (i < n) d = i; else if (m - i < n) d = m - i;
+    if (d >= 0) { v = wtab[d]; if (conj_w) v.y = -v.y; }
+    row[i] = v;
+}
+template <typename R>
+__global__ void k_bs_open(Params<R> p, typename cx_of<R>::type* wb, const typename cx_of<R>::type* __restrict__ wtab, int m,
+                          const typename cx_of<R>::type* __restrict__ sct) {
+    typedef typename cx_of<R>::type C;
+    const int row = blockIdx.y, b = row / p.n_pol;
+    const Ctrl ctl = p.ctrl[b];
+    if (ctl.done) return;
+    const R hh = (R)ctl.h / (R)2;
+    const C* __restrict__ f = p.field + (size_t)row * p.n;
+    R* __restrict__ st = p.stash + (size_t)row * p.n;
+    C* __restrict__ w = wb + (size_t)row * m;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        C a = mk<R>((R)0, (R)0);
+        if (i < p.n) {
+            a = f[i];
+            if (p.has_nl) {
+                const R pw = a.x * a.x + a.y * a.y;
+                const R ph = mul_rn(hh, mul_rn(p.gamma, pw));
+                st[i] = ph;
+                R s, c; sincos_r(ph, sct, &s, &c);
+                a = cmul(a, mk<R>(c, s));
+            }
+            a = cmul(a, wtab[i]);
+        }
+        w[i] = a;
+    }
+}
+template <typename R>
+__global__ void k_bs_mid(Params<R> p, typename cx_of<R>::type* wb, int m, const typename cx_of<R>::type* __restrict__ sct) {
+    typedef typename cx_of<R>::type C;
+    const int row = blockIdx.y, b = row / p.n_pol;
+    const Ctrl ctl = p.ctrl[b];
+    if (ctl.done) return;
+    const R h = (R)ctl.h;
+    C* __restrict__ w = wb + (size_t)row * m;
+    const int pos = (p.n + 1) >> 1;                             // numpy.fft.fftfreq: bins 0 .. ceil(n/2)-1 are non-negative
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        C a = mk<R>((R)0, (R)0);
+        if (i < p.n) {
+            const int k = (i < pos) ? i : i - p.n;
+            const R wk = (R)((double)k * p.wscale);
+            const R dim = add_rn(mul_rn(p.c2, mul_rn(wk, wk)), mul_rn(p.c3, cube_r(wk)));
+            R s, c; sincos_r(mul_rn(dim, h), sct, &s, &c);
+            a = cmul(w[i], mk<R>(c, s));
+        }
+        w[i] = a;
+    }
+}
+template <typename R>
+__global__ void k_bs_close(Params<R> p, const typename cx_of<R>::type* wb, const typename cx_of<R>::type* __restrict__ wtab, int m,
+                           const typename cx_of<R>::type* __restrict__ sct) {
+    typedef typename cx_of<R>::type C;
+    __shared__ unsigned long long red[32];
+    const int row = blockIdx.y, b = row / p.n_pol;
+    const Ctrl ctl = p.ctrl[b];
+    if (ctl.done) return;
+    const R sc = p.inv_n * exp_r(mul_rn(p.att_half, (R)ctl.h));
+    C* __restrict__ f = p.field + (size_t)row * p.n;
+    const R* __restrict__ st = p.stash + (size_t)row * p.n;
+    const C* __restrict__ w = wb + (size_t)row * m;
+    R pm = 0;
+    bool nan = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+        C a = cmulc(w[i], wtab[i]);
+        a.x *= sc; a.y *= sc;
+        if (p.has_nl) {
+            R s, c; sincos_r(st[i], sct, &s, &c);
+            a = cmul(a, mk<R>(c, s));
+        }
+        const R pw = a.x * a.x + a.y * a.y;
+        nan |= (pw != pw);
+        pm = pw > pm ? pw : pm;
+        f[i] = a;
+    }
+    if (nan) pm = pw_nan<R>();
+    pm = block_max_bits<R>(pm, red);
+    if (threadIdx.x == 0) atomicMax(&p.ctrl[b].pmax, ord_bits(pm));
+}
+template <typename R>
+__global__ void k_ctrl_steps(Params<R> p) {                    // deferred controller step of every unfinished waveform
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < p.batch && !p.ctrl[b].done) controller_update<R>(p, b, from_bits<R>(p.ctrl[b].pmax));
+}
 
 }  // namespace ssfm

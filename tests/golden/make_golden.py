@@ -55,7 +55,24 @@ def fiber_case(name, sig, fn=FIBER, **kw):
          is_dbp=np.bool_(fn is DBP))
 
 
+def nonpow2():
+    """Lengths that are not powers of two (the reference accepts any N; added later, own RNG stream)."""
+    rng = np.random.default_rng(20261018)
+    s = tx(10, 127, 7, 10.0)   # N = 1270
+    fiber_case("fiber_n1270_adaptive", s, length=20.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0)
+    s = tx(12, 250, 9, 8.0)    # N = 3000
+    fiber_case("fiber_n3000_fixed", s, length=12.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, h=0.5)
+    s = tx(8, 125, 7, 10.0)    # N = 1000, two polarisations + noise, odd-symmetric check of the bin map via DBP
+    sig2 = np.stack([s.signal, 0.5j * s.signal[::-1]])
+    noi2 = 1e-3 * (rng.standard_normal(sig2.shape) + 1j * rng.standard_normal(sig2.shape))
+    fiber_case("dbp_2pol_n1000", optical_signal(sig2, noi2), fn=DBP, length=8.0, alpha=0.2, beta_2=-20.0, gamma=1.5)
+    s = tx(9, 111, 7, 10.0)    # N = 999 (odd)
+    fiber_case("fiber_n999_odd", s, length=10.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.02)
+
+
 def main():
+    if "nonpow2" in sys.argv:
+        return nonpow2()
     rng = np.random.default_rng(20261017)
 
     # --- FIBER / DBP, shipped float32 path ------------------------------------------------

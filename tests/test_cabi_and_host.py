@@ -40,8 +40,9 @@ def test_struct_layout_matches_header():
 def test_argument_validation_needs_no_gpu(lib):
     from opticomlib_b200 import _lib
     h = ctypes.c_void_p()
-    assert lib.ssfm_plan_create(ctypes.byref(h), 1000, 1, 1, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_UNSUPPORTED
-    assert b"power of two" in lib.ssfm_last_error()
+    for bad_n in (1, 3 << 20, 1 << 23):                          # too short; not a power of two above 2^21; above 2^22
+        assert lib.ssfm_plan_create(ctypes.byref(h), bad_n, 1, 1, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_UNSUPPORTED
+        assert b"power of two" in lib.ssfm_last_error()
     assert lib.ssfm_plan_create(ctypes.byref(h), 4096, 3, 1, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_INVALID
     assert b"n_pol" in lib.ssfm_last_error()
     assert lib.ssfm_plan_create(ctypes.byref(h), 4096, 1, 0, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_INVALID

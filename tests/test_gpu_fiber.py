@@ -21,6 +21,8 @@ F32_CASES = [
     "fiber_adaptive_4096", "fiber_beta3_4096", "dbp_adaptive_4096", "fiber_gamma0_4096",
     "fiber_nodisp_4096", "fiber_alpha_only_4096", "fiber_fixed_h03_2048", "fiber_fixed_h01_1024",
     "fiber_2pol_noise_4096", "dbp_2pol_fixed_4096",
+    # lengths that are not powers of two (the reference accepts any N): 1270, 3000, 1000 (two polarisations), 999 (odd)
+    "fiber_n1270_adaptive", "fiber_n3000_fixed", "dbp_2pol_n1000", "fiber_n999_odd",
 ]
 
 
@@ -58,7 +60,7 @@ def test_fp32_matches_reference_output(ob, name):
 
 
 @pytest.mark.parametrize("name", ["fiber_fixed_h03_2048", "fiber_fixed_h01_1024", "dbp_2pol_fixed_4096",
-                                  "fiber_adaptive_4096", "fiber_beta3_4096"])
+                                  "fiber_adaptive_4096", "fiber_beta3_4096", "fiber_n3000_fixed", "fiber_n999_odd"])
 def test_fp32_step_positions(ob, name):
     g = golden(name)
     kw = fiber_kwargs(g)
@@ -176,6 +178,27 @@ def test_fused_and_unfused_schedules_agree(ob, precision, tol):
             assert np.array_equal(ia.h_log, ib.h_log) and np.array_equal(ia.z, ib.z)
 
 
+@pytest.mark.parametrize("n", [2, 3, 100, 255, 257, 6561, 10000, 65537])
+def test_arbitrary_lengths_against_the_oracle(ob, n):
+    """Any N, as numpy.fft accepts it: chirp-z transforms on the power-of-two kernels (fp64 and fp32), batch of 3 rows with
+    their own step sequences."""
+    rng = np.random.default_rng(n)
+    t = np.arange(n) / n
+    base = np.sqrt(2e-3) * (1 + 0.5 * np.cos(2 * np.pi * 3 * t)) * np.exp(2j * np.pi * 2 * t) + 1e-3 * (
+        rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    rows = np.stack([base, 0.6 * base[::-1], 1.5 * np.roll(base, n // 3)])
+    dt = 1 / 160e9
+    for kw in (dict(length=12.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.02),
+               dict(length=2.2, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, h=0.5)):
+        for precision, real, tol in (("fp64", np.float64, TOL64), ("fp32", np.float32, TOL32)):
+            out, info = ob.fiber_batch(rows, dt, precision=precision, want_log=True, **kw)
+            for i in range(3):
+                ref = oracle_fiber(rows[i], dt, real=real, **kw)
+                assert int(info.steps[i]) == ref["steps"], (precision, i)
+                assert rel_l2(out[i], ref["out"]) <= tol, (precision, i)
+                np.testing.assert_allclose(info.h_log[i, :ref["steps"]], ref["h"], rtol=1e-3 if precision == "fp32" else 1e-10)
+
+
 def test_two_polarisations_share_one_controller(ob):
     g = golden("fiber_2pol_noise_4096")
     kw = fiber_kwargs(g)
@@ -238,7 +261,9 @@ def test_errors_match_reference(ob):
     with pytest.raises(TypeError):
         ob.FIBER(ob.electrical_signal(np.ones(1024)), length=1.0)
     with pytest.raises(ValueError):                                    # unsupported length is loud, not a fallback
-        ob.FIBER(ob.optical_signal(np.ones(1000, complex)), length=1.0)
+        ob.FIBER(ob.optical_signal(np.ones(1, complex)), length=1.0)
+    with pytest.raises(ValueError):
+        ob.fiber_batch(np.ones((1, 3 << 20), complex), 1e-12, length=1.0)
 
 
 def test_c_abi_host_entry_point(ob):
@@ -259,6 +284,6 @@ def test_c_abi_host_entry_point(ob):
     assert steps[0] == ref["steps"] and rel_l2(y, ref["out"]) <= TOL64
     # error path: no exception across the ABI, a code and a message instead
     bad = ctypes.c_void_p()
-    assert lib.ssfm_plan_create(ctypes.byref(bad), 1000, 1, 1, _lib.SSFM_C128, 0) == _lib.SSFM_ERR_UNSUPPORTED
+    assert lib.ssfm_plan_create(ctypes.byref(bad), 3 << 20, 1, 1, _lib.SSFM_C128, 0) == _lib.SSFM_ERR_UNSUPPORTED
     assert b"power of two" in lib.ssfm_last_error()
     assert lib.ssfm_plan_destroy(plan) == 0

@@ -18,6 +18,8 @@ F32_CASES = [
     "fiber_adaptive_4096", "fiber_beta3_4096", "dbp_adaptive_4096", "fiber_gamma0_4096",
     "fiber_nodisp_4096", "fiber_alpha_only_4096", "fiber_fixed_h03_2048", "fiber_fixed_h01_1024",
     "fiber_2pol_noise_4096", "dbp_2pol_fixed_4096",
+    # lengths that are not powers of two (the reference accepts any N): 1270, 3000, 1000 (two polarisations), 999 (odd)
+    "fiber_n1270_adaptive", "fiber_n3000_fixed", "dbp_2pol_n1000", "fiber_n999_odd",
 ]
 
 
