@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--log2n", type=int, default=26, help="cfg5: log2 of the waveform length")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="cfg5 on several GPUs: kernels store into peer memory over NVLink (fused) or NCCL all-to-all")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--rows", type=int, default=0, help="override the number of waveforms (whole job)")
     ap.add_argument("--chunk", type=int, default=-1, help="waveforms propagated together (-1 = auto)")
@@ -421,7 +423,7 @@ def run_cfg5(a, torch, dist, dev, rank, world, local):
     tdtype = torch.complex128 if a.precision == "fp64" else torch.complex64
     csize = 16 if a.precision == "fp64" else 8
     group = dist.group.WORLD if world > 1 else None
-    plan = lw.get_long_plan(n, tdtype, dev, group)
+    plan = lw.get_long_plan(n, tdtype, dev, group, None, a.exchange == "fused")
     # synthetic PRBS23 NRZ field, built directly in this rank's layout [N0][N_l/G] (the reference DAC FIR would be 2^26 taps)
     bits = torch.from_numpy(wl.prbs(c["order"], n // c["sps"]).astype(np.float64)).to(dev)
     na = torch.arange(plan.n_outer, device=dev, dtype=torch.int64)[:, None]
@@ -499,8 +501,9 @@ def run_cfg5(a, torch, dist, dev, rank, world, local):
         "dtype": "f64" if a.precision == "fp64" else "f32", "data": "synthetic",
         "config": {"workload": DESCR["cfg5"], "samples": n, "n_outer": plan.n_outer, "n_inner": plan.n_inner,
                    "split_steps_per_bench_step": int(info.steps[0]),
-                   "parallelism": "columns of the %d x %d sample matrix over %d rank(s); 2 all-to-all per split step" %
-                                  (plan.n_outer, plan.n_inner, world),
+                   "parallelism": "columns of the %d x %d sample matrix over %d rank(s); 2 exchanges per split step (%s)" %
+                                  (plan.n_outer, plan.n_inner, world, "none: one rank" if world == 1 else
+                                   ("fused: kernels store into peer memory over NVLink" if plan.fused else "NCCL all-to-all + re-layout copy")),
                    "l2": "inputs larger than L2 (%.0f MiB per GPU)" % (x0.numel() * csize / 2 ** 20), **fiber},
         "e2e": {"value": e2e_units / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(x0.numel() * csize) * world,
                 "d2h_bytes_per_step": int(x0.numel() * csize) * world,

@@ -143,6 +143,17 @@ SSFM_API int ssfm_long_pmax(ssfm_plan_t plan, double* value_host, int32_t set, v
 SSFM_API int ssfm_long_ctrl(ssfm_plan_t plan, int32_t init, void* stream);
 SSFM_API int ssfm_long_outer(ssfm_plan_t plan, void* field_local_dev, int32_t stage, void* stream);
 SSFM_API int ssfm_long_inner(ssfm_plan_t plan, void* rows_local_dev, void* stream);
+/* Exchange fused into the kernels (several GPUs of one node, one process each).  Every rank exports the CUDA IPC handle
+ * (64 bytes) of its exchange buffer, the caller gathers the handles of all ranks (rank order) and every rank imports them.
+ * From then on the stage kernels store each result element straight into the buffer of the rank that owns it in the next
+ * stage's layout -- peer memory over NVLink, no collective and no re-layout copy -- and the caller replaces each
+ * exchange by ssfm_long_xbar (a flag barrier between the GPUs, on the stream).  The time-domain field lives in the
+ * library's buffer: ssfm_long_p2p_copy(to_internal = 1) before ssfm_long_begin, (0) after the last stage; the
+ * field / rows pointers of ssfm_long_begin / _outer / _inner are then ignored. */
+SSFM_API int ssfm_long_p2p_export(ssfm_plan_t plan, void* handle64_host);
+SSFM_API int ssfm_long_p2p_import(ssfm_plan_t plan, const void* handles_host);
+SSFM_API int ssfm_long_p2p_copy(ssfm_plan_t plan, void* field_local_dev, int32_t to_internal, void* stream);
+SSFM_API int ssfm_long_xbar(ssfm_plan_t plan, void* stream);
 
 /* Zero-phase cascaded-biquad filtering (scipy.signal.sosfiltfilt as called at devices.py:820-823 and
  * 1365-1368): x_dev[n_rows][n_samples] complex128 -> y_dev (may alias x_dev).

@@ -53,6 +53,10 @@ PROTOTYPES = {
     "ssfm_long_ctrl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "ssfm_long_outer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "ssfm_long_inner": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ssfm_long_p2p_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "ssfm_long_p2p_import": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "ssfm_long_p2p_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
+    "ssfm_long_xbar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "ssfm_filtfilt_sos": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
 }

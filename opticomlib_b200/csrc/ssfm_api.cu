@@ -159,6 +159,13 @@ struct ssfm_plan_s {
     int long_ranks = 1, long_rank = 0;
     ssfm_plan_t inner = nullptr; // N_l-point transforms of the N0 / ranks rows this rank owns after the exchange
                                  // (chirp plans: the M-point transforms of the padded rows)
+    // long waveforms over several GPUs with the exchange fused into the kernels (ssfm_long_p2p_*)
+    void* xbuf = nullptr;        // [time-layout field][rows-layout buffer][flags], exported to the peers through CUDA IPC
+    size_t xlocal = 0;           // bytes of one layout
+    void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // xbuf of every rank, mapped here
+    unsigned int** d_peer_flags = nullptr;
+    int p2p = 0;
+    unsigned int epoch = 0;
     // arbitrary lengths (chirp-z / Bluestein): n is not a power of two; rows are padded to chirp_m = 2^ceil(log2(2n-1))
     long long chirp_m = 0;
     void *wb = nullptr, *wtab = nullptr, *xf_fwd = nullptr, *xf_inv = nullptr;   // padded work rows, chirp, chirp spectra
@@ -782,6 +789,9 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     if (pl->ev[1]) cudaEventDestroy(pl->ev[1]);
     cudaFree(pl->wf_sync);
     cudaFree(pl->wb); cudaFree(pl->wtab); cudaFree(pl->xf_fwd); cudaFree(pl->xf_inv);
+    for (int r = 0; r < 8; ++r)
+        if (pl->peer_base[r] && pl->peer_base[r] != pl->xbuf) cudaIpcCloseMemHandle(pl->peer_base[r]);
+    cudaFree(pl->xbuf); cudaFree(pl->d_peer_flags);
     if (pl->wf_side) cudaStreamDestroy(pl->wf_side);
     if (pl->wf_ev_side) cudaEventDestroy(pl->wf_ev_side);
     if (pl->inner) ssfm_plan_destroy(pl->inner);
@@ -916,6 +926,14 @@ Params<R> long_outer_params(ssfm_plan_t pl, void* field) {
     p.n_glob = (int)pl->long_n;
     p.inv_n = (R)1 / (R)pl->long_n;
     p.defer_ctrl = 1;
+    if (pl->p2p) {                                              // time layout lives in xbuf; results go to the owners' rows buffers
+        p.field = (C*)pl->xbuf;
+        for (int r = 0; r < pl->long_ranks; ++r) p.peer[r] = (C*)((char*)pl->peer_base[r] + pl->xlocal);
+        p.peer_mode = 1;
+        p.peer_shift = ilog2(pl->n1 / pl->long_ranks);
+        p.peer_pitch = (int)(pl->long_n / pl->n1);              // N_l
+        p.peer_base = pl->long_rank * pl->n2;
+    }
     return p;
 }
 
@@ -934,6 +952,7 @@ Params<R> long_inner_params(ssfm_plan_t pl, void* rows) {
     p.wscale = ((1.0 / ((double)pl->long_n * pl->last.dt_s)) * 2.0) * 3.141592653589793 * 1e-12;
     p.inv_n = (R)1; p.att_half = (R)0;                          // 1/N and the attenuation are applied once, by the outer stage
     p.has_nl = 0;
+    if (pl->p2p) p.field = (C*)((char*)pl->xbuf + pl->xlocal);  // my rows buffer (filled by the peers' outer kernels)
     return p;
 }
 
@@ -969,15 +988,23 @@ template <typename R>
 int long_outer_t(ssfm_plan_t pl, void* field, int stage, cudaStream_t st) {
     Params<R> p = long_outer_params<R>(pl, field);
     if (stage == 0) return enqueue_col<R>(p, COL_FWD, st);
-    if (stage == 2) return enqueue_col<R>(p, COL_INV, st);
+    if (stage == 2) { p.peer_mode = 0; return enqueue_col<R>(p, COL_INV, st); }   // time domain out: local stores
     return enqueue_col<R>(p, COL_MID, st, SYNC_FIXED);         // fixed step only: no max, the device controller advances alone
 }
 
 template <typename R>
 int long_inner_t(ssfm_plan_t pl, void* rows, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
     Params<R> p = long_inner_params<R>(pl, rows);
     int rc = enqueue_col<R>(p, COL_FWD, st);
     if (!rc) rc = enqueue_row<R>(p, st);
+    if (pl->p2p) {                                              // last pass stores into the owners' time-layout fields
+        for (int r = 0; r < pl->long_ranks; ++r) p.peer[r] = (C*)pl->peer_base[r];
+        p.peer_mode = 2;
+        p.peer_shift = ilog2(pl->n2);                           // columns per rank
+        p.peer_pitch = pl->n2;
+        p.peer_base = pl->long_rank * (int)pl->inner->batch;
+    }
     if (!rc) rc = enqueue_col<R>(p, COL_INV, st);
     return rc;
 }
@@ -1049,6 +1076,62 @@ int ssfm_long_plan_create(ssfm_plan_t* out, int64_t n_global, int32_t n_outer, i
     cudaError_t es = cudaDeviceSynchronize();
     if (es != cudaSuccess) { ssfm_plan_destroy(pl); return fail(SSFM_ERR_CUDA, std::string("table build: ") + cudaGetErrorString(es)); }
     *out = pl;
+    return SSFM_OK;
+}
+
+int ssfm_long_p2p_export(ssfm_plan_t pl, void* handle64) {
+    if (!pl || !pl->long_n || !handle64) return fail(SSFM_ERR_INVALID, "null argument or not a long-waveform plan");
+    CU_TRY(cudaSetDevice(pl->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!pl->xbuf) {
+        pl->xlocal = (size_t)pl->n * (pl->dtype == SSFM_C64 ? 8 : 16);
+        if ((long long)(pl->long_n / pl->n1) / pl->long_ranks < pl->inner->n2)
+            return fail(SSFM_ERR_UNSUPPORTED, "fused exchange: more ranks than rows of the inner transform matrix");
+        CU_TRY(cudaMalloc(&pl->xbuf, 2 * pl->xlocal + 256));
+        CU_TRY(cudaMemset((char*)pl->xbuf + 2 * pl->xlocal, 0, 256));
+    }
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, pl->xbuf));
+    std::memcpy(handle64, &h, 64);
+    return SSFM_OK;
+}
+
+int ssfm_long_p2p_import(ssfm_plan_t pl, const void* handles) {
+    if (!pl || !pl->long_n || !handles || !pl->xbuf) return fail(SSFM_ERR_INVALID, "null argument, or ssfm_long_p2p_export not called");
+    if (pl->long_ranks > 8) return fail(SSFM_ERR_UNSUPPORTED, "fused exchange supports up to 8 ranks");
+    CU_TRY(cudaSetDevice(pl->device));
+    unsigned int* flags[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int r = 0; r < pl->long_ranks; ++r) {
+        if (r == pl->long_rank) pl->peer_base[r] = pl->xbuf;
+        else if (!pl->peer_base[r]) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const char*)handles + 64 * r, 64);
+            CU_TRY(cudaIpcOpenMemHandle(&pl->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        flags[r] = (unsigned int*)((char*)pl->peer_base[r] + 2 * pl->xlocal);
+    }
+    if (!pl->d_peer_flags) CU_TRY(cudaMalloc((void**)&pl->d_peer_flags, sizeof(flags)));
+    CU_TRY(cudaMemcpy(pl->d_peer_flags, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    pl->p2p = 1;
+    return SSFM_OK;
+}
+
+int ssfm_long_p2p_copy(ssfm_plan_t pl, void* field_user, int32_t to_internal, void* stream) {
+    if (!pl || !pl->p2p || !field_user) return fail(SSFM_ERR_INVALID, "null argument or fused exchange not set up");
+    CU_TRY(cudaSetDevice(pl->device));
+    if (to_internal) CU_TRY(cudaMemcpyAsync(pl->xbuf, field_user, pl->xlocal, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    else CU_TRY(cudaMemcpyAsync(field_user, pl->xbuf, pl->xlocal, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SSFM_OK;
+}
+
+int ssfm_long_xbar(ssfm_plan_t pl, void* stream) {
+    if (!pl || !pl->p2p) return fail(SSFM_ERR_INVALID, "null plan or fused exchange not set up");
+    CU_TRY(cudaSetDevice(pl->device));
+    ++pl->epoch;
+    k_xbar<<<1, 32, 0, (cudaStream_t)stream>>>(pl->d_peer_flags, (unsigned int*)((char*)pl->xbuf + 2 * pl->xlocal), pl->long_rank,
+                                               pl->long_ranks, pl->epoch);
+    ++ssfm_launches;
+    CU_TRY(cudaGetLastError());
     return SSFM_OK;
 }
 

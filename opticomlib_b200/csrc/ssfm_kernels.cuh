@@ -63,6 +63,14 @@ struct Params {
     // the controller state of waveform 0 (h, done), the row kernel maps its bins to global bins
     // k = bin_off + row + bin_mul (k1 + N1 k2) with the fftfreq wrap at n_glob, and k_col_inv leaves the controller alone.
     int n2_off, inner, bin_mul, bin_off, n_glob;
+    // long waveforms spread over several GPUs, exchange fused into the kernels: instead of storing a stage's result locally
+    // (and moving it with a collective afterwards) the column kernels store every element straight into the buffer of the
+    // rank that owns it in the NEXT stage's layout -- peer memory over NVLink (CUDA IPC), 16-byte elements in runs of T
+    // columns.  peer_mode 1 (outer stage -> rows layout): element (ka, nb) goes to rank ka >> peer_shift at
+    // [ka & mask][peer_base + nb] with row pitch peer_pitch = N_l; peer_mode 2 (inner k_col_inv -> time layout): element nb of
+    // my row goes to rank nb >> peer_shift at [peer_base + row][nb & mask] with pitch peer_pitch = columns per rank.
+    typename cx_of<R>::type* peer[8];
+    int peer_mode, peer_shift, peer_pitch, peer_base;
     int fwd_only;        // 1: the row kernel stops after the forward transforms and stores the spectrum (transposed order):
                          // used once per plan to build the chirp spectra of the arbitrary-length transform
     int defer_ctrl;      // 1: k_col_inv only accumulates max|A|^2 in ctrl.pmax; the controller runs later (k_ctrl_step), after
@@ -221,6 +229,21 @@ __global__ void k_ctrl_step(Params<R> p) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && !p.ctrl[0].done) controller_update<R>(p, 0, from_bits<R>(p.ctrl[0].pmax));
 }
 
+// Barrier between the GPUs that share one long waveform (fused exchange): every rank posts the epoch into its slot of
+// every peer's flag array (peer memory, system-scope release) and waits until all peers have posted theirs.  The
+// stores of the preceding kernel on this stream -- including its stores into peer memory -- are ordered before the post.
+static __global__ void k_xbar(unsigned int* const* peer_flags, unsigned int* my_flags, int me, int ranks, unsigned int epoch) {
+    const int r = threadIdx.x;
+    if (r < ranks) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[r] + me), "r"(epoch) : "memory");
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flags + r) : "memory");
+        } while ((int)(seen - epoch) < 0);
+    }
+}
+
 // Ask for SSFM_THREADS_PER_SM resident threads per SM (512 -> at most 128 registers per thread):
 // several small CTAs per SM so that one CTA's global loads overlap another's transform.
 #ifndef SSFM_THREADS_PER_SM
@@ -273,6 +296,18 @@ __device__ __forceinline__ void apply_fourstep(const Params<R>& p, typename cx_o
             v[q] = CONJ ? cmulc(v[q], w) : cmul(v[q], w);
         }
     }
+}
+
+// destination of element (r, col) of the local matrix of matrix-row pitch p.n2 (see Params::peer)
+template <typename R>
+__device__ __forceinline__ typename cx_of<R>::type* exchange_dst(const Params<R>& p, typename cx_of<R>::type* rowp, int r, int col, int bp) {
+    if (p.peer_mode == 1)
+        return p.peer[r >> p.peer_shift] + (size_t)(r & ((1 << p.peer_shift) - 1)) * p.peer_pitch + p.peer_base + col;
+    if (p.peer_mode == 2) {
+        const int nb = r * p.n2 + col;
+        return p.peer[nb >> p.peer_shift] + (size_t)(p.peer_base + bp) * p.peer_pitch + (nb & ((1 << p.peer_shift) - 1));
+    }
+    return rowp + (size_t)r * p.n2 + col;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -360,7 +395,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
     fft_passes<R, M, -1, ColExchange<T>, E>::run(v, sm + c, tw, t);
     apply_fourstep<false, R, E, M>(p, v, n2 + p.n2_off, t);
 #pragma unroll
-    for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
+    for (int q = 0; q < E; ++q) *exchange_dst<R>(p, rowp, t + q * (M / E), n2, row) = v[q];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,7 +510,8 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
         const R pw = a.x * a.x + a.y * a.y;
         nan |= (pw != pw);
         pm = pw > pm ? pw : pm;
-        rowp[off] = a;
+        if (p.peer_mode) *exchange_dst<R>(p, rowp, t + q * (M / E), n2, row) = a;
+        else rowp[off] = a;
     }
     if (nan) pm = pw_nan<R>();
     if (p.inner) return;                                        // inner transform of a long waveform: no controller
@@ -755,7 +791,7 @@ __global__ void __launch_bounds__(T * (M / points_per_thread<R>::value), min_cta
         fft_passes<R, M, -1, ColExchange<T>, E>::run(v, sm + c, tw, t);
         apply_fourstep<false, R, E, M>(p, v, n2 + p.n2_off, t);
 #pragma unroll
-        for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M / E)) * p.n2 + n2] = v[q];
+        for (int q = 0; q < E; ++q) *exchange_dst<R>(p, rowp, t + q * (M / E), n2, row) = v[q];
     }
     if (SYNC == SYNC_FIXED && tile == 0 && (row % p.n_pol) == 0 && threadIdx.x == 0) {
         // every tile of the waveform has read the old state by now (or will within microseconds)

@@ -102,6 +102,21 @@ class CudaStages:
     def inner(self, rows):
         _lib.check(self.lib.ssfm_long_inner(self.handle, rows.data_ptr(), self._stream()))
 
+    # ---- exchange fused into the kernels (peer memory over NVLink, CUDA IPC) --------------------------
+    def p2p_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.ssfm_long_p2p_export(self.handle, buf))
+        return buf.raw
+
+    def p2p_import(self, handles: bytes):
+        _lib.check(self.lib.ssfm_long_p2p_import(self.handle, ctypes.c_char_p(handles)))
+
+    def p2p_copy(self, field, to_internal):
+        _lib.check(self.lib.ssfm_long_p2p_copy(self.handle, field.data_ptr(), 1 if to_internal else 0, self._stream()))
+
+    def xbar(self):
+        _lib.check(self.lib.ssfm_long_xbar(self.handle, self._stream()))
+
     def sync(self):
         _torch().cuda.current_stream(self.device).synchronize()
 
@@ -125,7 +140,7 @@ class LongPlan:
     """Sequencer of one rank: stages (``CudaStages``; the CPU tests inject a NumPy model of the same stages to check
     the sequencing and the exchange under gloo) + the two layout exchanges + the scalar max all-reduce."""
 
-    def __init__(self, n_global, complex_dtype, device=None, group=None, n_outer=None, stages=None):
+    def __init__(self, n_global, complex_dtype, device=None, group=None, n_outer=None, stages=None, fused_exchange=True):
         torch = _torch()
         self.group = group
         self.ranks, self.rank = 1, 0
@@ -145,6 +160,27 @@ class LongPlan:
             self.device = torch.device("cpu")
         self.stages = stages
         self._buf = None                                   # exchange buffers (only with more than one rank)
+        # Several GPUs: let the kernels store straight into the peers' buffers (CUDA IPC over NVLink) instead of an NCCL
+        # all-to-all plus a re-layout copy.  Needs all ranks on one node; falls back to the collective otherwise.
+        self.fused = False
+        if self.ranks > 1 and fused_exchange and isinstance(stages, CudaStages) and self.ranks <= 8:
+            import torch.distributed as dist
+            try:
+                mine = stages.p2p_export()
+                ok = 1
+            except Exception:
+                mine, ok = b"\0" * 64, 0
+            gathered = [None] * self.ranks
+            dist.all_gather_object(gathered, (ok, mine), group=group)
+            if all(g[0] for g in gathered):
+                try:
+                    stages.p2p_import(b"".join(g[1] for g in gathered))
+                    ok = 1
+                except Exception:
+                    ok = 0
+                flags = [None] * self.ranks
+                dist.all_gather_object(flags, ok, group=group)
+                self.fused = all(flags)
 
     def close(self):
         if getattr(self, "stages", None) is not None:
@@ -168,6 +204,9 @@ class LongPlan:
         """[N0][N_l/G] (time layout, outer transform done) -> [N0/G][N_l] (this rank's rows)."""
         if self.ranks == 1:
             return field
+        if self.fused:                                     # the outer kernel already stored into the owners' rows buffers
+            self.stages.xbar()
+            return field
         import torch.distributed as dist
         torch = _torch()
         recv, rows = self._buffers(field)
@@ -178,6 +217,9 @@ class LongPlan:
 
     def _to_columns(self, rows, field):
         if self.ranks == 1:
+            return
+        if self.fused:
+            self.stages.xbar()
             return
         import torch.distributed as dist
         torch = _torch()
@@ -214,12 +256,16 @@ class LongPlan:
 
         ctx = torch.cuda.device(self.device) if on_cuda else _Null()
         with ctx:
+            if self.fused:
+                sg.p2p_copy(field, True)                        # the time-domain field lives in the library's IPC buffer
             sg.begin(field, prm)
             if not fixed and not single:
                 combine_max()
             sg.ctrl(True)
             if sg.state().done[0]:
                 return sg.state(want_log)
+            if self.fused:
+                sg.xbar()                                       # nobody stores into a peer before every peer has loaded its field
             sg.outer(field, 0)
             n_fixed = fixed_step_count(length, h, R) if fixed else 0
             done_steps = 0
@@ -239,6 +285,8 @@ class LongPlan:
                     if sg.state().done[0]:
                         break
                     sg.outer(field, 0)
+            if self.fused:
+                sg.p2p_copy(field, False)
             sg.sync()
         info = sg.state(want_log)
         if not info.done[0]:
@@ -260,16 +308,16 @@ class _Null:
 _PLANS: dict = {}
 
 
-def get_long_plan(n_global, complex_dtype, device=None, group=None, n_outer=None) -> LongPlan:
+def get_long_plan(n_global, complex_dtype, device=None, group=None, n_outer=None, fused_exchange=True) -> LongPlan:
     torch = _torch()
     dev = engine.require_cuda(device)
     cd = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
-    key = (int(n_global), cd, dev.index, id(group) if group is not None else None, n_outer)
+    key = (int(n_global), cd, dev.index, id(group) if group is not None else None, n_outer, bool(fused_exchange))
     pl = _PLANS.get(key)
     if pl is None:
         if len(_PLANS) >= 2:                                # long plans own O(N) device memory
             _PLANS.pop(next(iter(_PLANS))).close()
-        pl = _PLANS[key] = LongPlan(n_global, cd, dev, group, n_outer)
+        pl = _PLANS[key] = LongPlan(n_global, cd, dev, group, n_outer, fused_exchange=fused_exchange)
     return pl
 
 
@@ -279,12 +327,14 @@ def clear_plans():
 
 
 def fiber_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
-               precision="fp32", device=None, group=None, n_outer=None, want_log=False, gather=True):
+               precision="fp32", device=None, group=None, n_outer=None, want_log=False, gather=True, fused_exchange=True):
     """Propagate ONE waveform ``field[N]`` (NumPy array or tensor, the same on every rank of ``group``).
 
     With ``group=None`` the whole waveform lives on this process's GPU (any power-of-two N in [2^12, 2^30]); with a
     process group its columns are spread over the ranks and the result is gathered back on every rank
-    (``gather=False`` returns this rank's [N0, N_l/G] share instead).  Returns ``(out, StepInfo)``.
+    (``gather=False`` returns this rank's [N0, N_l/G] share instead).  ``fused_exchange`` (default): the kernels store
+    straight into the peers' buffers over NVLink (CUDA IPC); ``False``: NCCL all-to-all + re-layout copy.
+    Returns ``(out, StepInfo)``.
     """
     torch = _torch()
     dev = engine.require_cuda(device)
@@ -293,7 +343,7 @@ def fiber_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, 
     x = torch.from_numpy(np.ascontiguousarray(field)) if as_numpy else field
     if x.ndim != 1:
         raise ValueError("fiber_long takes one single-polarisation waveform of shape [N]")
-    plan = get_long_plan(x.shape[0], tdtype, dev, group, n_outer)
+    plan = get_long_plan(x.shape[0], tdtype, dev, group, n_outer, fused_exchange)
     mine = local_columns(x, plan.n_outer, plan.ranks, plan.rank).to(dev).to(tdtype).contiguous()
     if mine.data_ptr() == x.data_ptr():
         mine = mine.clone()

@@ -141,8 +141,11 @@ def _nccl_worker(rank, world, port, q):
                        dict(length=0.8, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.005)):
                 with np.errstate(all="ignore"):
                     ref = oracle_fiber(x, DT, real=REAL[precision], **kw)
-                out, info = lw.fiber_long(x, DT, precision=precision, group=dist.group.WORLD, **kw)
-                ok &= int(info.steps[0]) == ref["steps"] and rel_l2(out, ref["out"]) <= TOL[precision]
+                for fused in (True, False):                       # kernels store into peer memory / NCCL all-to-all
+                    out, info = lw.fiber_long(x, DT, precision=precision, group=dist.group.WORLD, fused_exchange=fused, **kw)
+                    plan = lw.get_long_plan(n, precision, None, dist.group.WORLD, None, fused)
+                    ok &= plan.fused == fused
+                    ok &= int(info.steps[0]) == ref["steps"] and rel_l2(out, ref["out"]) <= TOL[precision]
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
