@@ -36,6 +36,9 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 int ilog2(long long v) { int l = 0; while ((1ll << l) < v) ++l; return l; }
 
+constexpr int kMaxDevices = 64;
+int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
+
 // compile-time geometry ------------------------------------------------------------------------
 // Column tile width T (columns per CTA) and row group G (rows per CTA) for transforms of M points
 // with E points per thread: aim at 256-thread CTAs, keep at least 2 columns (32 B of complex128) per
@@ -195,7 +198,8 @@ int launch_col_fwd(const Params<R>& p, int nblocks, cudaStream_t st) {
     constexpr int T = col_tile_of<R>(M);
     constexpr int E = points_per_thread<R>::value;
     const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M, E>::table_size + SC_N);
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {false};     // function attributes are per device
+    bool& attr = attr_dev[current_device()];
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_fwd<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_col_fwd<R, M, T><<<nblocks, T * (M / E), smem, st>>>(p);
     ++ssfm_launches;
@@ -207,7 +211,8 @@ int launch_col_inv(const Params<R>& p, int nblocks, cudaStream_t st) {
     constexpr int T = col_tile_of<R>(M);
     constexpr int E = points_per_thread<R>::value;
     const size_t smem = sizeof(C) * (size_t)(M * T + fft_plan<M, E>::table_size + SC_N) + sizeof(R) * (size_t)(M * T);
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {false};     // function attributes are per device
+    bool& attr = attr_dev[current_device()];
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_col_inv<R, M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_col_inv<R, M, T><<<nblocks, T * (M / E), smem, st>>>(p);
     ++ssfm_launches;
@@ -226,7 +231,8 @@ int launch_col_mid(const Params<R>& p, int nblocks, int cluster, cudaStream_t st
     constexpr int T = col_tile_of<R>(M);
     constexpr int E = points_per_thread<R>::value;
     const size_t smem = col_mid_smem<R, M>();
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {false};     // function attributes are per device
+    bool& attr = attr_dev[current_device()];
     if (!attr) {
         CU_TRY(cudaFuncSetAttribute(k_col_mid<R, M, T, SYNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (SYNC == SYNC_CLUSTER)
@@ -292,7 +298,8 @@ int launch_row(const Params<R>& p, int nblocks, cudaStream_t st) {
     constexpr int G = row_group_of<R>(M);
     constexpr int E = points_per_thread<R>::value;
     const size_t smem = sizeof(C) * (size_t)(G * RowExchange<M, E>::size + fft_plan<M, E>::table_size + SC_N);
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {false};     // function attributes are per device
+    bool& attr = attr_dev[current_device()];
     if (!attr) { CU_TRY(cudaFuncSetAttribute(k_row<R, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_row<R, M, G><<<nblocks, G * (M / E), smem, st>>>(p);
     ++ssfm_launches;

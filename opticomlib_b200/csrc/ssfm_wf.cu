@@ -35,7 +35,10 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     typedef wf_geom<R, M1, M2> GEO;
     auto kern = k_wf<R, M1, M2, SMALL, true>;
     const int total = p.n_pol * (p.n2 / GEO::T);
-    static int max_clusters[17] = {0};                           // per instantiation and cluster size
+    static int max_clusters_dev[64][17] = {{0}};                 // per instantiation, device and cluster size
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int (&max_clusters)[17] = max_clusters_dev[(dev >= 0 && dev < 64) ? dev : 0];
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(GEO::NT); cfg.dynamicSmemBytes = GEO::smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -103,7 +106,12 @@ template <typename R, int M1, int M2, bool SMALL>
 int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
     typedef wf_geom<R, M1, M2> GEO;
     auto kern = k_wf<R, M1, M2, SMALL, false>;
-    static int per_sm = -1;                                     // per instantiation; one device kind per process
+    static int per_sm_dev[64];                                  // per instantiation and device (function attributes are per device)
+    static bool per_sm_init = false;
+    if (!per_sm_init) { for (int& v : per_sm_dev) v = -1; per_sm_init = true; }
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    int& per_sm = per_sm_dev[(dev0 >= 0 && dev0 < 64) ? dev0 : 0];
     if (per_sm < 0) {
         WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
         int v = 0;

@@ -262,6 +262,57 @@ def DBP(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.0
                  phi_max=phi_max, h=h, show_progress=show_progress, return_steps=return_steps, **kw)
 
 
+# ---- DM: dispersive medium = one FFT-domain transfer function ------------------------------------------
+def transfer_batch(x, h, *, device=None):
+    """``ifft(fft(x) * H)`` along the last axis of ``x[..., N]`` (NumPy array or CUDA tensor, complex128 arithmetic) with
+    ``H[N]`` in numpy bin order -- the operation of DM and of the apply step of FBG.  N: a power of two in [2^8, 2^22]."""
+    torch = engine._torch()
+    as_tensor = torch.is_tensor(x)
+    dev = engine.require_cuda(x.device if as_tensor and x.is_cuda else device)
+    xt = (x if as_tensor else torch.from_numpy(np.ascontiguousarray(x))).to(dev).to(torch.complex128)
+    ht = (h if torch.is_tensor(h) else torch.from_numpy(np.ascontiguousarray(h))).to(dev).to(torch.complex128).contiguous()
+    n = xt.shape[-1]
+    if n < 256 or n > (1 << 22) or n & (n - 1):
+        raise ValueError("transfer functions need a power-of-two length in [2^8, 2^22], got %d" % n)
+    y = xt.reshape(-1, n).contiguous()
+    if y.data_ptr() == xt.data_ptr() and as_tensor and x.is_cuda and x.dtype == torch.complex128:
+        y = y.clone()
+    plan = engine.get_plan(n, 1, y.shape[0], torch.complex128, dev, lane=99)
+    plan.apply_transfer(y, ht)
+    y = y.reshape(xt.shape)
+    return y if as_tensor else y.cpu().numpy()
+
+
+def DM(input, D, retH=False, *, device=None):
+    """Dispersive medium -- reference devices.py:941-1035: ``H = exp(j w^2 D/2)``, ``output = ifft(fft(input) * H)``
+    for signal and noise (complex128, as NumPy computes it).  ``D`` in ps^2."""
+    tic()
+    if _kind(input) != "optical":
+        toc()
+        raise TypeError("`input` must be of type 'optical_signal'.")
+    dev = engine.require_cuda(device)
+    D = D * 1e-12 ** 2                                        # devices.py:1023 (the reference rebinds its argument the same way)
+    n = input.size
+    w = np.fft.fftfreq(n, _gv_of(input).dt) * 2 * np.pi      # input.w(), typing.py:1641
+    H = np.exp(1j * w ** 2 * D / 2)
+    sig = np.asarray(input.signal, dtype=np.complex128)
+    has_noise = not _is_null(input.noise)
+    rows = [sig.reshape(-1, n)]
+    if has_noise:
+        rows.append(np.asarray(input.noise, dtype=np.complex128).reshape(-1, n))
+    try:
+        y = transfer_batch(np.concatenate(rows), H, device=dev)
+    except Exception:
+        toc()
+        raise
+    k = rows[0].shape[0]
+    output = type(input)(y[:k].reshape(sig.shape), y[k:].reshape(sig.shape)) if has_noise else type(input)(y[:k].reshape(sig.shape))
+    if retH:
+        return output, np.fft.fftshift(H)                     # (the reference leaks its tic on this branch)
+    output.execution_time = toc()
+    return output
+
+
 # ---- LPF / BPF ------------------------------------------------------------------------------------
 def _bessel_sos(n, wn, fs):
     """Filter design on the host exactly as the reference asks SciPy for it (devices.py:814, 1363)."""
@@ -367,7 +418,7 @@ def install(precision: str | None = None):
     if precision is not None:
         _complex_dtype(precision)
         DEFAULT_PRECISION = precision
-    for name, fn in (("FIBER", FIBER), ("DBP", DBP), ("LPF", LPF), ("BPF", BPF)):
+    for name, fn in (("FIBER", FIBER), ("DBP", DBP), ("LPF", LPF), ("BPF", BPF), ("DM", DM)):
         _SAVED.setdefault(("opticomlib.devices", name), getattr(dv, name))
         setattr(dv, name, fn)
     for modname in ("opticomlib.ook", "opticomlib.ppm"):

@@ -107,6 +107,21 @@ class Plan:
                                                        ms, ctypes.c_void_p(stream)))
         return [float(v) for v in ms]
 
+    def apply_transfer(self, field, h):
+        """In place: row <- ifft(fft(row) * H) for every row of ``field`` ([rows, N] CUDA tensor, plan dtype);
+        ``h`` = H[N] in numpy bin order, same dtype and device (DM, devices.py:1025-1029; FBG apply step 2314-2316)."""
+        torch = _torch()
+        if field.dtype != self.cdtype or h.dtype != self.cdtype or not field.is_cuda or not h.is_cuda:
+            raise ValueError("field and h must be CUDA tensors of dtype %s" % self.cdtype)
+        if not field.is_contiguous() or not h.is_contiguous() or h.numel() != self.n:
+            raise ValueError("field must be contiguous and h must hold %d bins" % self.n)
+        if field.numel() != self.batch * self.n_pol * self.n:
+            raise ValueError("field has %d elements, plan expects %d" % (field.numel(), self.batch * self.n_pol * self.n))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ssfm_apply_transfer(self.handle, field.data_ptr(), h.data_ptr(), ctypes.c_void_p(stream)))
+        return field
+
     def last_timing(self):
         """(kind, teams, kernel_ms) of the last propagate: kind 2 = persistent kernel (one launch, timed with
         CUDA events on the launching stream), kind 1 = multi-launch schedule (kernel_ms = 0)."""

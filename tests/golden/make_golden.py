@@ -70,9 +70,24 @@ def nonpow2():
     fiber_case("fiber_n999_odd", s, length=10.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.02)
 
 
+def dm():
+    """DM (devices.py:941-1035): two polarisations + noise, and a plain single-polarisation field."""
+    from opticomlib.devices import DM
+    rng = np.random.default_rng(20261019)
+    s = tx(16, 256, 9, 10.0)   # N = 4096
+    sig2 = np.stack([s.signal, 0.5j * s.signal[::-1]])
+    noi2 = 1e-3 * (rng.standard_normal(sig2.shape) + 1j * rng.standard_normal(sig2.shape))
+    o, H = DM(optical_signal(sig2, noi2), D=4000.0, retH=True)
+    save("dm_2pol_noise_4096", x=sig2, xn=noi2, dt=np.float64(gv.dt), D=np.float64(4000.0), out=o.signal, outn=o.noise, H=H)
+    o = DM(optical_signal(s.signal), D=-1700.0)
+    save("dm_1pol_4096", x=s.signal, dt=np.float64(gv.dt), D=np.float64(-1700.0), out=o.signal)
+
+
 def main():
     if "nonpow2" in sys.argv:
         return nonpow2()
+    if "dm" in sys.argv:
+        return dm()
     rng = np.random.default_rng(20261017)
 
     # --- FIBER / DBP, shipped float32 path ------------------------------------------------

@@ -126,3 +126,21 @@ def test_filter_errors_match_reference(ob):
         ob.LPF(ob.optical_signal(np.ones((2, 100), complex)), BW=1e9)
     with pytest.raises(ValueError, match="padlen"):                     # scipy's message for N <= edge
         ob.LPF(ob.electrical_signal(np.ones(15)), BW=1e9)
+
+
+def test_dm_matches_reference_output(ob):
+    """DM drop-in (N1 of SURVEY.md section 8(f)) against outputs of the unmodified reference (tests/golden/dm_*.npz)."""
+    from conftest import golden
+    g = golden("dm_2pol_noise_4096")
+    ob.gv.dt = float(g["dt"]); ob.gv.fs = 1 / float(g["dt"])
+    out, H = ob.DM(ob.optical_signal(g["x"], g["xn"]), D=float(g["D"]), retH=True)
+    assert isinstance(out, ob.optical_signal) and out.signal.shape == g["out"].shape and out.signal.dtype == np.complex128
+    assert rel_l2(out.signal, g["out"]) <= 1e-12 and rel_l2(out.noise, g["outn"]) <= 1e-12
+    assert np.array_equal(H, g["H"])
+    g = golden("dm_1pol_4096")
+    out = ob.DM(ob.optical_signal(g["x"]), D=float(g["D"]))
+    assert out.noise is ob.NULL and rel_l2(out.signal, g["out"]) <= 1e-12 and out.execution_time > 0
+    back = ob.DM(out, D=-float(g["D"]))                                  # the inverse medium restores the field
+    assert rel_l2(back.signal, g["x"]) <= 1e-12
+    with pytest.raises(TypeError, match="optical_signal"):
+        ob.DM(ob.electrical_signal(np.ones(1024)), D=1.0)
