@@ -151,12 +151,12 @@ def _nccl_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpus_nccl_exchange(ob):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_several_gpus_fused_and_nccl_exchange(ob, world):
     import torch
     import torch.multiprocessing as mp
-    world = 2
     if torch.cuda.device_count() < world:
-        pytest.skip("needs two GPUs")
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
