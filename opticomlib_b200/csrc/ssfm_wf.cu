@@ -126,7 +126,7 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
     if (teams < 1) return SSFM_ERR_UNSUPPORTED;                          // one waveform does not fit on the chip
     if constexpr (M2 <= 256) {                                           // teams of <= 16 CTAs can be thread-block clusters
-        if (l.cluster != 0 && total <= 16 && total >= 2) {
+        if (l.cluster != 0 && total <= 16 && total >= 2 && (total & (total - 1)) == 0) {
             const int rc = wf_launch_cluster<R, M1, M2, SMALL>(p, l, teams_out, st, per_sm * l.num_sms);
             if (rc != SSFM_ERR_UNSUPPORTED) return rc;
         }
@@ -181,6 +181,7 @@ template <typename R>
 int wf_propagate(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
     if (p.xfer) return SSFM_ERR_UNSUPPORTED;
 #define WF_CASE(A, B) if (p.n1 == A && p.n2 == B) return wf_launch_small<R, A, B>(p, l, teams_out, st);
+    WF_CASE(64, 64) WF_CASE(64, 128)      // 2^12, 2^13: teams of one / two CTAs (per polarisation)
     WF_CASE(128, 128) WF_CASE(128, 256) WF_CASE(256, 256) WF_CASE(256, 512) WF_CASE(512, 512) WF_CASE(512, 1024)
     WF_CASE(1024, 1024)
 #undef WF_CASE

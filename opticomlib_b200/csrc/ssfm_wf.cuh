@@ -191,12 +191,14 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     unsigned int* const bar = a.bar + (size_t)team * 32;
     auto bar_arrive = [&](WfSlot<R>& S) {
         if (CL) { cluster_arrive_release(); return; }           // every thread releases its own stores
+        if (total == 1u) return;                                // a team of one CTA: the CTA barrier in bar_wait is enough
         __syncthreads();                                        // every thread's stores are ordered before the release
         S.bar_target += total;
         if (tid == 0) red_release_add_u32(bar, 1u);
     };
     auto bar_wait = [&](const WfSlot<R>& S) {
         if (CL) { cluster_wait_acquire(); return; }
+        if (total == 1u) { __syncthreads(); return; }           // stores (write-through) -> bar.sync -> ld.global.cg of the same CTA
         if (tid == 0) {
             while ((int)(ld_relaxed_u32(bar) - S.bar_target) < 0) { if (total > 32u) __nanosleep(20); }   // big teams: ease off L2
             fence_acq_rel_gpu();
@@ -230,6 +232,13 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
             unsigned long long m = cl_max[0];
             for (unsigned i = 1; i < total; ++i) m = cl_max[i] > m ? cl_max[i] : m;
             return from_bits<R>(m);                             // (the next write to cl_max / red is behind a later cluster barrier)
+        }
+        if (total == 1u) {                                      // a team of one CTA: the block maximum is the answer
+            unsigned long long b = red[0];
+#pragma unroll
+            for (int i = 1; i < NT / 32; ++i) b = red[i] > b ? red[i] : b;
+            __syncthreads();                                    // red[] is free for the next exchange
+            return from_bits<R>(b);
         }
         const int nwords = (int)total * NW;
         unsigned long long best = 0ull;

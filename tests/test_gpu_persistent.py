@@ -1,7 +1,7 @@
 """GPU parity tests of the persistent whole-propagation kernel k_wf (opticomlib_b200/csrc/ssfm_wf.cuh).
 
 The golden fixtures of the reference are 1024..4096 samples long and therefore run on the multi-launch
-schedule; k_wf adopts waveforms of 2^14 .. 2^20 samples.  Every case here is checked against the CPU oracle
+schedule for 1024 and 2048 samples; k_wf adopts waveforms of 2^12 .. 2^20 samples.  Every case here is checked against the CPU oracle
 (oracle/ssfm_oracle.py, pinned to the reference) and against the multi-launch schedule on the same input.
 Tolerances are BASELINE.json's: rel-L2 <= 1e-4 (fp32), <= 1e-10 (fp64), identical step counts.
 """
@@ -46,6 +46,9 @@ def _kind(ob, n, n_pol, rows, precision):
 
 CASES = [
     # name, log2n, kwargs
+    ("adaptive_2_12", 12, dict(length=12.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.01)),
+    ("fixed_2_12", 12, dict(length=3.05, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, h=0.3)),
+    ("adaptive_2_13", 13, dict(length=10.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.02)),
     ("adaptive_b3", 14, dict(length=12.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.01)),
     ("adaptive_odd", 15, dict(length=10.0, alpha=0.2, beta_2=-20.0, beta_3=0.0, gamma=2.0, phi_max=0.02)),
     ("adaptive_16", 16, dict(length=25.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.01)),
