@@ -189,6 +189,8 @@ static int chirp_plan_create(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t
 template <typename R>
 static int chirp_propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long long max_steps, int resume,
                              cudaStream_t st);
+template <typename R>
+static int chirp_apply_transfer_t(ssfm_plan_t pl, void* field, const void* h_dev, cudaStream_t st);
 
 namespace {
 
@@ -667,7 +669,15 @@ extern "C" {
 
 int ssfm_apply_transfer(ssfm_plan_t pl, void* field, const void* h_dev, void* stream) {
     if (!pl || !field || !h_dev) return fail(SSFM_ERR_INVALID, "null plan, field or transfer function");
-    if (pl->chirp_m || pl->long_n) return fail(SSFM_ERR_UNSUPPORTED, "transfer functions need a power-of-two plan of at most 2^22 samples");
+    if (pl->long_n) return fail(SSFM_ERR_UNSUPPORTED, "transfer functions are not available for long-waveform plans");
+    if (pl->chirp_m) {
+        CU_TRY(cudaSetDevice(pl->device));
+        const int rc = pl->dtype == SSFM_C64 ? chirp_apply_transfer_t<float>(pl, field, h_dev, (cudaStream_t)stream)
+                                             : chirp_apply_transfer_t<double>(pl, field, h_dev, (cudaStream_t)stream);
+        if (rc) return rc;
+        CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        return SSFM_OK;
+    }
     CU_TRY(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_xfer(pl);
@@ -1344,5 +1354,33 @@ static int chirp_propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_param
     }
     pl->have_state = true;
     pl->last = prm;
+    return SSFM_OK;
+}
+
+// row <- ifft_N(fft_N(row) * H) for a length that is not a power of two: the chirp-z pipeline without the Kerr steps
+template <typename R>
+static int chirp_apply_transfer_t(ssfm_plan_t pl, void* field, const void* h_dev, cudaStream_t st) {
+    typedef typename cx_of<R>::type C;
+    ssfm_fiber_params prm{};
+    prm.dt_s = 1.0; prm.length_km = 1e30; prm.phi_max_rad = 0.01; prm.h_km = 1.0;
+    bool fixed, single;
+    Params<R> p = base_params<R>(pl, prm, fixed, single);      // gamma = 0: no Kerr rotation, alpha = 0: no attenuation
+    ssfm_plan_t pi = pl->inner;
+    const C* sct = (const C*)pi->tw_col + pass_table_size(pi->n1, points_per_thread<R>::value);
+    p.field = (C*)field; p.stash = (R*)pl->stash; p.ctrl = pl->ctrl; p.active = pl->active; p.hlog = nullptr;
+    p.batch = (int)pl->batch; p.n_glob = (int)pl->n; p.inv_n = (R)1 / (R)pl->n; p.xfer = (const C*)h_dev;
+    CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)pl->batch, st));   // done = 0, h = 0
+    const int m = (int)pl->chirp_m, rows = (int)(pl->batch * pl->n_pol);
+    const dim3 grid((unsigned)std::min<long long>((m + 255) / 256, 1024), (unsigned)rows);
+    k_bs_open<R><<<grid, 256, 0, st>>>(p, (C*)pl->wb, (const C*)pl->wtab, m, sct);
+    int rc = chirp_transfer<R>(pl, pl->xf_fwd, st);
+    if (rc) return rc;
+    k_bs_mid<R><<<grid, 256, 0, st>>>(p, (C*)pl->wb, m, sct);
+    rc = chirp_transfer<R>(pl, pl->xf_inv, st);
+    if (rc) return rc;
+    k_bs_close<R><<<grid, 256, 0, st>>>(p, (const C*)pl->wb, (const C*)pl->wtab, m, sct);
+    ssfm_launches += 3;
+    CU_TRY(cudaGetLastError());
+    pl->have_state = false;
     return SSFM_OK;
 }

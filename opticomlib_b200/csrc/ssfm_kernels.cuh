@@ -869,11 +869,15 @@ __global__ void k_bs_mid(Params<R> p, typename cx_of<R>::type* wb, int m, const 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         C a = mk<R>((R)0, (R)0);
         if (i < p.n) {
-            const int k = (i < pos) ? i : i - p.n;
-            const R wk = (R)((double)k * p.wscale);
-            const R dim = add_rn(mul_rn(p.c2, mul_rn(wk, wk)), mul_rn(p.c3, cube_r(wk)));
-            R s, c; sincos_r(mul_rn(dim, h), sct, &s, &c);
-            a = cmul(w[i], mk<R>(c, s));
+            if (p.xfer) {                                       // arbitrary transfer function H[k], numpy bin order (DM, FBG)
+                a = cmul(w[i], p.xfer[i]);
+            } else {
+                const int k = (i < pos) ? i : i - p.n;
+                const R wk = (R)((double)k * p.wscale);
+                const R dim = add_rn(mul_rn(p.c2, mul_rn(wk, wk)), mul_rn(p.c3, cube_r(wk)));
+                R s, c; sincos_r(mul_rn(dim, h), sct, &s, &c);
+                a = cmul(w[i], mk<R>(c, s));
+            }
         }
         w[i] = a;
     }

@@ -265,15 +265,14 @@ def DBP(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.0
 # ---- DM: dispersive medium = one FFT-domain transfer function ------------------------------------------
 def transfer_batch(x, h, *, device=None):
     """``ifft(fft(x) * H)`` along the last axis of ``x[..., N]`` (NumPy array or CUDA tensor, complex128 arithmetic) with
-    ``H[N]`` in numpy bin order -- the operation of DM and of the apply step of FBG.  N: a power of two in [2^8, 2^22]."""
+    ``H[N]`` in numpy bin order -- the operation of DM and of the apply step of FBG.  Any N in [2, 2^21] (powers of two up to
+    2^22); lengths that are not powers of two run chirp-z transforms."""
     torch = engine._torch()
     as_tensor = torch.is_tensor(x)
     dev = engine.require_cuda(x.device if as_tensor and x.is_cuda else device)
     xt = (x if as_tensor else torch.from_numpy(np.ascontiguousarray(x))).to(dev).to(torch.complex128)
     ht = (h if torch.is_tensor(h) else torch.from_numpy(np.ascontiguousarray(h))).to(dev).to(torch.complex128).contiguous()
     n = xt.shape[-1]
-    if n < 256 or n > (1 << 22) or n & (n - 1):
-        raise ValueError("transfer functions need a power-of-two length in [2^8, 2^22], got %d" % n)
     y = xt.reshape(-1, n).contiguous()
     if y.data_ptr() == xt.data_ptr() and as_tensor and x.is_cuda and x.dtype == torch.complex128:
         y = y.clone()

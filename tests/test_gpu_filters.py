@@ -144,3 +144,11 @@ def test_dm_matches_reference_output(ob):
     assert rel_l2(back.signal, g["x"]) <= 1e-12
     with pytest.raises(TypeError, match="optical_signal"):
         ob.DM(ob.electrical_signal(np.ones(1024)), D=1.0)
+    # any length, as numpy.fft accepts it (chirp-z transforms): against the reference's own statements
+    rng = np.random.default_rng(5)
+    for n in (1000, 1270, 4099):
+        x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+        out = ob.DM(ob.optical_signal(x), D=2500.0)
+        w = np.fft.fftfreq(n, ob.gv.dt) * 2 * np.pi
+        ref = np.fft.ifft(np.fft.fft(x, axis=-1) * np.exp(1j * w ** 2 * (2500.0 * 1e-12 ** 2) / 2), axis=-1)
+        assert rel_l2(out.signal, ref) <= 1e-12
