@@ -95,6 +95,11 @@ SSFM_API int ssfm_propagate(ssfm_plan_t plan, void* field_dev, const ssfm_fiber_
  * 1 if z >= length. */
 SSFM_API int ssfm_get_state(ssfm_plan_t plan, int32_t* steps_host, double* z_host, double* h_next_host,
                    int32_t* done_host);
+/* Host pipelines: with plan option "async" = 1, ssfm_propagate returns as soon as the persistent kernel is enqueued on
+ * `stream` (when the multi-launch schedule has to be used the call still blocks).  ssfm_copy_state_async enqueues a copy of
+ * the raw per-waveform controller records to (pinned) host memory on the same stream: n_waveforms records of 40 bytes
+ * { double z; double h_next; uint64 scratch; int32 steps; int32 done; uint32 scratch; int32 pad }. */
+SSFM_API int ssfm_copy_state_async(ssfm_plan_t plan, void* records_host, void* stream);
 /* Schedule used by the last ssfm_propagate on this plan: *kind = 1 multi-launch, 2 persistent kernel
  * (then *teams = waveforms in flight and *kernel_ms = device time of that one launch, CUDA events on the
  * launching stream).  Any pointer may be NULL.  Measurement hook for bench.py's roofline object. */

@@ -149,6 +149,7 @@ struct ssfm_plan_s {
     int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
     int placement = -1;          // k_wf: SM-aware team placement (-1 = auto)
+    int async_mode = 0;          // 1: ssfm_propagate returns once the persistent kernel is enqueued (host pipelines)
     int cluster = -1;            // k_wf: teams as thread-block clusters (-1 = auto, 0 = never, 1 = always when possible)
     void* wf_sync = nullptr;     // k_wf barriers / mailboxes / max words
     cudaEvent_t wf_ev[2] = {nullptr, nullptr};
@@ -424,7 +425,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         int teams = 0;
         const int rc = wf_propagate<R>(p, l, &teams, st);
         if (rc == SSFM_OK) {
-            CU_TRY(cudaStreamSynchronize(st));
+            if (!pl->async_mode) CU_TRY(cudaStreamSynchronize(st));
             pl->have_state = true; pl->last = prm; pl->last_kind = 2; pl->last_teams = teams;
             return SSFM_OK;
         }
@@ -826,6 +827,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "fused") { pl->fused = (int)value; }   // 0 unfused, 1 fused (LL barrier), 2 fused (atomic barrier), 3 fused (cluster barrier when possible)
     else if (k == "debug") { pl->debug = (int)value; }
     else if (k == "persistent") { pl->persistent = value ? 1 : 0; }
+    else if (k == "async") { pl->async_mode = value ? 1 : 0; }
     else if (k == "cluster") { pl->cluster = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "placement") { pl->placement = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "teams") { if (value < 0) return fail(SSFM_ERR_INVALID, "teams < 0"); pl->teams_cap = (int)value; }
@@ -879,6 +881,13 @@ int ssfm_get_last_timing(ssfm_plan_t pl, int32_t* kind, int32_t* teams, float* k
             CU_TRY(cudaEventElapsedTime(kernel_ms, pl->wf_ev[0], pl->wf_ev[1]));
         }
     }
+    return SSFM_OK;
+}
+
+int ssfm_copy_state_async(ssfm_plan_t pl, void* dst_host, void* stream) {
+    if (!pl || !dst_host) return fail(SSFM_ERR_INVALID, "null plan or buffer");
+    CU_TRY(cudaSetDevice(pl->device));
+    CU_TRY(cudaMemcpyAsync(dst_host, pl->ctrl, sizeof(Ctrl) * (size_t)pl->batch, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return SSFM_OK;
 }
 

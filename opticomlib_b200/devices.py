@@ -138,6 +138,8 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
         rows = -(-B // max(HOST_LANES, -(-B // rows)))            # even chunks, at least HOST_LANES of them
     chunks = [(r0, min(B, r0 + rows)) for r0 in range(0, B, rows)]
     lanes = min(HOST_LANES, len(chunks))
+    if not want_log and fused and persistent in (None, True):
+        return _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes)
     steps = np.zeros(B, np.int32); z = np.zeros(B); hn = np.zeros(B); done = np.zeros(B, bool)
     logs, errors = {}, []
 
@@ -178,6 +180,42 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
         for ci, (r0, r1) in enumerate(chunks):
             h_log[r0:r1, :logs[ci].shape[1]] = logs[ci]
     return out, engine.StepInfo(steps, z, hn, done, h_log)
+
+
+def _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes):
+    """One host thread, `lanes` CUDA streams: per chunk  H2D copy -> (cast) -> persistent kernel -> D2H copy -> copy of the
+    controller records, all enqueued without waiting (plan option "async"), so the PCIe transfers of one chunk overlap
+    the propagation of another and the device never waits for the host.  (If a plan has to use the multi-launch schedule its
+    call blocks; the result is the same.)"""
+    torch = engine._torch()
+    B = host.shape[0]
+    P, N = (1, host.shape[1]) if host.ndim == 2 else (host.shape[1], host.shape[2])
+    rec = torch.empty(B * engine.STATE_RECORD, dtype=torch.uint8, pin_memory=True)
+    with torch.cuda.device(dev):
+        ln = []
+        for _ in range(lanes):
+            ln.append((torch.cuda.Stream(device=dev),
+                       torch.empty((rows,) + tuple(host.shape[1:]), dtype=host.dtype, device=dev) if host.dtype != tdtype else None,
+                       torch.empty((rows,) + tuple(host.shape[1:]), dtype=tdtype, device=dev)))
+        torch.cuda.current_stream(dev).synchronize()            # the lane buffers exist before any lane stream touches them
+        for ci, (r0, r1) in enumerate(chunks):
+            stream, stage, xbuf = ln[ci % lanes]
+            m = r1 - r0
+            with torch.cuda.stream(stream):
+                x = xbuf[:m]
+                if stage is not None:
+                    stage[:m].copy_(host[r0:r1], non_blocking=True)
+                    x.copy_(stage[:m])                          # cast to the compute dtype on the device
+                else:
+                    x.copy_(host[r0:r1], non_blocking=True)
+                plan = engine.get_plan(N, P, m, tdtype, dev, lane=ci % lanes)
+                plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
+                _set_schedule(plan, True, True)
+                plan.propagate(x, *args, state_out=rec[r0 * engine.STATE_RECORD:r1 * engine.STATE_RECORD])
+                out[r0:r1].copy_(x, non_blocking=True)
+        for stream, _, _ in ln:
+            stream.synchronize()
+    return out, engine.decode_state(rec.numpy())
 
 
 def dbp_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, **kw):

@@ -47,6 +47,17 @@ class StepInfo:
         return int(self.steps.astype(np.int64).sum()) * int(samples_per_waveform)
 
 
+STATE_RECORD = 40      # bytes per waveform copied by ssfm_copy_state_async
+_STATE_DTYPE = np.dtype([("z", "<f8"), ("h", "<f8"), ("pmax", "<u8"), ("steps", "<i4"), ("done", "<i4"), ("arrived", "<u4"),
+                         ("pad", "<i4")])
+
+
+def decode_state(records: np.ndarray) -> StepInfo:
+    """Controller records (uint8 array of B * STATE_RECORD bytes, see ssfm_copy_state_async) -> StepInfo."""
+    r = np.frombuffer(np.ascontiguousarray(records).tobytes(), dtype=_STATE_DTYPE)
+    return StepInfo(r["steps"].astype(np.int32), r["z"].copy(), r["h"].copy(), r["done"].astype(bool), None)
+
+
 class Plan:
     """Owner of one ``ssfm_plan_t`` (twiddles, Kerr-phase stash, controller state)."""
 
@@ -78,8 +89,12 @@ class Plan:
 
     # ------------------------------------------------------------------------------------------
     def propagate(self, field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01,
-                  h=None, max_steps=0, resume=False, want_log=False) -> StepInfo:
-        """In place on ``field`` (CUDA tensor [B, P, N] or [B, N], plan dtype, contiguous)."""
+                  h=None, max_steps=0, resume=False, want_log=False, state_out=None) -> StepInfo:
+        """In place on ``field`` (CUDA tensor [B, P, N] or [B, N], plan dtype, contiguous).
+
+        ``state_out`` (a pinned uint8 host tensor of B * STATE_RECORD bytes): do not wait -- the call returns once the
+        work is enqueued on the current stream (persistent schedule), the controller records are copied to ``state_out``
+        on the same stream, and None is returned; decode with ``decode_state`` after synchronising the stream."""
         torch = _torch()
         if field.dtype != self.cdtype or not field.is_cuda or not field.is_contiguous():
             raise ValueError("field must be a contiguous CUDA tensor of dtype %s" % self.cdtype)
@@ -89,9 +104,17 @@ class Plan:
                                float(phi_max), math.nan if h is None else float(h))
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.ssfm_propagate(self.handle, field.data_ptr(), ctypes.byref(prm), int(max_steps),
-                                               1 if resume else 0, ctypes.c_void_p(stream)))
-        return self.state(want_log)
+            if state_out is not None:
+                self.set_option("async", 1)
+            try:
+                _lib.check(self.lib.ssfm_propagate(self.handle, field.data_ptr(), ctypes.byref(prm), int(max_steps),
+                                                   1 if resume else 0, ctypes.c_void_p(stream)))
+                if state_out is not None:
+                    _lib.check(self.lib.ssfm_copy_state_async(self.handle, state_out.data_ptr(), ctypes.c_void_p(stream)))
+            finally:
+                if state_out is not None:
+                    self.set_option("async", 0)
+        return None if state_out is not None else self.state(want_log)
 
     def time_step_kernels(self, field, dt, reps=5, **fiber):
         """Average device time [ms] of (column forward, row, column inverse) over ``reps`` steps.
