@@ -114,6 +114,11 @@ def _set_schedule(plan, fused=True, persistent=None):
     plan.set_option("persistent", int(bool(fused)) if persistent is None else int(bool(persistent)))
 
 
+HOST_PIPELINE = "threads"       # "threads" (default): one host thread + stream per lane, blocking calls.  "async": one host
+                                # thread enqueues everything without waiting (plan option "async"); "async_sync": the same, but a
+                                # lane is drained before reuse.  Measured on B200 (scripts/exp_e2e.py, 4096 x 2^16 fp64): threads
+                                # 410-450 ms per propagation, async 780-790 ms -- copies issued behind queued cooperative / cluster
+                                # launches did not overlap them -- so the single-thread pipeline stays an experiment.
 HOST_LANES = 3                  # concurrent host->device->host pipelines (threads + streams) of the host path
 HOST_CHUNK_BYTES = 256 << 20    # target size of one chunk of rows on the device
 
@@ -138,7 +143,7 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
         rows = -(-B // max(HOST_LANES, -(-B // rows)))            # even chunks, at least HOST_LANES of them
     chunks = [(r0, min(B, r0 + rows)) for r0 in range(0, B, rows)]
     lanes = min(HOST_LANES, len(chunks))
-    if not want_log and fused and persistent in (None, True):
+    if HOST_PIPELINE != "threads" and not want_log and fused and persistent in (None, True):
         return _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes)
     steps = np.zeros(B, np.int32); z = np.zeros(B); hn = np.zeros(B); done = np.zeros(B, bool)
     logs, errors = {}, []
@@ -201,6 +206,8 @@ def _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, row
         for ci, (r0, r1) in enumerate(chunks):
             stream, stage, xbuf = ln[ci % lanes]
             m = r1 - r0
+            if HOST_PIPELINE == "async_sync":
+                stream.synchronize()
             with torch.cuda.stream(stream):
                 x = xbuf[:m]
                 if stage is not None:

@@ -11,7 +11,9 @@ xh[:] = (10 ** 0.5) * base
 xh *= (1 + 0.01 * torch.rand((rows, 1), dtype=torch.float64)).to(torch.complex128)
 out_h = torch.empty_like(xh)
 orig_get_plan = engine.get_plan
-for chunk_mib, lanes, cluster in ((256, 3, -1), (256, 3, 0), (256, 4, -1), (512, 4, -1), (1024, 3, -1), (1024, 4, 0), (128, 4, -1)):
+for chunk_mib, lanes, cluster, pipe in ((256, 3, -1, "threads"), (256, 3, -1, "async"), (256, 3, -1, "async_sync"), (256, 4, -1, "async_sync"),
+                                       (256, 2, -1, "async_sync"), (512, 3, -1, "async_sync"), (256, 4, -1, "threads")):
+    devices.HOST_PIPELINE = pipe
     devices.HOST_CHUNK_BYTES = chunk_mib << 20
     devices.HOST_LANES = lanes
     def get_plan(*a, **k):
@@ -24,4 +26,4 @@ for chunk_mib, lanes, cluster in ((256, 3, -1), (256, 3, 0), (256, 4, -1), (512,
         torch.cuda.synchronize(); t0 = time.perf_counter()
         _, info = devices.fiber_batch(xh, dt, precision='fp64', out=out_h, **kw)
         torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
-    print('chunk %4d MiB lanes %d cluster %2d: %s ms  best %.3e sample*steps/s' % (chunk_mib, lanes, cluster, ' '.join('%.0f' % (t * 1e3) for t in ts), info.sample_steps(n) / min(ts)), flush=True)
+    print(pipe, 'chunk %4d MiB lanes %d cluster %2d: %s ms  best %.3e sample*steps/s' % (chunk_mib, lanes, cluster, ' '.join('%.0f' % (t * 1e3) for t in ts), info.sample_steps(n) / min(ts)), flush=True)
