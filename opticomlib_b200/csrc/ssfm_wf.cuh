@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     if (CL) {
         team = (int)cluster_id_x();
         me = (int)cluster_ctarank();
+        cluster_arrive_release();                              // every CTA of the cluster has started (its shared memory exists)
+        cluster_wait_acquire();                                // before anyone stores into it through DSMEM
     } else {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
