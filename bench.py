@@ -526,6 +526,21 @@ def secondary(torch, engine, dev, a):
     """Other single-GPU numbers reported next to the headline (not bench lines of their own)."""
     from opticomlib_b200 import workloads as wl
     out = {}
+    # BASELINE config #1 (one 2^16-sample waveform, 8 adaptive steps): launch-latency dominated, reported only
+    x, dt, kw = wl.config_input("cfg1")
+    for prec, td in (("fp64", torch.complex128), ("fp32", torch.complex64)):
+        x0 = torch.from_numpy(x).to(dev).to(td).reshape(1, -1)
+        work = torch.empty_like(x0)
+        plan = engine.get_plan(x0.shape[1], 1, 1, td, dev)
+        best = None
+        for i in range(5):
+            work.copy_(x0); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); info = plan.propagate(work, dt, **kw); e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        out["cfg1_%s" % prec] = {"value": info.sample_steps(x0.shape[1]) / (best * 1e-3), "unit": UNIT,
+                                 "steps": int(info.steps[0]), "ms": best}
     x, dt, kw = wl.config_input("cfg2")
     for prec, td in (("fp64", torch.complex128), ("fp32", torch.complex64)):
         x0 = torch.from_numpy(x).to(dev).to(td).reshape(1, -1)
@@ -559,6 +574,47 @@ def secondary(torch, engine, dev, a):
             ms = e0.elapsed_time(e1)
             best = ms if best is None or ms < best else best
         out["cfg3_%s_%drows" % (other, w["rows"])] = {"value": info.sample_steps(w["n"]) / (best * 1e-3), "unit": UNIT, "ms": best}
+    # a length that is not a power of two (60000 samples: chirp-z transforms of 2^17 points), 64 rows, fp64
+    try:
+        n_odd = 60000
+        base = torch.from_numpy(wl.config_input("cfg1")[0][:n_odd]).to(dev)
+        x0 = ((10.0 ** 0.5) * base).repeat(64, 1).contiguous()
+        work = torch.empty_like(x0)
+        plan = engine.get_plan(n_odd, 1, 64, torch.complex128, dev)
+        kw1 = wl.config_input("cfg1")[2]
+        best = None
+        for i in range(2):
+            work.copy_(x0); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); info = plan.propagate(work, 1.0 / 640e9, **kw1); e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        out["arbitrary_length_60000_fp64_64rows"] = {"value": info.sample_steps(n_odd) / (best * 1e-3), "unit": UNIT, "ms": best,
+                                                     "steps_per_row_mean": float(info.steps.mean())}
+        engine.clear_plans()
+    except Exception as e:
+        out["arbitrary_length_60000_fp64_64rows"] = {"error": repr(e)}
+    # BASELINE config #5's waveform (2^26 samples) on this one GPU: 20 fixed steps of 1 km through the staged transform
+    try:
+        from opticomlib_b200 import longwave as lw
+        n5 = 1 << 26
+        plan5 = lw.get_long_plan(n5, torch.complex128, dev)
+        gen = torch.Generator(device=dev); gen.manual_seed(5)
+        x5 = torch.view_as_complex(torch.randn((plan5.n_outer, plan5.cols, 2), dtype=torch.float64, device=dev, generator=gen) * 0.02).contiguous()
+        c5 = dict(wl.CONFIGS["cfg5"]["fiber"]); c5["length"] = 20.0
+        best = None
+        for i in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); info = plan5.propagate(x5, 1.0 / 640e9, **c5); e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None or ms < best else best
+        out["cfg5_2^26_fp64_1gpu_20steps"] = {"value": int(info.steps[0]) * n5 / (best * 1e-3), "unit": UNIT, "ms": best,
+                                              "ms_per_split_step": best / int(info.steps[0])}
+        del x5
+        lw.clear_plans(); torch.cuda.empty_cache()
+    except Exception as e:
+        out["cfg5_2^26_fp64_1gpu_20steps"] = {"error": repr(e)}
     # BASELINE config #4 receiver on 256 of its 1024 frames x 2^18: BPF -> 10 x [gain; DBP 80 km, h = 10] -> |.|^2 -> LPF
     try:
         from opticomlib_b200 import devices
