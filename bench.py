@@ -378,7 +378,7 @@ def main():
 
     cpu = None
     extra = {}
-    if not a.no_extra:
+    if not a.no_extra and world == 1:                                   # CPU baseline and secondary numbers: one-GPU runs only
         c = cpu_sample(w, a.precision, a.cpu_seconds)
         cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port",
                "sample": "%d of %d rows, oracle port of devices.py:1137-1196 in %s, %d worker processes, %.1f s"
