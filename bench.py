@@ -399,7 +399,8 @@ def main():
                    "untimed device copy before each timed propagation" % (rows * n * csize / 2 ** 20), **fiber},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "opticomlib_b200.fiber_batch(pinned host complex128 -> pinned host %s), rows streamed in chunks over %d "
-                       "lanes (H2D / propagate / D2H overlapped)" % ("complex128" if csize == 16 else "complex64", devices.HOST_LANES)},
+                       "streams (H2D / propagate / D2H overlapped, one enqueueing host thread)"
+                       % ("complex128" if csize == 16 else "complex64", devices.HOST_LANES)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

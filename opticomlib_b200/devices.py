@@ -114,11 +114,14 @@ def _set_schedule(plan, fused=True, persistent=None):
     plan.set_option("persistent", int(bool(fused)) if persistent is None else int(bool(persistent)))
 
 
-HOST_PIPELINE = "threads"       # "threads" (default): one host thread + stream per lane, blocking calls.  "async": one host
-                                # thread enqueues everything without waiting (plan option "async"); "async_sync": the same, but a
-                                # lane is drained before reuse.  Measured on B200 (scripts/exp_e2e.py, 4096 x 2^16 fp64): threads
-                                # 410-450 ms per propagation, async 780-790 ms -- copies issued behind queued cooperative / cluster
-                                # launches did not overlap them -- so the single-thread pipeline stays an experiment.
+HOST_PIPELINE = "auto"          # "async": ONE host thread enqueues, per chunk and round-robin over HOST_LANES streams, H2D copy ->
+                                # persistent kernel (plan option "async": the call does not wait) -> D2H copy -> copy of the
+                                # controller records; nothing blocks until the final synchronisation.  Needs PINNED input and
+                                # output (a pageable copy blocks the enqueueing thread).  "threads": one host thread + stream per
+                                # lane, blocking calls (pageable buffers: the blocking copies of one lane overlap the others).
+                                # "auto" = async for pinned buffers, threads otherwise.  Measured on B200 (scripts/exp_e2e.py,
+                                # 4096 x 2^16 fp64, pinned): async 392 ms per propagation, +-1 ms (device-resident: 387 ms);
+                                # threads 403 ... 654 ms.
 HOST_LANES = 3                  # concurrent host->device->host pipelines (threads + streams) of the host path
 HOST_CHUNK_BYTES = 256 << 20    # target size of one chunk of rows on the device
 
@@ -143,8 +146,11 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
         rows = -(-B // max(HOST_LANES, -(-B // rows)))            # even chunks, at least HOST_LANES of them
     chunks = [(r0, min(B, r0 + rows)) for r0 in range(0, B, rows)]
     lanes = min(HOST_LANES, len(chunks))
-    if HOST_PIPELINE != "threads" and not want_log and fused and persistent in (None, True):
-        return _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes)
+    pipe = HOST_PIPELINE
+    if pipe == "auto":
+        pipe = "async" if (host.is_pinned() and out.is_pinned()) else "threads"
+    if pipe != "threads" and not want_log and fused and persistent in (None, True):
+        return _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes, pipe)
     steps = np.zeros(B, np.int32); z = np.zeros(B); hn = np.zeros(B); done = np.zeros(B, bool)
     logs, errors = {}, []
 
@@ -187,7 +193,7 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
     return out, engine.StepInfo(steps, z, hn, done, h_log)
 
 
-def _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes):
+def _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes, pipe="async"):
     """One host thread, `lanes` CUDA streams: per chunk  H2D copy -> (cast) -> persistent kernel -> D2H copy -> copy of the
     controller records, all enqueued without waiting (plan option "async"), so the PCIe transfers of one chunk overlap
     the propagation of another and the device never waits for the host.  (If a plan has to use the multi-launch schedule its
@@ -206,7 +212,7 @@ def _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, row
         for ci, (r0, r1) in enumerate(chunks):
             stream, stage, xbuf = ln[ci % lanes]
             m = r1 - r0
-            if HOST_PIPELINE == "async_sync":
+            if pipe == "async_sync":
                 stream.synchronize()
             with torch.cuda.stream(stream):
                 x = xbuf[:m]

@@ -9,7 +9,7 @@ base = torch.from_numpy(x)
 xh = torch.empty((rows, n), dtype=torch.complex128, pin_memory=True)
 xh[:] = (10 ** 0.5) * base
 xh *= (1 + 0.01 * torch.rand((rows, 1), dtype=torch.float64)).to(torch.complex128)
-out_h = torch.empty_like(xh)
+out_h = torch.empty(xh.shape, dtype=xh.dtype, pin_memory=True)
 orig_get_plan = engine.get_plan
 for chunk_mib, lanes, cluster, pipe in ((256, 3, -1, "threads"), (256, 3, -1, "async"), (256, 3, -1, "async_sync"), (256, 4, -1, "async_sync"),
                                        (256, 2, -1, "async_sync"), (512, 3, -1, "async_sync"), (256, 4, -1, "threads")):
