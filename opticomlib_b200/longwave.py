@@ -229,8 +229,11 @@ class LongPlan:
 
     # ---- one propagation ------------------------------------------------------------------------
     def propagate(self, field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None,
-                  want_log=False) -> engine.StepInfo:
-        """In place on ``field``: CUDA tensor [N0, N_l/G] (this rank's columns of the sample matrix)."""
+                  want_log=False, on_step=None) -> engine.StepInfo:
+        """In place on ``field``: CUDA tensor [N0, N_l/G] (this rank's columns of the sample matrix).
+
+        ``on_step(field, state)``: called after every split step with the field back in the time domain (the trajectory of
+        ``return_steps=True``, devices.py:1184-1186, 1201-1202); it forces the open/close stages also for a fixed step."""
         torch = _torch()
         on_cuda = isinstance(self.stages, CudaStages)
         if field.dtype != self.cdtype or field.is_cuda != on_cuda or not field.is_contiguous():
@@ -274,15 +277,21 @@ class LongPlan:
                 sg.inner(rows)
                 self._to_columns(rows, field)
                 done_steps += 1
-                if fixed:
+                if fixed and on_step is None:
                     sg.outer(field, 1)                           # end of this step (+ start of the next one)
                     if done_steps >= n_fixed:
                         break
                 else:
                     sg.outer(field, 2)
-                    combine_max()
+                    if not fixed:
+                        combine_max()
                     sg.ctrl(False)
-                    if sg.state().done[0]:
+                    st = sg.state()
+                    if on_step is not None:
+                        if self.fused:
+                            sg.p2p_copy(field, False)
+                        on_step(field, st)
+                    if st.done[0]:
                         break
                     sg.outer(field, 0)
             if self.fused:
@@ -327,14 +336,16 @@ def clear_plans():
 
 
 def fiber_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
-               precision="fp32", device=None, group=None, n_outer=None, want_log=False, gather=True, fused_exchange=True):
+               precision="fp32", device=None, group=None, n_outer=None, want_log=False, gather=True, fused_exchange=True,
+               return_steps=False):
     """Propagate ONE waveform ``field[N]`` (NumPy array or tensor, the same on every rank of ``group``).
 
     With ``group=None`` the whole waveform lives on this process's GPU (any power-of-two N in [2^12, 2^30]); with a
     process group its columns are spread over the ranks and the result is gathered back on every rank
     (``gather=False`` returns this rank's [N0, N_l/G] share instead).  ``fused_exchange`` (default): the kernels store
     straight into the peers' buffers over NVLink (CUDA IPC); ``False``: NCCL all-to-all + re-layout copy.
-    Returns ``(out, StepInfo)``.
+    Returns ``(out, StepInfo)``; with ``return_steps=True`` (one rank only) ``(z, A_z)`` like devices.py:1201-1202: positions
+    ``z[steps+1]`` (float64, ``z[0] = 0``) and the field after every step ``A_z[steps+1, N]`` (host array).
     """
     torch = _torch()
     dev = engine.require_cuda(device)
@@ -347,6 +358,14 @@ def fiber_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, 
     mine = local_columns(x, plan.n_outer, plan.ranks, plan.rank).to(dev).to(tdtype).contiguous()
     if mine.data_ptr() == x.data_ptr():
         mine = mine.clone()
+    if return_steps:
+        if plan.ranks > 1:
+            raise NotImplementedError("return_steps is available for one rank only")
+        real = np.float32 if tdtype == torch.complex64 else np.float64
+        z_list, snaps = [0.0], [mine.reshape(-1).cpu()]           # snapshots go to the host: a trajectory of a long waveform is large
+        plan.propagate(mine, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h,
+                       on_step=lambda f, st: (z_list.append(real(st.z[0])), snaps.append(f.reshape(-1).cpu())))
+        return np.array(z_list, dtype=np.float64), torch.stack(snaps).numpy()
     info = plan.propagate(mine, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
     if not gather:
         return mine, info

@@ -65,6 +65,22 @@ def test_one_gpu_matches_oracle(ob, name, log2n, n_outer, kw, precision):
         assert info.z[0] == info2.z[0]
 
 
+def test_return_steps_long(ob):
+    """The trajectory of return_steps=True through the staged transform (open / close stages per step)."""
+    from opticomlib_b200 import longwave as lw
+    n = 1 << 14
+    x = _wave(n, 4)
+    for kw in (dict(length=5.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.02),
+               dict(length=2.2, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, h=0.5)):
+        with np.errstate(all="ignore"):
+            ref = oracle_fiber(x, DT, real=np.float64, return_steps=True, **kw)
+        z, traj = lw.fiber_long(x, DT, precision="fp64", n_outer=16, return_steps=True, **kw)
+        assert z[0] == 0.0 and len(z) == ref["steps"] + 1 and traj.shape == (len(z), n)
+        np.testing.assert_allclose(z[1:], ref["z"], rtol=1e-10)
+        for k in (0, 1, len(z) // 2, len(z) - 1):
+            assert rel_l2(traj[k], ref["traj"][k]) <= TOL["fp64"]
+
+
 def test_dbp_long(ob):
     from opticomlib_b200 import longwave as lw
     n = 1 << 14

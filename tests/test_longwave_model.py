@@ -64,6 +64,24 @@ def test_one_rank_model_matches_the_oracle(name, real, tol):
     np.testing.assert_allclose(info.h_log[0], ref["h"], rtol=1e-3 if real is np.float32 else 1e-10)
 
 
+def test_trajectory_callback_forces_open_close_stages():
+    """on_step (return_steps) on the NumPy stage model: fixed and adaptive runs, snapshots against the oracle's trajectory."""
+    n = 1 << 12
+    x = _wave(n, seed=2)
+    for name in ("fixed", "adaptive"):
+        kw = CASES[name]
+        with np.errstate(all="ignore"):
+            ref = oracle_fiber(x, DT, real=np.float64, return_steps=True, **kw)
+        plan = lw.LongPlan(n, torch.complex128, stages=NumpyStages(n, 16, 1, 0, np.float64), n_outer=16)
+        mine = torch.from_numpy(np.ascontiguousarray(lw.local_columns(x, 16, 1, 0))).contiguous()
+        zs, snaps = [], []
+        info = plan.propagate(mine, DT, on_step=lambda f, st: (zs.append(float(st.z[0])), snaps.append(f.numpy().reshape(-1).copy())), **kw)
+        assert len(snaps) == ref["steps"] == int(info.steps[0])
+        np.testing.assert_allclose(zs, ref["z"], rtol=1e-12)
+        for k in (0, len(snaps) // 2, len(snaps) - 1):
+            assert rel_l2(snaps[k], ref["traj"][k + 1]) <= 1e-11
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
