@@ -44,7 +44,10 @@ int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxD
 // with E points per thread: aim at 256-thread CTAs, keep at least 2 columns (32 B of complex128) per
 // row segment, never more than 32, and never more rows/columns than the matrix has.
 constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-constexpr int col_tile(int M, int E) { return clampi(clampi(256 * E / M, 2, 32), 1, M); }
+#ifndef SSFM_COL_THREADS
+#define SSFM_COL_THREADS 256      // threads per CTA of the column kernels (experiments: 128 = four smaller CTAs per SM)
+#endif
+constexpr int col_tile(int M, int E) { return clampi(clampi(SSFM_COL_THREADS * E / M, 2, 32), 1, M); }
 constexpr int row_group(int M, int E) { return clampi(256 * E / M, 1, M / 2); }
 template <typename R> constexpr int col_tile_of(int M) { return col_tile(M, points_per_thread<R>::value); }
 template <typename R> constexpr int row_group_of(int M) { return row_group(M, points_per_thread<R>::value); }

@@ -165,3 +165,23 @@ def test_single_waveform_2_20(ob):
         assert _kind(ob, n, 1, 1, precision)[0] == 2
         assert int(info.steps[0]) == ref["steps"] and ref["steps"] >= 3
         assert rel_l2(out[0], ref["out"]) <= TOL[precision]
+
+
+@pytest.mark.parametrize("log2n", [11, 12, 14])
+def test_degenerate_step_rules(ob, log2n):
+    """length = 0 (no step, field untouched), h > length (one clamped step), a sliver of a last step: same bookkeeping as the
+    reference loop (devices.py:1159-1162, 1172-1173, 1195-1196) on the multi-launch schedule (2^11) and on k_wf."""
+    n = 1 << log2n
+    x = _wave(n, 30 + log2n)
+    base = dict(alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0)
+    for precision in ("fp64", "fp32"):
+        out, info = ob.fiber_batch(x[None, :], DT, precision=precision, length=0.0, **base)
+        assert int(info.steps[0]) == 0 and bool(info.done[0])
+        assert rel_l2(out[0], x.astype(np.complex64 if precision == "fp32" else np.complex128)) == 0.0
+        for kw in (dict(length=2.0, h=5.0), dict(length=1.0, h=0.3), dict(length=3.0, phi_max=100.0)):
+            with np.errstate(all="ignore"):
+                ref = oracle_fiber(x, DT, real=REAL[precision], **base, **kw)
+            out, info = ob.fiber_batch(x[None, :], DT, precision=precision, **base, **kw)
+            assert int(info.steps[0]) == ref["steps"], (precision, kw)
+            assert rel_l2(out[0], ref["out"]) <= TOL[precision], (precision, kw)
+            np.testing.assert_allclose(info.z[0], ref["z"][-1], rtol=1e-6 if precision == "fp32" else 1e-12)
