@@ -152,6 +152,7 @@ struct ssfm_plan_s {
     int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
     int placement = -1;          // k_wf: SM-aware team placement (-1 = auto)
+    void* dim_tab = nullptr;     // k_wf: imag(D~) per bin (transposed order), refilled by every propagation
     int async_mode = 0;          // 1: ssfm_propagate returns once the persistent kernel is enqueued (host pipelines)
     int cluster = -1;            // k_wf: teams as thread-block clusters (-1 = auto, 0 = never, 1 = always when possible)
     void* wf_sync = nullptr;     // k_wf barriers / mailboxes / max words
@@ -418,6 +419,10 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         Params<R> p = base;
         p.field = (C*)field; p.stash = (R*)pl->stash; p.ctrl = pl->ctrl; p.active = pl->active;
         p.ticket = pl->ticket; p.slots = pl->slots; p.hlog = pl->hlog; p.batch = (int)B;
+        if (!pl->dim_tab) CU_TRY(cudaMalloc(&pl->dim_tab, sizeof(R) * (size_t)pl->n));
+        k_fill_dim<R><<<(unsigned)((pl->n + 255) / 256), 256, 0, st>>>(p, (R*)pl->dim_tab);
+        ++ssfm_launches;
+        p.dim_tab = (const R*)pl->dim_tab;
         WfLaunch l{};
         l.sync_buf = pl->wf_sync; l.num_sms = pl->num_sms;
         l.fixed = fixed ? 1 : 0; l.single = single ? 1 : 0; l.resume = resume ? 1 : 0;
@@ -812,7 +817,7 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     cudaFree(pl->wb); cudaFree(pl->wtab); cudaFree(pl->xf_fwd); cudaFree(pl->xf_inv);
     for (int r = 0; r < 8; ++r)
         if (pl->peer_base[r] && pl->peer_base[r] != pl->xbuf) cudaIpcCloseMemHandle(pl->peer_base[r]);
-    cudaFree(pl->xbuf); cudaFree(pl->d_peer_flags);
+    cudaFree(pl->xbuf); cudaFree(pl->d_peer_flags); cudaFree(pl->dim_tab);
     if (pl->wf_side) cudaStreamDestroy(pl->wf_side);
     if (pl->wf_ev_side) cudaEventDestroy(pl->wf_ev_side);
     if (pl->inner) ssfm_plan_destroy(pl->inner);

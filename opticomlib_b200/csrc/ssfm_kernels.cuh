@@ -71,6 +71,9 @@ struct Params {
     // my row goes to rank nb >> peer_shift at [peer_base + row][nb & mask] with pitch peer_pitch = columns per rank.
     typename cx_of<R>::type* peer[8];
     int peer_mode, peer_shift, peer_pitch, peer_base;
+    const R* dim_tab;    // k_wf: imag(D~(w_k)) per bin in transposed order [k1][k2], filled once per propagation by k_fill_dim with
+                         // exactly the operations of the inline evaluation (bit-identical), so that the row phase spends one
+                         // L2 load instead of ~10 arithmetic instructions per sample and step
     int fwd_only;        // 1: the row kernel stops after the forward transforms and stores the spectrum (transposed order):
                          // used once per plan to build the chirp spectra of the arbitrary-length transform
     int defer_ctrl;      // 1: k_col_inv only accumulates max|A|^2 in ctrl.pmax; the controller runs later (k_ctrl_step), after
@@ -221,6 +224,18 @@ __device__ __forceinline__ void controller_update(const Params<R>& p, int b, R p
     const int s = c.steps;
     const CtrlNext<R> n = controller_next<R>(p, (R)c.z, h, s, pmax);
     controller_commit<R>(p, b, h, s, n);
+}
+
+// imag(D~(w_k)) = imag(1j/2 beta_2) w^2 + imag(1j/6 beta_3) w^3 on the fftfreq grid (devices.py:1144-1145), one value per bin in
+// transposed order: pos = k1 * N2 + k2 holds bin k = k1 + N1 k2
+template <typename R>
+__global__ void k_fill_dim(Params<R> p, R* out) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= p.n) return;
+    int k = pos / p.n2 + p.n1 * (pos % p.n2);
+    k = (k < (p.n >> 1)) ? k : k - p.n;
+    const R wk = (R)((double)k * p.wscale);
+    out[pos] = add_rn(mul_rn(p.c2, mul_rn(wk, wk)), mul_rn(p.c3, cube_r(wk)));
 }
 
 // deferred controller step of waveform 0 (long waveforms: ctrl.pmax holds the max over all ranks by now)

@@ -390,15 +390,10 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
                 fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
                 {
-                    const int half = p.n_glob >> 1;
+                    const R* __restrict__ drow = p.dim_tab + (size_t)k1 * p.n2;   // imag(D~) of my row's bins (k_fill_dim)
 #pragma unroll
                     for (int q = 0; q < E; ++q) {
-                        const int k2 = tr + q * (M2 / E);
-                        int k = k1 + p.n1 * k2;                 // transposed-order bin index
-                        k = (k < half) ? k : k - p.n_glob;      // fftfreq ordering
-                        const R wk = (R)((double)k * p.wscale); // rad/ps (see Params::wscale)
-                        const R dim = add_rn(mul_rn(p.c2, mul_rn(wk, wk)), mul_rn(p.c3, cube_r(wk)));
-                        const R ph = mul_rn(dim, h);
+                        const R ph = mul_rn(__ldg(drow + tr + q * (M2 / E)), h);
                         R sn, co; sincos_r(ph, sct, &sn, &co);
                         v[q] = cmul(v[q], mk<R>(co, sn));
                     }
