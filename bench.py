@@ -57,7 +57,7 @@ def workload(name, rows_override=0):
     c = wl.CONFIGS[name]
     rows = rows_override or c.get("rows", 1)
     return dict(name=name, base=base, dt=dt, fiber=kw, rows=rows, n=base.size,
-                gain_db=c.get("gain_db"), nf_db=c.get("nf_db"), fs=c["R"] * c["sps"])
+                gain_db=c.get("gain_db"), nf_db=c.get("nf_db"), fs=c["R"] * c["sps"], sps=c["sps"], rate=c["R"])
 
 
 DESCR = {
@@ -138,8 +138,33 @@ def _cpu_row(args):
     return o["steps"] * row.shape[-1], time.perf_counter() - t
 
 
-def cpu_sample(w, precision, budget_s, cores=None):
-    """Time the oracle on a bounded sample of the workload's rows with a process pool."""
+def _ref_row(args):
+    """One row through the UNMODIFIED reference FIBER (installed under baseline/_ref; import shim for matplotlib / pympler only).
+    return_steps=True is how the reference reports its step count; the per-step snapshot copies cost < 1 % of a step."""
+    row, dt, kw, sps, rate = args
+    from oracle.ref_shim import import_reference
+    import_reference()
+    from opticomlib import gv, optical_signal
+    from opticomlib.devices import FIBER
+    gv(sps=sps, R=rate)
+    assert abs(gv.dt / dt - 1) < 1e-12
+    t = time.perf_counter()
+    with np.errstate(all="ignore"):
+        z, _ = FIBER(optical_signal(row), return_steps=True, **kw)
+    return (len(z) - 1) * row.shape[-1], time.perf_counter() - t
+
+
+def reference_available():
+    try:
+        from oracle.ref_shim import reference_root
+        return reference_root() is not None
+    except Exception:
+        return False
+
+
+def cpu_sample(w, precision, budget_s, cores=None, use_reference=False):
+    """Time the oracle (or, with use_reference, the unmodified reference) on a bounded sample of the workload's rows with a
+    process pool."""
     from concurrent.futures import ProcessPoolExecutor
     from opticomlib_b200 import workloads as wl
     cores = cores or os.cpu_count() or 1
@@ -147,14 +172,16 @@ def cpu_sample(w, precision, budget_s, cores=None):
         one = wl.ase_rows(w["base"], [0], w["fs"], w["gain_db"], w["nf_db"])[0]
     else:
         one = w["base"]
-    units, t1 = _cpu_row((one, w["dt"], w["fiber"], precision))          # calibrate on one row, one core
+    fn = _ref_row if use_reference else _cpu_row
+    mk = (lambda r: (r, w["dt"], w["fiber"], w["sps"], w["rate"])) if use_reference else (lambda r: (r, w["dt"], w["fiber"], precision))
+    units, t1 = fn(mk(one))                                             # calibrate on one row, one core
     if w["rows"] == 1:
         return dict(value=units / t1, cores=1, rows=1, seconds=t1, one_core=units / t1)
     nrows = int(max(cores, min(w["rows"], cores * max(1, int(budget_s / max(t1, 1e-3))))))
     rows = wl.ase_rows(w["base"], range(nrows), w["fs"], w["gain_db"], w["nf_db"])
     t0 = time.perf_counter()
     with ProcessPoolExecutor(max_workers=cores) as ex:
-        res = list(ex.map(_cpu_row, [(rows[i], w["dt"], w["fiber"], precision) for i in range(nrows)]))
+        res = list(ex.map(fn, [mk(rows[i]) for i in range(nrows)]))
     wall = time.perf_counter() - t0
     return dict(value=sum(r[0] for r in res) / wall, cores=cores, rows=nrows, seconds=wall, one_core=units / t1)
 
@@ -166,21 +193,26 @@ def run_reference(a):
     w = workload(a.workload, a.rows)
     cores = os.cpu_count() or 1
     per = []
+    real_ref = reference_available()                                     # baseline/_ref (pip --no-deps install of the reference)
     for _ in range(max(1, a.warmup) if a.warmup < 2 else 1):
-        cpu_sample(w, "fp32", 2.0, cores)
+        cpu_sample(w, "fp32", 2.0, cores, real_ref)
     budget = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps)))
     for _ in range(a.steps):
-        per.append(cpu_sample(w, "fp32", budget, cores))
+        per.append(cpu_sample(w, "fp32", budget, cores, real_ref))
     val = float(np.mean([p["value"] for p in per]))
     ms = float(np.mean([p["seconds"] for p in per]) * 1e3)
-    sample = ("%d of %d rows per step, reference algorithm as shipped (float32/complex64, devices.py:1137-1196) via the "
-              "oracle port, %d worker processes" % (per[0]["rows"], w["rows"], per[0]["cores"]))
+    sample = ("%d of %d rows per step, %s, %d worker processes" % (
+        per[0]["rows"], w["rows"],
+        "the UNMODIFIED reference opticomlib.devices.FIBER (float32/complex64 as shipped; baseline/_ref, NumPy single-threaded "
+        "per process)" if real_ref else
+        "reference algorithm as shipped (float32/complex64, devices.py:1137-1196) via the oracle port (baseline/_ref absent)",
+        per[0]["cores"]))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": DESCR[a.workload], "rows": w["rows"], "samples_per_row": w["n"], **w["fiber"]},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": per[0]["cores"], "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": per[0]["cores"], "kind": "reference" if real_ref else "port", "sample": sample,
                          "one_core": per[0]["one_core"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
