@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <algorithm>
 #include <cmath>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -19,7 +20,7 @@
 using namespace ssfm;
 
 thread_local std::string ssfm_err_slot;   // shared with filtfilt.cu
-long long ssfm_launches = 0;              // kernels launched by this library (bench.py's gpu_launches)
+std::atomic<long long> ssfm_launches{0};   // kernels launched by this library (bench.py's gpu_launches); host threads
 
 namespace {
 

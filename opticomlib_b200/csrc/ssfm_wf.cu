@@ -1,6 +1,7 @@
 // Launch side of the persistent whole-propagation kernel k_wf (ssfm_wf.cuh).
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,7 +12,7 @@
 #include "ssfm_wf.h"
 #include "ssfm_internal.h"
 
-extern long long ssfm_launches;
+extern std::atomic<long long> ssfm_launches;
 
 namespace ssfm {
 namespace {
