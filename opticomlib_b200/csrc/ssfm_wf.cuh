@@ -2,22 +2,31 @@
 //
 // Reference loop: opticomlib/devices.py:1155-1196.  The multi-launch schedule of ssfm_kernels.cuh streams
 // every waveform through HBM twice per step (k_row, k_col_mid).  Here a TEAM of `total` co-resident CTAs
-// (total = n_pol * N/4096) adopts waveforms and carries each through ALL of its steps, so that
-//   * the field of the waveforms in flight (teams x slots x N samples: a few MiB .. ~50 MiB) never leaves
-//     the 126 MB L2 -- HBM sees one read and one write of the field per PROPAGATION, not four per step;
+// (total = n_pol * N/4096, N = 2^12 .. 2^20) adopts waveforms -- handed out dynamically, since step counts
+// differ per waveform -- and carries each through ALL of its steps, so that
+//   * the field of the waveforms in flight (teams x N samples: a few MiB .. ~30 MiB) never leaves the 126 MB
+//     L2 -- HBM sees one read and one write of the field per PROPAGATION, not four per step;
+//   * the Kerr-phase stash of a tile lives in the shared memory of the CTA that owns the tile (the same CTA
+//     visits the same tile every step): the stash traffic of the multi-launch schedule is gone;
 //   * pass tables and the sincos table are loaded once per CTA; there are no launches, tickets or host
 //     polls inside a propagation, and the step-size controller runs redundantly in every CTA.
 //
 // Per step each CTA runs a ROW phase (G rows of the N1 x N2 matrix: forward transform, exp(D~ h),
 // inverse transform) and a COLUMN phase (T columns: inverse transform, 1/N, max|A|^2 -> team exchange
 // -> controller -> merged Kerr rotation of the second half step of step s and the first half step of
-// step s+1 -> forward transform).  The phases of one waveform are separated by team barriers (a monotonic
-// arrival counter in L2, release-arrive / acquire-wait).
+// step s+1 -> forward transform).  The phases of one waveform are separated by team barriers.
 //
-//   * the Kerr-phase stash of a tile lives in the shared memory of the CTA that owns the tile (the same CTA
-//     visits the same tile every step): the stash traffic of the multi-launch schedule is gone.
+// Two variants of the team synchronisation (template parameter CL):
+//   CL = true   teams of <= 16 CTAs are thread-block clusters: hardware cluster barrier (arrive.release /
+//               wait.acquire by every thread), per-CTA maxima and the waveform index through distributed shared
+//               memory.  1.4x (fp64) .. 1.6x (fp32) faster per team, but 16-CTA clusters must sit inside one GPC, so
+//               fewer teams are co-resident than the chip has CTA slots;
+//   CL = false  any team size: a monotonic arrival counter in L2 (red.release.gpu / relaxed poll + fence.acq_rel.gpu),
+//               maxima as self-validating 64-bit words {value bits | exchange tag}, waveform index through a mailbox
+//               word; launched cooperatively over every CTA slot, or as the second launch that fills the slots the
+//               clusters leave (ssfm_wf.cu).
 //
-// Tried and dropped (measured on B200, see DESIGN.md §5): letting a team multiplex two or three waveforms
+// Tried and dropped (measured on B200, see DESIGN.md section 3): letting a team multiplex two or three waveforms
 // ("slots") so that it runs a phase of waveform B while the barrier of waveform A completes.  The barrier waits
 // shrank from ~5 k to ~2 k cycles per phase but the time moved into the max|A|^2 exchange in the middle of the
 // column phase (where the registers ARE live and the CTA cannot switch), and the stash had to travel through
