@@ -42,10 +42,15 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     int (&max_clusters)[17] = max_clusters_dev[(dev >= 0 && dev < 64) ? dev : 0];
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(GEO::NT); cfg.dynamicSmemBytes = GEO::smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)total; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (const char* pol = getenv("SSFM_CLUSTER_POLICY")) {      // experiments: 1 = spread, 2 = load balancing
+        at[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+        at[1].val.clusterSchedulingPolicyPreference = (cudaClusterSchedulingPolicy)atoi(pol);
+        cfg.numAttrs = 2;
+    }
     if (max_clusters[total] == 0) {
         WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
         WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
