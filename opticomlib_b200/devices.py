@@ -254,7 +254,7 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
     a = np.asarray(input.to_numpy())                      # signal + noise (typing.py:1596)
     n_pol = 1 if a.ndim == 1 else a.shape[0]
     n = a.shape[-1]
-    if n > (1 << 22) and n_pol == 1:                       # beyond one two-pass transform: N = N0 x N_l stages (longwave.py)
+    if n > (1 << 22):                                      # beyond one two-pass transform: N = N0 x N_l stages (longwave.py)
         from . import longwave
         if return_steps:
             z, traj = longwave.fiber_long(a, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, return_steps=True,

@@ -234,76 +234,102 @@ class LongPlan:
 
         ``on_step(field, state)``: called after every split step with the field back in the time domain (the trajectory of
         ``return_steps=True``, devices.py:1184-1186, 1201-1202); it forces the open/close stages also for a fixed step."""
-        torch = _torch()
-        on_cuda = isinstance(self.stages, CudaStages)
-        if field.dtype != self.cdtype or field.is_cuda != on_cuda or not field.is_contiguous():
-            raise ValueError("field must be a contiguous %s tensor of dtype %s" % ("CUDA" if on_cuda else "CPU", self.cdtype))
-        if tuple(field.shape) != (self.n_outer, self.cols):
-            raise ValueError("field must have shape (%d, %d), got %s" % (self.n_outer, self.cols, tuple(field.shape)))
-        sg = self.stages
-        prm = _lib.FiberParams(float(dt), float(length), float(alpha), float(beta_2), float(beta_3), float(gamma),
-                               float(phi_max), math.nan if h is None else float(h))
-        R = self.real
-        fixed = h is not None
-        single = (not fixed) and ((R(beta_2) == 0 and R(beta_3) == 0) or R(gamma) == 0)
-
-        def combine_max():
-            if self.ranks == 1:
-                return
-            import torch.distributed as dist
-            t = torch.tensor([sg.pmax()], dtype=torch.float64, device=self.device)
-            t = torch.where(torch.isnan(t), torch.full_like(t, float("inf")), t)     # NaN must win the max, as in numpy
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            val = float(t.item())
-            sg.pmax(float("nan") if math.isinf(val) and val > 0 else val)
-
-        ctx = torch.cuda.device(self.device) if on_cuda else _Null()
-        with ctx:
-            if self.fused:
-                sg.p2p_copy(field, True)                        # the time-domain field lives in the library's IPC buffer
-            sg.begin(field, prm)
-            if not fixed and not single:
-                combine_max()
-            sg.ctrl(True)
-            if sg.state().done[0]:
-                return sg.state(want_log)
-            if self.fused:
-                sg.xbar()                                       # nobody stores into a peer before every peer has loaded its field
-            sg.outer(field, 0)
-            n_fixed = fixed_step_count(length, h, R) if fixed else 0
-            done_steps = 0
-            while True:
-                rows = self._to_rows(field)
-                sg.inner(rows)
-                self._to_columns(rows, field)
-                done_steps += 1
-                if fixed and on_step is None:
-                    sg.outer(field, 1)                           # end of this step (+ start of the next one)
-                    if done_steps >= n_fixed:
-                        break
-                else:
-                    sg.outer(field, 2)
-                    if not fixed:
-                        combine_max()
-                    sg.ctrl(False)
-                    st = sg.state()
-                    if on_step is not None:
-                        if self.fused:
-                            sg.p2p_copy(field, False)
-                        on_step(field, st)
-                    if st.done[0]:
-                        break
-                    sg.outer(field, 0)
-            if self.fused:
-                sg.p2p_copy(field, False)
-            sg.sync()
-        info = sg.state(want_log)
-        if not info.done[0]:
-            raise RuntimeError("long-waveform propagation ended before z reached the fibre length (controller out of step)")
-        return info
+        cb = None if on_step is None else (lambda fields, st: on_step(fields[0], st))
+        return propagate_together([self], [field], dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log, cb)
 
     def state(self, want_log=False) -> engine.StepInfo:
         return self.stages.state(want_log)
+
+
+def propagate_together(plans, fields, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None,
+                       want_log=False, on_step=None) -> engine.StepInfo:
+    """Propagate the rows ``fields[i]`` (one per plan: the POLARISATIONS of one waveform) in lock step with ONE step-size
+    sequence: the reference takes the max of |A|^2 over both polarisations (devices.py:1156, 1194), so after every close stage
+    the per-plan maxima are combined (and all-reduced over the ranks) before every plan's controller runs."""
+    torch = _torch()
+    p0 = plans[0]
+    on_cuda = isinstance(p0.stages, CudaStages)
+    for pl, field in zip(plans, fields):
+        if field.dtype != pl.cdtype or field.is_cuda != on_cuda or not field.is_contiguous():
+            raise ValueError("field must be a contiguous %s tensor of dtype %s" % ("CUDA" if on_cuda else "CPU", pl.cdtype))
+        if tuple(field.shape) != (pl.n_outer, pl.cols):
+            raise ValueError("field must have shape (%d, %d), got %s" % (pl.n_outer, pl.cols, tuple(field.shape)))
+    prm = _lib.FiberParams(float(dt), float(length), float(alpha), float(beta_2), float(beta_3), float(gamma),
+                           float(phi_max), math.nan if h is None else float(h))
+    R = p0.real
+    fixed = h is not None
+    single = (not fixed) and ((R(beta_2) == 0 and R(beta_3) == 0) or R(gamma) == 0)
+    pairs = list(zip(plans, fields))
+
+    def combine_max():
+        if p0.ranks == 1 and len(plans) == 1:
+            return
+        vals = [pl.stages.pmax() for pl in plans]
+        val = float("inf") if any(math.isnan(v) for v in vals) else max(vals)    # NaN must win the max, as in numpy
+        if p0.ranks > 1:
+            import torch.distributed as dist
+            t = torch.tensor([val], dtype=torch.float64, device=p0.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=p0.group)
+            val = float(t.item())
+        val = float("nan") if math.isinf(val) and val > 0 else val
+        for pl in plans:
+            pl.stages.pmax(val)
+
+    ctx = torch.cuda.device(p0.device) if on_cuda else _Null()
+    with ctx:
+        for pl, f in pairs:
+            if pl.fused:
+                pl.stages.p2p_copy(f, True)                     # the time-domain field lives in the library's IPC buffer
+            pl.stages.begin(f, prm)
+        if not fixed and not single:
+            combine_max()
+        for pl, f in pairs:
+            pl.stages.ctrl(True)
+        if p0.stages.state().done[0]:
+            return p0.stages.state(want_log)
+        for pl, f in pairs:
+            if pl.fused:
+                pl.stages.xbar()                                # nobody stores into a peer before every peer has loaded its field
+            pl.stages.outer(f, 0)
+        n_fixed = fixed_step_count(length, h, R) if fixed else 0
+        done_steps = 0
+        while True:
+            for pl, f in pairs:
+                rows = pl._to_rows(f)
+                pl.stages.inner(rows)
+                pl._to_columns(rows, f)
+            done_steps += 1
+            if fixed and on_step is None:
+                for pl, f in pairs:
+                    pl.stages.outer(f, 1)                       # end of this step (+ start of the next one)
+                if done_steps >= n_fixed:
+                    break
+            else:
+                for pl, f in pairs:
+                    pl.stages.outer(f, 2)
+                if not fixed:
+                    combine_max()
+                for pl, f in pairs:
+                    pl.stages.ctrl(False)
+                st = p0.stages.state()
+                if on_step is not None:
+                    for pl, f in pairs:
+                        if pl.fused:
+                            pl.stages.p2p_copy(f, False)
+                    on_step(fields, st)
+                if st.done[0]:
+                    break
+                for pl, f in pairs:
+                    pl.stages.outer(f, 0)
+        for pl, f in pairs:
+            if pl.fused:
+                pl.stages.p2p_copy(f, False)
+        for pl, f in pairs:
+            pl.stages.sync()
+    info = p0.stages.state(want_log)
+    if not info.done[0]:
+        raise RuntimeError("long-waveform propagation ended before z reached the fibre length (controller out of step)")
+    return info
 
 
 class _Null:
@@ -317,14 +343,14 @@ class _Null:
 _PLANS: dict = {}
 
 
-def get_long_plan(n_global, complex_dtype, device=None, group=None, n_outer=None, fused_exchange=True) -> LongPlan:
+def get_long_plan(n_global, complex_dtype, device=None, group=None, n_outer=None, fused_exchange=True, pol=0) -> LongPlan:
     torch = _torch()
     dev = engine.require_cuda(device)
     cd = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
-    key = (int(n_global), cd, dev.index, id(group) if group is not None else None, n_outer, bool(fused_exchange))
+    key = (int(n_global), cd, dev.index, id(group) if group is not None else None, n_outer, bool(fused_exchange), int(pol))
     pl = _PLANS.get(key)
     if pl is None:
-        if len(_PLANS) >= 2:                                # long plans own O(N) device memory
+        if len(_PLANS) >= 4:                                # long plans own O(N) device memory
             _PLANS.pop(next(iter(_PLANS))).close()
         pl = _PLANS[key] = LongPlan(n_global, cd, dev, group, n_outer, fused_exchange=fused_exchange)
     return pl
@@ -338,7 +364,8 @@ def clear_plans():
 def fiber_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
                precision="fp32", device=None, group=None, n_outer=None, want_log=False, gather=True, fused_exchange=True,
                return_steps=False):
-    """Propagate ONE waveform ``field[N]`` (NumPy array or tensor, the same on every rank of ``group``).
+    """Propagate ONE waveform ``field[N]`` or ``field[P, N]`` (P = 1 | 2 polarisations sharing one step-size sequence; NumPy
+    array or tensor, the same on every rank of ``group``).
 
     With ``group=None`` the whole waveform lives on this process's GPU (any power-of-two N in [2^12, 2^30]); with a
     process group its columns are spread over the ranks and the result is gathered back on every rank
@@ -352,30 +379,41 @@ def fiber_long(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, 
     tdtype = torch.complex64 if precision in ("fp32", "float32") else torch.complex128
     as_numpy = not torch.is_tensor(field)
     x = torch.from_numpy(np.ascontiguousarray(field)) if as_numpy else field
-    if x.ndim != 1:
-        raise ValueError("fiber_long takes one single-polarisation waveform of shape [N]")
-    plan = get_long_plan(x.shape[0], tdtype, dev, group, n_outer, fused_exchange)
-    mine = local_columns(x, plan.n_outer, plan.ranks, plan.rank).to(dev).to(tdtype).contiguous()
-    if mine.data_ptr() == x.data_ptr():
-        mine = mine.clone()
+    if x.ndim not in (1, 2) or (x.ndim == 2 and x.shape[0] not in (1, 2)):
+        raise ValueError("fiber_long takes one waveform of shape [N] or [P, N] with P = 1 or 2 polarisations")
+    xs = [x] if x.ndim == 1 else [x[p] for p in range(x.shape[0])]
+    plans = [get_long_plan(xs[0].shape[0], tdtype, dev, group, n_outer, fused_exchange, pol=p) for p in range(len(xs))]
+    p0 = plans[0]
+    mine = []
+    for xp in xs:                                                  # one plan per polarisation, propagated in lock step
+        m = local_columns(xp, p0.n_outer, p0.ranks, p0.rank).to(dev).to(tdtype).contiguous()
+        mine.append(m.clone() if m.data_ptr() == xp.data_ptr() else m)
+
+    def whole(parts):                                              # [P][N0, cols] -> tensor shaped like the input (this rank's share)
+        flat = [m.reshape(-1) for m in parts]
+        return flat[0] if x.ndim == 1 else torch.stack(flat)
+
     if return_steps:
-        if plan.ranks > 1:
+        if p0.ranks > 1:
             raise NotImplementedError("return_steps is available for one rank only")
         real = np.float32 if tdtype == torch.complex64 else np.float64
-        z_list, snaps = [0.0], [mine.reshape(-1).cpu()]           # snapshots go to the host: a trajectory of a long waveform is large
-        plan.propagate(mine, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h,
-                       on_step=lambda f, st: (z_list.append(real(st.z[0])), snaps.append(f.reshape(-1).cpu())))
+        z_list, snaps = [0.0], [whole(mine).cpu()]                 # snapshots go to the host: a trajectory of a long waveform is large
+        propagate_together(plans, mine, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h,
+                           on_step=lambda fs, st: (z_list.append(real(st.z[0])), snaps.append(whole(fs).cpu())))
         return np.array(z_list, dtype=np.float64), torch.stack(snaps).numpy()
-    info = plan.propagate(mine, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
+    info = propagate_together(plans, mine, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
     if not gather:
-        return mine, info
-    if plan.ranks > 1:
+        return (mine[0] if x.ndim == 1 else torch.stack(mine)), info
+    if p0.ranks > 1:
         import torch.distributed as dist
-        parts = [torch.empty_like(mine) for _ in range(plan.ranks)]
-        dist.all_gather(parts, mine, group=group)
-        out = torch.cat(parts, dim=1).reshape(-1)
+        full = []
+        for m in mine:
+            parts = [torch.empty_like(m) for _ in range(p0.ranks)]
+            dist.all_gather(parts, m, group=group)
+            full.append(torch.cat(parts, dim=1))
+        out = whole(full)
     else:
-        out = mine.reshape(-1)
+        out = whole(mine)
     return (out.cpu().numpy() if as_numpy else out), info
 
 

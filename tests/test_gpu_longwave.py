@@ -81,6 +81,28 @@ def test_return_steps_long(ob):
             assert rel_l2(traj[k], ref["traj"][k]) <= TOL["fp64"]
 
 
+def test_two_polarisations_long(ob):
+    """[2, N] through the staged transform: one plan per polarisation in lock step, one step-size sequence (devices.py:1194)."""
+    from opticomlib_b200 import longwave as lw
+    n = 1 << 14
+    x = np.stack([_wave(n, 5), 0.4j * _wave(n, 6)[::-1]])
+    for precision in ("fp64", "fp32"):
+        for kw in (dict(length=5.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.02),
+                   dict(length=2.2, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, h=0.5)):
+            with np.errstate(all="ignore"):
+                ref = oracle_fiber(x, DT, real=REAL[precision], **kw)
+            out, info = lw.fiber_long(x, DT, precision=precision, n_outer=16, **kw)
+            assert out.shape == x.shape and int(info.steps[0]) == ref["steps"]
+            assert rel_l2(out, ref["out"]) <= TOL[precision]
+            # the ordinary plan with two polarisation rows
+            out2, info2 = ob.fiber_batch(x[None], DT, precision=precision, **kw)
+            assert int(info2.steps[0]) == int(info.steps[0])
+            assert rel_l2(out, out2[0]) <= (1e-5 if precision == "fp32" else 1e-12)
+    z, traj = lw.fiber_long(x, DT, precision="fp64", n_outer=16, return_steps=True, length=2.2, alpha=0.2, beta_2=-21.27,
+                            gamma=1.3, h=0.5)
+    assert traj.shape == (len(z), 2, n) and len(z) == 6
+
+
 def test_dbp_long(ob):
     from opticomlib_b200 import longwave as lw
     n = 1 << 14

@@ -82,6 +82,22 @@ def test_trajectory_callback_forces_open_close_stages():
             assert rel_l2(snaps[k], ref["traj"][k + 1]) <= 1e-11
 
 
+def test_two_polarisations_share_one_step_sequence():
+    """Two plans (one per polarisation) in lock step, maxima combined before the controller: the 2-pol oracle."""
+    n, n0 = 1 << 12, 16
+    x = np.stack([_wave(n, seed=3), 0.4j * _wave(n, seed=4)[::-1]])
+    for name in ("adaptive", "fixed"):
+        kw = CASES[name]
+        with np.errstate(all="ignore"):
+            ref = oracle_fiber(x, DT, real=np.float64, **kw)
+        plans = [lw.LongPlan(n, torch.complex128, stages=NumpyStages(n, n0, 1, 0, np.float64), n_outer=n0) for _ in range(2)]
+        mine = [torch.from_numpy(np.ascontiguousarray(lw.local_columns(x[p], n0, 1, 0))).contiguous() for p in range(2)]
+        info = lw.propagate_together(plans, mine, DT, **kw)
+        assert int(info.steps[0]) == ref["steps"]
+        out = np.stack([m.numpy().reshape(-1) for m in mine])
+        assert rel_l2(out, ref["out"]) <= 1e-11
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
