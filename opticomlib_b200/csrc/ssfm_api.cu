@@ -138,7 +138,8 @@ struct ssfm_plan_s {
     long long n = 0, batch = 0;
     int log2n = 0, n1 = 0, n2 = 0;
     void *tw_col = nullptr, *tw_row = nullptr, *tw_lo = nullptr, *tw_hi = nullptr, *tw_full = nullptr;
-    void* stash = nullptr;
+    void* stash = nullptr;       // Kerr-phase stash of the multi-launch schedule, allocated on first use (k_wf keeps it in shared memory)
+    bool propagates = false;     // false: plan created for transfer functions only
     void* xfer = nullptr;        // transfer function table (transposed order), allocated on first use
     Ctrl* ctrl = nullptr;
     int* active = nullptr;       // one counter per chunk
@@ -393,6 +394,17 @@ Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed,
     return base;
 }
 
+int ensure_stash(ssfm_plan_t pl) {
+    if (pl->stash) return SSFM_OK;
+    const size_t rsz = pl->dtype == SSFM_C64 ? 4 : 8;
+    cudaError_t e = cudaMalloc(&pl->stash, (size_t)pl->batch * pl->n_pol * (size_t)pl->n * rsz);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(SSFM_ERR_NOMEM, std::string("Kerr-phase stash: ") + cudaGetErrorString(e));
+    }
+    return SSFM_OK;
+}
+
 template <typename R>
 int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long long max_steps, int resume,
                 cudaStream_t st) {
@@ -441,6 +453,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         if (rc != SSFM_ERR_UNSUPPORTED) return rc;
     }
     pl->last_kind = 1;
+    { const int rs = ensure_stash(pl); if (rs) return rs; }
     int ci = 0;
     for (long long b0 = 0; b0 < B; b0 += chunk, ++ci) {
         const long long nb = (B - b0 < chunk) ? (B - b0) : chunk;
@@ -536,6 +549,7 @@ int time_kernels_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm_in,
     if (std::isnan(prm.h_km)) prm.h_km = 1e-3;
     prm.length_km = 1e30;                                 // never finishes: every launch does full work
     bool fixed, single;
+    { const int rs = ensure_stash(pl); if (rs) return rs; }
     Params<R> p = base_params<R>(pl, prm, fixed, single);
     p.field = (C*)field; p.stash = (R*)pl->stash; p.ctrl = pl->ctrl; p.active = pl->active; p.hlog = nullptr;
     p.batch = (int)pl->batch;
@@ -752,7 +766,8 @@ static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t 
     const size_t rsz = dtype == SSFM_C64 ? 4 : 8, csz = 2 * rsz;
     const size_t elems = (size_t)batch * n_pol * n;
     cudaError_t e;
-    e = with_stash ? cudaMalloc(&pl->stash, elems * rsz) : cudaSuccess;
+    pl->propagates = with_stash;
+    e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->ctrl, sizeof(Ctrl) * (size_t)batch);
     if (e == cudaSuccess) { pl->n_active = (int)batch; e = cudaMalloc((void**)&pl->active, sizeof(int) * (size_t)batch); }
     pl->slots_bytes = sizeof(unsigned long long) * 2 * (size_t)batch * n_pol * (size_t)(pl->n2 / col_tile_rt(pl->n1, pl->dtype));
@@ -849,7 +864,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
 int ssfm_propagate(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, int64_t max_steps, int32_t resume,
                    void* stream) {
     if (!pl || !field || !prm) return fail(SSFM_ERR_INVALID, "null plan, field or params");
-    if (!pl->stash) return fail(SSFM_ERR_INVALID, "this plan was created for transfer functions only");
+    if (!pl->propagates && !pl->chirp_m) return fail(SSFM_ERR_INVALID, "this plan was created for transfer functions only");
     if (pl->long_n) return fail(SSFM_ERR_INVALID, "long-waveform plans are driven through ssfm_long_*");
     if (!(prm->dt_s > 0)) return fail(SSFM_ERR_INVALID, "dt_s must be > 0");
     if (max_steps < 0) return fail(SSFM_ERR_INVALID, "max_steps < 0");
