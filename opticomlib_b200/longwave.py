@@ -181,6 +181,10 @@ class LongPlan:
                 flags = [None] * self.ranks
                 dist.all_gather_object(flags, ok, group=group)
                 self.fused = all(flags)
+            if not self.fused and self.rank == 0:
+                import warnings
+                warnings.warn("opticomlib_b200.longwave: peer-memory exchange could not be set up on every rank (CUDA IPC); "
+                              "falling back to the NCCL all-to-all", RuntimeWarning)
 
     def close(self):
         if getattr(self, "stages", None) is not None:
