@@ -38,16 +38,23 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    """profile=True: a second library `_ssfm_b200_prof.so` with the clock64 phase instrumentation of k_wf
+    (-DSSFM_WF_PROFILE; load it with SSFM_B200_LIB=...; experiments only, never the product path)."""
+    if profile:
+        return _build(os.path.join(HERE, "_ssfm_b200_prof.so"), os.path.join(HERE, "build", "prof"), ["-DSSFM_WF_PROFILE"], verbose)
     if not force and not _stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    return _build(LIB, os.path.join(HERE, "build"), [], verbose)
+
+
+def _build(lib: str, objdir: str, extra: list, verbose: bool) -> str:
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)
@@ -55,9 +62,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB
+    subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))
