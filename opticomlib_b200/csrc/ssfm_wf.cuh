@@ -89,12 +89,17 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 
 enum { WF_GRAB = 0, WF_ROW = 1, WF_COL = 2, WF_END = 3 };
 
+// State of the team's current waveform, uniform over the CTA and over the team.  Its home is SHARED memory (two versions,
+// written by thread 0 before a team barrier and read by everyone after it): carried in registers across a phase it gets
+// spilled to local memory, and since the cluster barrier invalidates L1 every phase then began with a serialised L2 round
+// trip before the first field load could be issued (round-1 ncu source page: ~4 % of all warp samples).
 template <typename R>
-struct WfSlot {                   // state of the team's current waveform (uniform over the CTA and over the team)
-    unsigned int w, bar_target, xchg, seq;
-    int state, steps;
-    long long taken;
-    R z, h;
+struct WfShared {
+    unsigned int w;               // waveform index
+    unsigned int xchg;            // max|A|^2 exchanges of this team so far (mbarrier phase parity / tag of the flag-based words)
+    int steps;                    // steps taken so far
+    long long taken;              // steps taken in this call (budget)
+    R z, h;                       // position reached, size of the step in progress
 };
 
 __device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
@@ -103,6 +108,34 @@ __device__ __forceinline__ void st_cluster_u32(void* local_smem, unsigned rank, 
     unsigned ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+
+// mbarrier in shared memory + st.async through distributed shared memory: the data word and its "arrived" signal travel
+// together (complete_tx on the destination CTA's barrier), so the max|A|^2 exchange of a cluster team needs neither the cluster
+// barrier nor a release fence in the middle of the column phase (where the round-1 kernel stalled ~1.5 k cycles in MEMBAR).
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// store `v` into `local_slot` of CTA `rank` and count 8 bytes on that CTA's copy of `local_bar`
+__device__ __forceinline__ void st_async_u64(void* local_slot, unsigned long long* local_bar, unsigned rank, unsigned long long v) {
+    unsigned ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((unsigned)__cvta_generic_to_shared(local_slot)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"((unsigned)__cvta_generic_to_shared(local_bar)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(ra), "l"(v), "r"(rb) : "memory");
 }
 
 // CL = true: the team is one thread-block cluster (teams of <= 16 CTAs): the team barrier is the hardware cluster barrier
@@ -117,7 +150,9 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[32];
     __shared__ unsigned int s_w, s_wcl[2];
-    __shared__ unsigned long long cl_max[16];
+    __shared__ unsigned long long cl_max[16 * (256 / 32)];     // [CTA of the cluster][warp] maxima (st.async from every CTA)
+    __shared__ __align__(8) unsigned long long mb_max;         // mbarrier counting the bytes that arrive in cl_max
+    __shared__ WfShared<R> sh[2];
     C* xb = reinterpret_cast<C*>(smem_raw);                    // exchange buffer: column tile [M1][T] or G padded rows
     constexpr bool TABS = GEO::TABS;
     C* tw1s = xb + GEO::XB;                                    // pass tables of the N1-point (column) transforms
@@ -128,7 +163,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     const C* tw2 = TABS ? ((M1 == M2) ? tw1s : tw2s) : p.tw_row;
 
     const int tid = threadIdx.x;
-    const int tiles = p.n2 / T;                                // column tiles (= row groups) per polarisation
+    constexpr int tiles = M2 / T;                              // column tiles (= row groups) per polarisation (p.n2 == M2, p.n == M1*M2)
+    constexpr int NN = M1 * M2;
     const unsigned total = (unsigned)(tiles * p.n_pol);        // CTAs per team
 
     // ---- team placement.  A team is bulk-synchronous, so its CTAs should run at the same speed, and a CTA's
@@ -143,8 +179,12 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     if (CL) {
         team = (int)cluster_id_x();
         me = (int)cluster_ctarank();
-        cluster_arrive_release();                              // every CTA of the cluster has started (its shared memory exists)
-        cluster_wait_acquire();                                // before anyone stores into it through DSMEM
+        if (tid == 0) {
+            mbar_init(&mb_max, 1u);                            // one arrival per exchange: thread 0's expect_tx
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_arrive_release();                              // every CTA of the cluster has started (its shared memory and its
+        cluster_wait_acquire();                                // barrier exist) before anyone stores into it through DSMEM
     } else {
     unsigned int smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -200,18 +240,20 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
 
     // team barrier, split: arrive after the phase's stores, wait before the next phase's loads
     unsigned int* const bar = a.bar + (size_t)team * 32;
-    auto bar_arrive = [&](WfSlot<R>& S) {
+    unsigned int bar_target = 0u, xchg = 0u, seq = 0u, ver = 0u;   // (xchg is reloaded from shared memory in every phase)
+    int state = WF_GRAB;
+    auto bar_arrive = [&]() {
         if (CL) { cluster_arrive_release(); return; }           // every thread releases its own stores
         if (total == 1u) return;                                // a team of one CTA: the CTA barrier in bar_wait is enough
         __syncthreads();                                        // every thread's stores are ordered before the release
-        S.bar_target += total;                                  // (one arrival per WARP instead -- no CTA barrier, each warp releases
+        bar_target += total;                                  // (one arrival per WARP instead -- no CTA barrier, each warp releases
         if (tid == 0) red_release_add_u32(bar, 1u);             //  its own stores -- was measured 25-35 % slower: 8x the atomics and polls)
     };
-    auto bar_wait = [&](const WfSlot<R>& S) {
+    auto bar_wait = [&]() {
         if (CL) { cluster_wait_acquire(); return; }
         if (total == 1u) { __syncthreads(); return; }           // stores (write-through) -> bar.sync -> ld.global.cg of the same CTA
         if (tid == 0) {
-            while ((int)(ld_relaxed_u32(bar) - S.bar_target) < 0) { if (total > 32u) __nanosleep(20); }   // big teams: ease off L2
+            while ((int)(ld_relaxed_u32(bar) - bar_target) < 0) { if (total > 32u) __nanosleep(20); }   // big teams: ease off L2
             fence_acq_rel_gpu();
         }
         __syncthreads();
@@ -220,30 +262,34 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     // max over the team of a per-thread value (NaN wins, like numpy's max): block reduction, one self-validating
     // word (two for double) per CTA -- {32 value bits | 32-bit exchange tag}: the flag travels with the data, so no
     // fence and no atomic is needed -- and the first warps poll the team's words.
-    auto team_max = [&](WfSlot<R>& S, R pm) -> R {
+    auto team_max = [&](R pm) -> R {
         constexpr int NW = sizeof(R) / 4;
-        ++S.xchg;
-        const unsigned long long tag = (unsigned long long)S.xchg;
-        volatile unsigned long long* wf = a.slots + ((size_t)(team * 2 + (S.xchg & 1u)) * total) * 2;
         const int warp = tid >> 5, lane = tid & 31;
         unsigned long long bits = ord_bits(pm);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
+        if (CL) {
+            // Every WARP sends its maximum to slot [me][warp] of every CTA of the cluster with st.async; the bytes are counted
+            // by the destination's mbarrier, whose phase completes when thread 0's expect_tx and all total x 8 words are in.
+            // No CTA barrier, no cluster barrier, no fence.  (Two exchanges are always separated by a cluster barrier that
+            // every thread passes after it has read cl_max, so one buffer and one barrier are enough.)
+            constexpr int NWARP = NT / 32;
+            const unsigned par = xchg & 1u;
+            ++xchg;
+            if (tid == 0) mbar_expect_tx(&mb_max, total * NWARP * 8u);
+            if (lane < (int)total) st_async_u64(&cl_max[me * NWARP + warp], &mb_max, (unsigned)lane, bits);
+            mbar_wait(&mb_max, par);
+            unsigned long long m = 0ull;
+            for (int i = lane; i < (int)total * NWARP; i += 32) { const unsigned long long x = cl_max[i]; m = x > m ? x : m; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
+            return from_bits<R>(m);
+        }
+        ++xchg;
+        const unsigned long long tag = (unsigned long long)xchg;
+        volatile unsigned long long* wf = a.slots + ((size_t)(team * 2 + (xchg & 1u)) * total) * 2;
         if (lane == 0) red[warp] = bits;
         __syncthreads();
-        if (CL) {                                               // my maximum -> slot [me] of every CTA of the cluster
-            if (tid < (int)total) {
-                unsigned long long b = red[0];
-#pragma unroll
-                for (int i = 1; i < NT / 32; ++i) b = red[i] > b ? red[i] : b;
-                st_cluster_u64(&cl_max[me], (unsigned)tid, b);
-            }
-            cluster_arrive_release();
-            cluster_wait_acquire();
-            unsigned long long m = cl_max[0];
-            for (unsigned i = 1; i < total; ++i) m = cl_max[i] > m ? cl_max[i] : m;
-            return from_bits<R>(m);                             // (the next write to cl_max / red is behind a later cluster barrier)
-        }
         if (total == 1u) {                                      // a team of one CTA: the block maximum is the answer
             unsigned long long b = red[0];
 #pragma unroll
@@ -295,32 +341,43 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
         return from_bits<R>(best);
     };
 
-    WfSlot<R> S;
-    S.w = 0u; S.bar_target = 0u; S.xchg = 0u; S.seq = 0u; S.state = WF_GRAB; S.steps = 0; S.taken = 0; S.z = 0; S.h = 0;
+    // A waveform that is skipped (already done under `resume`, zero length, no step budget) passes through no team barrier,
+    // so the leader of a flag-based team could draw again and overwrite the mailbox word before a slower CTA has read the
+    // current draw: synchronise the team once before the next draw (cluster teams: every draw has its own cluster barrier).
+    auto grab_fence = [&]() {
+        if (!CL) { bar_arrive(); bar_wait(); }
+    };
+    auto sh_read = [&](unsigned v) -> WfShared<R> {
+        const volatile WfShared<R>* q = &sh[v & 1u];
+        WfShared<R> r;
+        r.w = q->w; r.xchg = q->xchg; r.steps = q->steps; r.taken = q->taken; r.z = q->z; r.h = q->h;
+        return r;
+    };
 
-    while (S.state != WF_END) {
+    if (tid == 0) { sh[0].xchg = 0u; sh[1].xchg = 0u; }        // (the draw below synchronises the CTA before anyone reads it)
+    while (state != WF_END) {
         {
-            if (S.state == WF_GRAB) {
-                // ---------------------------------------------------------- next waveform of this slot
-                ++S.seq;
+            if (state == WF_GRAB) {
+                // ---------------------------------------------------------- next waveform of this team
+                ++seq;
                 if (CL) {                                       // CTA 0 of the cluster draws the waveform and posts it to every CTA
                     if (me == 0) {
                         if (tid == 0) s_w = atomicAdd(a.next_wf, 1u);
                         __syncthreads();
-                        if (tid < (int)total) st_cluster_u32(&s_wcl[S.seq & 1u], (unsigned)tid, s_w);
+                        if (tid < (int)total) st_cluster_u32(&s_wcl[seq & 1u], (unsigned)tid, s_w);
                     }
                     cluster_arrive_release();
                     cluster_wait_acquire();
-                    if (tid == 0) s_w = s_wcl[S.seq & 1u];
+                    if (tid == 0) s_w = s_wcl[seq & 1u];
                 } else if (tid == 0) {
                     volatile unsigned long long* mb = a.mail + (size_t)team * 16;
                     unsigned int wn;
                     if (me == 0) {
                         wn = atomicAdd(a.next_wf, 1u);
-                        *mb = ((unsigned long long)S.seq << 32) | (unsigned long long)wn;
+                        *mb = ((unsigned long long)seq << 32) | (unsigned long long)wn;
                     } else {
                         unsigned long long m;
-                        for (;;) { m = *mb; if ((unsigned int)(m >> 32) == S.seq) break; __nanosleep(40); }
+                        for (;;) { m = *mb; if ((unsigned int)(m >> 32) == seq) break; __nanosleep(40); }
                         wn = (unsigned int)m;
                     }
                     s_w = wn;
@@ -328,20 +385,23 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 __syncthreads();
                 const unsigned int w = s_w;
                 __syncthreads();
-                if (w >= (unsigned int)p.batch) { S.state = WF_END; continue; }
-                S.w = w; S.taken = 0;
+                if (w >= (unsigned int)p.batch) { state = WF_END; continue; }
+                xchg = ((const volatile WfShared<R>*)&sh[ver & 1u])->xchg;
 
                 // ---------------------------------------------------------- prologue: first step size, first Kerr
                 // half step (devices.py:1155-1161, 1175-1177), forward column transforms, four-step twiddle
-                C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + pol) * p.n;
-                C v[E];
-#pragma unroll
-                for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * p.n2 + n2);
+                R z0 = 0, h_first;
+                int steps0 = 0;
                 if (a.resume) {
                     const Ctrl cs = p.ctrl[w];
-                    if (cs.done) continue;                      // stays in WF_GRAB: next waveform
-                    S.z = (R)cs.z; S.h = (R)cs.h; S.steps = cs.steps;
-                } else {
+                    if (cs.done) { grab_fence(); continue; }    // stays in WF_GRAB: next waveform
+                    z0 = (R)cs.z; h_first = (R)cs.h; steps0 = cs.steps;
+                }
+                C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + pol) * NN;
+                C v[E];
+#pragma unroll
+                for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + n2);
+                if (!a.resume) {
                     R h0;
                     if (a.fixed) h0 = a.h_fixed;
                     else if (a.single) h0 = p.length;           // no dispersion or no Kerr effect: one step
@@ -355,19 +415,23 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                             pm = pw > pm ? pw : pm;
                         }
                         if (nan) pm = pw_nan<R>();
-                        h0 = p.phi_max / mul_rn(p.abs_gamma, team_max(S, pm));
+                        h0 = p.phi_max / mul_rn(p.abs_gamma, team_max(pm));
                     }
-                    S.h = (p.length < h0) ? p.length : h0;      // python min(h_, length)
-                    S.z = 0; S.steps = 0;
+                    h_first = (p.length < h0) ? p.length : h0;  // python min(h_, length)
                     const int done0 = !((R)0 < p.length) || a.budget <= 0;
                     if (me == 0 && tid == 0) {
                         Ctrl& cs = p.ctrl[w];
-                        cs.z = 0.0; cs.h = (double)S.h; cs.pmax = 0ull; cs.steps = 0; cs.arrived = 0u; cs.done = !((R)0 < p.length);
+                        cs.z = 0.0; cs.h = (double)h_first; cs.pmax = 0ull; cs.steps = 0; cs.arrived = 0u; cs.done = !((R)0 < p.length);
                     }
-                    if (done0) continue;
+                    if (done0) { grab_fence(); continue; }
                 }
+                if (tid == 0) {                                  // (the last readers of this version are two team barriers back)
+                    WfShared<R>& o = sh[(ver ^ 1u) & 1u];
+                    o.w = w; o.xchg = xchg; o.steps = steps0; o.taken = 0; o.z = z0; o.h = h_first;
+                }
+                ver ^= 1u;
                 if (p.has_nl) {
-                    const R hh = S.h / (R)2;                    // h_/2
+                    const R hh = h_first / (R)2;                // h_/2
 #pragma unroll
                     for (int q = 0; q < E; ++q) {
                         const R pw = v[q].x * v[q].x + v[q].y * v[q].y; // |A|^2
@@ -380,26 +444,26 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
                 apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
-                for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
-                bar_arrive(S);
-                S.state = WF_ROW;
+                for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
+                bar_arrive();
+                state = WF_ROW;
                 continue;
             }
 
-            C* __restrict__ rowp = p.field + ((size_t)S.w * p.n_pol + pol) * p.n;
-            if (S.state == WF_ROW) {
+            if (state == WF_ROW) {
                 // ---------------------------------------------------------- row phase (devices.py:1178-1180)
                 WF_T0(t_r0);
-                bar_wait(S);
+                bar_wait();
                 WF_ACC(0, t_r0);
-                C* __restrict__ rbase = rowp + (size_t)k1 * p.n2;
+                const WfShared<R> S = sh_read(ver);
+                C* __restrict__ rbase = p.field + ((size_t)S.w * p.n_pol + pol) * NN + (size_t)k1 * M2;
                 const R h = S.h;
                 C v[E];
 #pragma unroll
                 for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
                 fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
                 {
-                    const R* __restrict__ drow = p.dim_tab + (size_t)k1 * p.n2;   // imag(D~) of my row's bins (k_fill_dim)
+                    const R* __restrict__ drow = p.dim_tab + (size_t)k1 * M2;   // imag(D~) of my row's bins (k_fill_dim)
 #pragma unroll
                     for (int q = 0; q < E; ++q) {
                         const R ph = mul_rn(__ldg(drow + tr + q * (M2 / E)), h);
@@ -410,21 +474,24 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 fft_passes<R, M2, +1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
 #pragma unroll
                 for (int q = 0; q < E; ++q) rbase[tr + q * (M2 / E)] = v[q];
-                bar_arrive(S);
-                S.state = WF_COL;
+                bar_arrive();
+                state = WF_COL;
                 WF_ACC(1, t_r0);
                 continue;
             }
 
             // -------------------------------------------------------------- column phase: end of step s ...
             WF_T0(t_c0);
-            bar_wait(S);
+            bar_wait();
             WF_ACC(2, t_c0);
+            const WfShared<R> S = sh_read(ver);
+            C* __restrict__ rowp = p.field + ((size_t)S.w * p.n_pol + pol) * NN;
             const R z = S.z, h = S.h;
             const int steps = S.steps;
+            xchg = S.xchg;
             C v[E];
 #pragma unroll
-            for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * p.n2 + n2);
+            for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + n2);
             apply_fourstep<true, R, E, M1>(p, v, n2, t);
             fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
             const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h)); // 1/N (exact) and exp(-alpha/2 h) (real part of D~ h)
@@ -442,15 +509,15 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 }
                 if (nan) pm = pw_nan<R>();
                 WF_T0(t_x0);
-                pmax = team_max(S, pm);
+                pmax = team_max(pm);
                 WF_ACC(3, t_x0);
             }
             const CtrlNext<R> nx = controller_next<R>(p, z, h, steps, pmax);
-            ++S.taken;
+            const long long taken = S.taken + 1;
 #ifdef SSFM_WF_PROFILE
             ++pn;
 #endif
-            const bool stop = nx.done || S.taken >= a.budget;
+            const bool stop = nx.done || taken >= a.budget;
             if (me == 0 && tid == 0) {
                 Ctrl& cs = p.ctrl[S.w];
                 if (p.hlog && steps < p.hlog_cap) p.hlog[(size_t)S.w * p.hlog_cap + steps] = (double)h;
@@ -463,13 +530,19 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                         R sn, co; kerr_sincos<SMALL>(st_sm[q * NT + tid], sct, &sn, &co);
                         v[q] = cmul(v[q], mk<R>(co, sn));
                     }
-                    rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
+                    rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
                 }
-                S.state = WF_GRAB;
+                if (tid == 0) sh[ver & 1u].xchg = xchg;         // (adaptive mode: every warp read this version before its exchange)
+                state = WF_GRAB;
                 WF_ACC(4, t_c0);
                 continue;
             }
             // -------------------------------------------------------------- ... and start of step s+1
+            if (tid == 0) {                                     // next version of the state (read after the next team barrier)
+                WfShared<R>& o = sh[(ver ^ 1u) & 1u];
+                o.w = S.w; o.xchg = xchg; o.steps = steps + 1; o.taken = taken; o.z = nx.z; o.h = nx.h;
+            }
+            ver ^= 1u;
             if (p.has_nl) {
                 const R hh = nx.h / (R)2;
 #pragma unroll
@@ -485,15 +558,14 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
             fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
             apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
-            for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * p.n2 + n2] = v[q];
-            S.z = nx.z; S.h = nx.h; S.steps = steps + 1;
-            bar_arrive(S);
-            S.state = WF_ROW;
+            for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
+            bar_arrive();
+            state = WF_ROW;
             WF_ACC(4, t_c0);
         }
     }
 #ifdef SSFM_WF_PROFILE
-    if (tid == 0 && me == 1 && team < 2 && pn > 0)
+    if (tid == 0 && me == 1 && pn > 0)
         printf("[k_wf profile] team %d steps %lld cycles/step: row wait %lld | row phase %lld | col wait %lld | exchange %lld | col phase %lld\n",
                team, pn, prof[0] / pn, (prof[1] - prof[0]) / pn, prof[2] / pn, prof[3] / pn, (prof[4] - prof[2]) / pn);
 #endif
