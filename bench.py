@@ -348,6 +348,43 @@ def main():
     e2e_val = e2e_units / t_e2e
     h2d = int(xh.numel() * 16) * world
     d2h = int(out_h.numel() * csize) * world
+    e2e_ms = t_e2e * 1e3 / a.steps
+
+    # ---- parity of what was just timed (outside the timed region): rows of the e2e output against the oracle ----
+    e2e_parity = None
+    if rank == 0:
+        try:
+            from oracle.ssfm_oracle import oracle_fiber, rel_l2
+            pick = sorted(set([0, 1, 17 % rows, rows - 1]))
+            worst, same_steps = 0.0, True
+            for b in pick:
+                with np.errstate(all="ignore"):
+                    ref = oracle_fiber(xh[b].numpy(), w["dt"], real=np.float64 if a.precision == "fp64" else np.float32, **fiber)
+                worst = max(worst, rel_l2(out_h[b].numpy(), ref["out"]))
+                same_steps &= int(info_h.steps[b]) == int(ref["steps"])
+            e2e_parity = {"rows_checked": pick, "max_rel_l2": worst, "steps_equal": bool(same_steps),
+                          "tolerance": 1e-10 if a.precision == "fp64" else 1e-4,
+                          "against": "oracle/ssfm_oracle.py (restatement of devices.py:1137-1196, pinned to the reference)"}
+        except Exception as e:
+            e2e_parity = {"error": repr(e)}
+    del xh, out_h
+    engine.clear_plans(); torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations (all ranks take part when world > 1) ----
+    extra = {}
+    if not a.no_extra:
+        try:
+            extra = secondary(torch, engine, dev, a) if world == 1 else {}
+        except Exception as e:                                          # secondary numbers never break the line
+            extra = {"error": repr(e)}
+        for name, fn in (("cfg4_receiver_1024x2^18_fp64", extra_cfg4), ("cfg5_2^26_fp64", extra_cfg5)):
+            if name.startswith("cfg5") and world == 1:
+                continue                                                # one GPU: secondary() already ran the 2^26 waveform
+            try:
+                extra[name] = fn(torch, dist, dev, rank, world)
+            except Exception as e:
+                extra[name] = {"error": repr(e)}
+            barrier()
 
     if rank != 0:
         if world > 1:
@@ -409,17 +446,17 @@ def main():
             roofline["traffic"] = t1 * samples_launch
 
     cpu = None
-    extra = {}
-    if not a.no_extra and world == 1:                                   # CPU baseline and secondary numbers: one-GPU runs only
+    if not a.no_extra and world == 1:                                   # CPU baseline: one-GPU runs only
         c = cpu_sample(w, a.precision, a.cpu_seconds)
         cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": "port",
                "sample": "%d of %d rows, oracle port of devices.py:1137-1196 in %s, %d worker processes, %.1f s"
                          % (c["rows"], w["rows"], a.precision, c["cores"], c["seconds"]),
-               "one_core": c["one_core"]}
-        try:
-            extra = secondary(torch, engine, dev, a)
-        except Exception as e:                                          # secondary numbers never break the line
-            extra = {"error": repr(e)}
+               "one_core": c["one_core"], "cupy_path": cupy_note()}
+    for k, v in list(extra.items()):                                    # every extra carries its fraction of the HBM roofline
+        if isinstance(v, dict) and "value" in v and "roofline" not in v:
+            b = v.get("bytes_per_unit", 64 if "fp32" not in k else 32)
+            v["roofline"] = {"bound": "hbm", "achieved": v["value"] / max(1, v.get("n_gpus", 1)) * b / 1e9, "peak": peak, "unit": "GB/s per GPU",
+                             "frac": v["value"] / max(1, v.get("n_gpus", 1)) * b / 1e9 / peak, "bytes_per_unit": b}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -430,9 +467,13 @@ def main():
                    "schedule": a.schedule, "chunk_waveforms": chunk, "l2": "inputs larger than L2 (%.0f MiB per GPU); input restored by an "
                    "untimed device copy before each timed propagation" % (rows * n * csize / 2 ** 20), **fiber},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "exposed_copy_ms": e2e_ms - ms_total / a.steps,
+                "chunks_per_gpu": -(-rows // devices.host_chunk_rows(rows, 1, n, tdtype)),
                 "api": "opticomlib_b200.fiber_batch(pinned host complex128 -> pinned host %s), rows streamed in chunks over %d "
-                       "streams (H2D / propagate / D2H overlapped, one enqueueing host thread)"
+                       "streams (H2D / propagate / D2H overlapped, one enqueueing host thread); exposed_copy_ms = e2e ms per step "
+                       "- device-resident ms per step (the first chunk's H2D and the last chunk's D2H)"
                        % ("complex128" if csize == 16 else "complex64", devices.HOST_LANES)},
+        "e2e_parity": e2e_parity,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -555,6 +596,160 @@ def run_cfg5(a, torch, dist, dev, rank, world, local):
         dist.destroy_process_group()
 
 
+def cupy_note():
+    """The reference's GPU path is CuPy dispatch (devices.py:1114-1119); BASELINE.md section 4 asks for it 'where it installs
+    offline'."""
+    try:
+        import cupy  # noqa: F401
+        return "cupy importable: not timed (the reference's CuPy path is not the optimisation target)"
+    except Exception as e:
+        return "unavailable offline: import cupy fails (%s); no wheel in /opt/wheelhouse, no network" % type(e).__name__
+
+
+def _events(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def extra_cfg4(torch, dist, dev, rank, world):
+    """BASELINE config #4 at full size: 1024 received frames x 2^18 samples (fp64), frames sharded over the ranks, receiver
+    chain BPF(40 GHz) -> 10 x [x 10^(-16/20); DBP 80 km at h = 10 km] -> PD square law + LPF(7.5 GHz), every stage timed with
+    CUDA events on the launching stream after one warm-up pass (max over ranks).  Rooflines: filters against 1 read + 1 write
+    of the complex128 frames (32 B/sample), DBP against 64 B/sample*step."""
+    from opticomlib_b200 import devices, engine, workloads as wl
+    from scipy import signal as sg
+    c4 = wl.CFG4_RX
+    fs = wl.CONFIGS["cfg4"]["R"] * wl.CONFIGS["cfg4"]["sps"]
+    frames_total, n4 = wl.CONFIGS["cfg4"]["rows"], 1 << 18
+    frames = max(1, frames_total // world)
+    base4 = torch.from_numpy(wl.ook_field(15, 4096, 64, 0.0)).to(dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(2000 + rank)
+    rx0 = base4.repeat(frames, 1) * (1 + 0.01 * torch.rand((frames, 1), device=dev, dtype=torch.float64, generator=gen))
+    sos_b = sg.bessel(4, c4["bpf_bw"] / 2, "low", fs=fs, output="sos", norm="mag")
+    sos_l = sg.bessel(4, c4["lpf_bw"], "low", fs=fs, output="sos", norm="mag")
+    y = torch.empty_like(rx0)
+    gain = 10 ** (-c4["span_loss_db"] / 20)
+    best = None
+    for it in range(3):                                               # pass 0 warms plans, tables and the allocator
+        y.copy_(rx0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        engine.filtfilt_sos(y, sos_b, out=y)
+        ev[1].record()
+        nsteps = 0
+        for _ in range(c4["spans"]):
+            y.mul_(gain)
+            _, info = devices.dbp_batch(y, 1.0 / fs, precision="fp64", inplace=True, **c4["dbp"])
+            nsteps += int(info.steps.sum())
+        ev[2].record()
+        z = devices.pd_lpf_batch(y, sos_l, responsivity=1.0)          # |.|^2 fused into the filter's first pass
+        ev[3].record(); ev[3].synchronize()
+        cur = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)] + [nsteps]
+        if it > 0 and (best is None or sum(cur[:3]) < sum(best[:3])):
+            best = cur
+        del z
+    t = torch.tensor(best[:3], dtype=torch.float64, device=dev)
+    u = torch.tensor([float(best[3]) * n4], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    bpf_ms, dbp_ms, lpf_ms = [float(v) for v in t]
+    peak, _ = measured_peaks()
+    samples = frames * n4
+    out = {
+        "frames": frames_total, "frames_per_gpu": frames, "n_gpus": world, "samples_per_frame": n4, "unit": UNIT,
+        "value": float(u[0]) / (dbp_ms * 1e-3), "bytes_per_unit": 64,
+        "stage_ms": {"bpf": bpf_ms, "dbp_10_spans": dbp_ms, "pd_lpf": lpf_ms},
+        "steps_per_frame": best[3] / frames,
+        "roofline_per_stage": {
+            "bpf": {"ideal_bytes": 32 * samples, "achieved_GBps": 32 * samples / (bpf_ms * 1e-3) / 1e9, "frac": 32 * samples / (bpf_ms * 1e-3) / 1e9 / peak},
+            "dbp": {"ideal_bytes_per_sample_step": 64, "achieved_GBps": float(u[0]) / world * 64 / (dbp_ms * 1e-3) / 1e9,
+                    "frac": float(u[0]) / world * 64 / (dbp_ms * 1e-3) / 1e9 / peak},
+            "pd_lpf": {"ideal_bytes": 24 * samples, "achieved_GBps": 24 * samples / (lpf_ms * 1e-3) / 1e9, "frac": 24 * samples / (lpf_ms * 1e-3) / 1e9 / peak,
+                       "note": "ideal = read the complex128 field (16 B) + write the real float64 photocurrent (8 B)"},
+        },
+        "timing": "CUDA events on the launching stream, best of 2 after 1 warm-up pass, max over ranks",
+    }
+    del rx0, y
+    engine.clear_plans(); torch.cuda.empty_cache()
+    return out
+
+
+def extra_cfg5(torch, dist, dev, rank, world):
+    """BASELINE config #5 on the ranks of this run: two 100-km spans (h = 1 km: 100 split steps each) of one 2^26-sample
+    waveform with the exchange fused into the kernels (peer stores over NVLink), the same with the NCCL all-to-all, and -- in
+    this process, on the same distributed code path -- the 2^20-sample parity check against the oracle."""
+    from opticomlib_b200 import longwave as lw, workloads as wl
+    n = 1 << 26
+    c = wl.CONFIGS["cfg5"]
+    fiber = dict(c["fiber"])
+    dt = 1.0 / (c["R"] * c["sps"])
+    group = dist.group.WORLD if world > 1 else None
+    peak, _ = measured_peaks()
+    out = {"samples": n, "n_gpus": world, "unit": UNIT, "bytes_per_unit": 64}
+    for mode in (("fused", True), ("nccl", False)):
+        if world == 1 and mode[0] == "nccl":
+            continue
+        plan = lw.get_long_plan(n, torch.complex128, dev, group, None, mode[1])
+        gen = torch.Generator(device=dev); gen.manual_seed(5 + rank)
+        x0 = torch.view_as_complex(torch.randn((plan.n_outer, plan.cols, 2), dtype=torch.float64, device=dev, generator=gen) * 0.02).contiguous()
+        work = torch.empty_like(x0)
+        spans = 3 if mode[0] == "fused" else 2
+        ms_best, steps = None, 0
+        for it in range(spans):
+            work.copy_(x0)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = _events(torch)
+            e0.record(); info = plan.propagate(work, dt, **fiber); e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            steps = int(info.steps[0])
+            if it > 0:
+                ms_best = ms if ms_best is None else min(ms_best, ms)
+        t = torch.tensor([ms_best], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        rec = {"value": steps * n / (ms * 1e-3), "ms_per_span": ms, "ms_per_split_step": ms / steps, "split_steps": steps,
+               "exchange": ("kernels store into peer memory over NVLink (CUDA IPC), flag barrier between the GPUs" if plan.fused else
+                            "NCCL all_to_all_single + re-layout copy") if world > 1 else "none (one rank)"}
+        if world > 1:
+            link = 2 * 16 * (world - 1) / world                       # bytes per sample*step leaving (and entering) each GPU
+            per_gpu = rec["value"] / world
+            rec["nvlink_roofline"] = {"bytes_per_sample_step_per_direction": link, "achieved_GBps_per_direction": per_gpu * link / 1e9,
+                                      "peak_GBps_per_direction": 900.0, "frac": per_gpu * link / 1e9 / 900.0,
+                                      "peak_source": "NVLink 5 nominal, 900 GB/s per direction per GPU"}
+        rec["hbm_roofline_frac"] = rec["value"] / world * 64 / 1e9 / peak
+        if mode[0] == "fused":
+            out.update(rec)
+        else:
+            out["nccl_exchange"] = rec
+        del x0, work
+        lw.clear_plans(); torch.cuda.empty_cache()
+    # parity of the distributed path at 2^20 samples against the oracle (full length, same code path)
+    try:
+        from oracle.ssfm_oracle import oracle_fiber, rel_l2
+        n20 = 1 << 20
+        rng = np.random.default_rng(9)
+        tt = np.arange(n20) / n20
+        env = np.sqrt(20e-3) * (0.55 + 0.45 * np.sign(np.sin(2 * np.pi * 37 * tt + 0.3)))
+        x = np.convolve(env, np.ones(9) / 9, mode="same") * np.exp(2j * np.pi * 3 * tt) + 1e-4 * (rng.standard_normal(n20) + 1j * rng.standard_normal(n20))
+        kw = dict(length=0.9, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, h=0.3)
+        res, info = lw.fiber_long(x, 1 / 640e9, precision="fp64", group=group, **kw)
+        if rank == 0:
+            with np.errstate(all="ignore"):
+                ref = oracle_fiber(x, 1 / 640e9, real=np.float64, **kw)
+            out["parity_2^20"] = {"rel_l2": rel_l2(res, ref["out"]), "steps_equal": int(info.steps[0]) == int(ref["steps"]), "tolerance": 1e-10,
+                                  "path": "fiber_long over the %d rank(s) of this run, fused exchange, against oracle/ssfm_oracle.py" % world}
+        lw.clear_plans(); torch.cuda.empty_cache()
+    except Exception as e:
+        out["parity_2^20"] = {"error": repr(e)}
+    return out
+
+
 def secondary(torch, engine, dev, a):
     """Other single-GPU numbers reported next to the headline (not bench lines of their own)."""
     from opticomlib_b200 import workloads as wl
@@ -648,36 +843,6 @@ def secondary(torch, engine, dev, a):
         lw.clear_plans(); torch.cuda.empty_cache()
     except Exception as e:
         out["cfg5_2^26_fp64_1gpu_20steps"] = {"error": repr(e)}
-    # BASELINE config #4 receiver on 256 of its 1024 frames x 2^18: BPF -> 10 x [gain; DBP 80 km, h = 10] -> |.|^2 -> LPF
-    try:
-        from opticomlib_b200 import devices
-        from scipy import signal as sg
-        c4 = wl.CFG4_RX
-        fs = wl.CONFIGS["cfg4"]["R"] * wl.CONFIGS["cfg4"]["sps"]
-        frames, n4 = 256, 1 << 18
-        base4 = torch.from_numpy(wl.ook_field(15, 4096, 64, 0.0)).to(dev)
-        rx = base4.repeat(frames, 1) * (1 + 0.01 * torch.rand((frames, 1), device=dev, dtype=torch.float64))
-        sos_b = sg.bessel(4, c4["bpf_bw"] / 2, "low", fs=fs, output="sos", norm="mag")
-        sos_l = sg.bessel(4, c4["lpf_bw"], "low", fs=fs, output="sos", norm="mag")
-        best = None
-        for i in range(2):
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            y = devices.filtfilt_batch(rx, sos_b)
-            t1 = time.perf_counter(); nsteps = 0
-            for _ in range(c4["spans"]):
-                y, info = devices.dbp_batch(y * 10 ** (-c4["span_loss_db"] / 20), 1.0 / fs, precision="fp64", inplace=True, **c4["dbp"])
-                nsteps += int(info.steps.sum())
-            torch.cuda.synchronize(); t2 = time.perf_counter()
-            pw = (y.abs() ** 2).to(torch.complex128)
-            z = devices.filtfilt_batch(pw, sos_l)
-            torch.cuda.synchronize(); t3 = time.perf_counter()
-            cur = (t1 - t0, t2 - t1, t3 - t2, nsteps)
-            best = cur if best is None or sum(cur[:3]) < sum(best[:3]) else best
-        out["cfg4_receiver_fp64_256frames"] = {
-            "dbp_value": best[3] * n4 / best[1], "unit": UNIT, "dbp_ms": best[1] * 1e3,
-            "bpf_ms": best[0] * 1e3, "lpf_ms": best[2] * 1e3, "steps_per_frame": best[3] / frames}
-    except Exception as e:
-        out["cfg4_receiver_fp64_256frames"] = {"error": repr(e)}
     return out
 
 

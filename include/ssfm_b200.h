@@ -80,6 +80,9 @@ SSFM_API int ssfm_plan_destroy(ssfm_plan_t plan);
  * "chunk_waveforms" (multi-launch schedule: waveforms propagated together, 0 = all), "burst_steps",
  * "fused" (multi-launch schedule: 0 three kernels per step, 1..3 two kernels per step). */
 SSFM_API int ssfm_plan_set_option(ssfm_plan_t plan, const char* name, int64_t value);
+/* Read a tunable back, or one of the read-only properties "hlog_cap" (entries per waveform of the step-size log),
+ * "n1", "n2" (the two-pass split of the transform). */
+SSFM_API int ssfm_plan_get_option(ssfm_plan_t plan, const char* name, int64_t* value);
 
 /* FIBER hot loop, devices.py:1155-1196, in place on field_dev[n_waveforms][n_pol][n_samples].
  * DBP (devices.py:1280-1283) is the same call with alpha, beta_2, beta_3, gamma negated by the caller.
@@ -100,6 +103,10 @@ SSFM_API int ssfm_get_state(ssfm_plan_t plan, int32_t* steps_host, double* z_hos
  * the raw per-waveform controller records to (pinned) host memory on the same stream: n_waveforms records of 40 bytes
  * { double z; double h_next; uint64 scratch; int32 steps; int32 done; uint32 scratch; int32 pad }. */
 SSFM_API int ssfm_copy_state_async(ssfm_plan_t plan, void* records_host, void* stream);
+/* Progress of one waveform WHILE an asynchronous ssfm_propagate (option "async") is running: the controller record of
+ * `row` is copied on a stream of its own (it does not wait for the propagation).  The reference updates a tqdm bar after
+ * every step (devices.py:1164-1170, 1188-1191); this is the device-side counter such a bar polls. */
+SSFM_API int ssfm_peek_state(ssfm_plan_t plan, int64_t row, int32_t* steps_host, double* z_host, int32_t* done_host);
 /* Schedule used by the last ssfm_propagate on this plan: *kind = 1 multi-launch, 2 persistent kernel
  * (then *teams = waveforms in flight and *kernel_ms = device time of that one launch, CUDA events on the
  * launching stream).  Any pointer may be NULL.  Measurement hook for bench.py's roofline object. */
@@ -166,6 +173,44 @@ SSFM_API int ssfm_long_xbar(ssfm_plan_t plan, void* stream);
  * Real signals are passed as complex with zero imaginary part, or two real rows packed as re/im. */
 SSFM_API int ssfm_filtfilt_sos(void* x_dev, void* y_dev, int64_t n_rows, int64_t n_samples,
                       const double* sos_host, int32_t n_sections, int32_t device, void* stream);
+
+/* Photodetector front end + zero-phase low-pass + sampler in one call (reference PD, devices.py:1514-1552, whose last
+ * statement is LPF(output, BW), devices.py:1363-1368; SAMPLER, devices.py:1871-1891, output[instant :: sps]).
+ *   signal:  R_load * r * sum_pol |E|^2                                      -> out_signal_dev[n_rows][m]   (float64)
+ *   noise:   R_load * (r * sum_pol (2 Re(E n*) + |n|^2) + extra + i_dark)    -> out_noise_dev[n_rows][m]    (float64, optional)
+ * both filtered separately by the zero-phase cascade `sos_host` (as the reference filters signal and noise separately)
+ * and sampled at sample_offset + j * sample_stride, j < m = ceil((n_samples - sample_offset) / sample_stride)
+ * (offset 0, stride 1: every sample).  field_dev / noise_dev: complex128 [n_rows][n_pol][n_samples] (noise_dev may be
+ * null); extra_noise_dev: float64 [n_rows][n_samples] additive noise CURRENT (thermal + shot; may be null -- see
+ * ssfm_gaussian_noise).  out_noise_dev may be null when there is no noise input; i_dark is then ignored, as in the
+ * reference's include_noise='none'. */
+SSFM_API int ssfm_pd_lpf(const void* field_dev, const void* noise_dev, const double* extra_noise_dev, double* out_signal_dev,
+                double* out_noise_dev, int64_t n_rows, int32_t n_pol, int64_t n_samples, double responsivity, double r_load,
+                double i_dark, const double* sos_host, int32_t n_sections, int64_t sample_offset, int64_t sample_stride,
+                int32_t device, void* stream);
+
+/* out_dev[i] = mean + sigma * N(0,1), i < count: Philox4x32-10 + Box-Muller, a pure function of (seed, substream, i).
+ * Stands in for the np.random.normal / randn draws of EDFA (devices.py:933) and PD (devices.py:1523, 1527), which come from
+ * NumPy's global stream and cannot be reproduced bit for bit on a device. */
+SSFM_API int ssfm_gaussian_noise(double* out_dev, int64_t count, double mean, double sigma, uint64_t seed, uint32_t substream,
+                        int32_t device, void* stream);
+
+/* EDFA gain and ASE on the device (reference EDFA, devices.py:921-936, without its optional BPF -- call ssfm_filtfilt_sos):
+ *   out[row][pol][i] = sqrt(10^(gain_db/10)) * in[row][pol][i] + sqrt(p_ase_w/4) * (n1 + j n2),  n1, n2 ~ N(0,1) (Philox)
+ * in_dev: complex128 [in_rows][in_pol][n_samples] with in_rows == n_rows, or in_rows == 1 to amplify ONE waveform into n_rows
+ * independent noise realisations (the Monte-Carlo batch of BASELINE config #3 without any host->device copy);
+ * out_dev: complex128 [n_rows][out_pol][n_samples], out_pol >= in_pol (the reference always returns two polarisations: a
+ * polarisation the input does not have carries ASE only).  p_ase_w = idb(NF) h f0 (idb(G) - 1) fs (devices.py:930). */
+SSFM_API int ssfm_edfa(const void* in_dev, void* out_dev, int64_t n_rows, int64_t in_rows, int32_t in_pol, int32_t out_pol,
+              int64_t n_samples, double gain_db, double p_ase_w, uint64_t seed, int32_t device, void* stream);
+
+/* Welch power spectral density of every row, as the reference computes it for `signal.psd()` (typing.py:1899-1902) and
+ * `utils.get_psd` (utils.py:2074-2079): scipy.signal.welch(x, nperseg, scaling='spectrum', return_onesided=False,
+ * detrend=False) -- periodic Hann window, 50 % overlap, mean over the segments -- followed by fftshift of the bins.
+ * x_dev: complex128 [n_rows][n_samples]; psd_dev: float64 [n_rows][nperseg] (bin order of fftshift(fftfreq(nperseg)));
+ * nperseg in {256, 512, 1024, 2048} (the reference uses min(2048, n_samples)). */
+SSFM_API int ssfm_welch_psd(const void* x_dev, double* psd_dev, int64_t n_rows, int64_t n_samples, int32_t nperseg,
+                   int32_t device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,9 @@ PROTOTYPES = {
                                         ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     "ssfm_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "ssfm_plan_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "ssfm_plan_get_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]),
+    "ssfm_peek_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(ctypes.c_int32)]),
     "ssfm_propagate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(FiberParams),
                                       ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]),
     "ssfm_get_state": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -60,6 +63,16 @@ PROTOTYPES = {
     "ssfm_long_xbar": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "ssfm_filtfilt_sos": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+    "ssfm_pd_lpf": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_double, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                   ctypes.c_int32, ctypes.c_void_p]),
+    "ssfm_gaussian_noise": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_uint64,
+                                           ctypes.c_uint32, ctypes.c_int32, ctypes.c_void_p]),
+    "ssfm_welch_psd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_void_p]),
+    "ssfm_edfa": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                 ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int32, ctypes.c_void_p]),
 }
 
 _lib = None

@@ -7,14 +7,24 @@
 // Two device paths, both exact to rounding (no CPU path):
 //   * FFT path (rows of 2^8..2^22 samples): the forward-backward cascade is a linear filter with
 //     the real, zero-phase response |H(e^{jw})|^2.  Away from the ends its output equals the circular
-//     convolution  IFFT(|H|^2 FFT(x))  (computed with the SSFM transform kernels, 3 kernels, all rows
-//     in parallel); the deviation comes from the start-up transients of the two recursions and decays
-//     like rho^n (rho = largest pole radius).  The first and last K samples (rho^K < 1e-19) are then
-//     recomputed exactly with the recursion itself on a short segment (k_filtfilt_edges).
+//     convolution  IFFT(|H|^2 FFT(x))  (computed with the SSFM transform kernels); the deviation comes from
+//     the start-up transients of the two recursions and decays like rho^n (rho = largest pole radius).
+//     The first and last K samples (rho^K < 1e-19) are then recomputed exactly with the recursion itself on
+//     a short segment (k_filtfilt_edges).
+//     Schedule (round 2): the rows are cut into chunks of <= 32 MiB and the three transform kernels (plus
+//     the optional pack / unpack stages of the photodetector path) run back to back on one chunk, so the
+//     chunk stays in the 126 MB L2 between them: HBM sees ONE read of the input and ONE write of the
+//     output (round 1 streamed every row through HBM four times).  The end segments of ALL rows are saved
+//     first and their recursions run on a side stream while the chunks go through (one launch, one wave of
+//     threads, latency-bound: ~0.4 ms that used to sit on the critical path); a last small kernel writes
+//     the exact end samples over the circular ones.
 //   * sequential path (any other length, or K too large for the row): one thread per
 //     (row, real|imag) walks the whole recursion, same operation order as the SciPy loop.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../include/ssfm_b200.h"
@@ -78,45 +88,6 @@ __global__ void k_save_edges(const double2* __restrict__ x, double2* __restrict_
     seg[i] = x[row * n + (side ? n - L + j : j)];
 }
 
-// ---- FFT path, step 3: exact recursion on the two end segments, overwrite the first / last K outputs.
-// One thread per (row, side, component).  Head: exact forward pass from the true start (odd extension,
-// zi*ext[0]); the backward pass starts at the cut with the steady-state guess, whose error has decayed
-// by rho^(L-K) when it reaches sample K.  Tail: mirror image (approximate forward start at the cut, exact
-// odd extension and backward pass from the true end).
-__global__ void k_filtfilt_edges(const double* __restrict__ seg, double* __restrict__ y, double* __restrict__ ws,
-                                 long long rows, long long n, int L, int K, Sos f) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= rows * 4) return;
-    const long long row = tid >> 2;
-    const int side = (int)((tid >> 1) & 1), comp = (int)(tid & 1);
-    const double* s = seg + ((row * 2 + side) * (long long)L) * 2 + comp;   // s[2*i]: sample i of the segment
-    const int E = f.edge, len = L + E;
-    double* w = ws + tid * (long long)len;
-    double* yr = y + row * n * 2 + comp;
-    double z[MAX_SECTIONS][2];
-    if (side == 0) {
-        const double x0 = s[0];
-        init_state(f, 2.0 * x0 - s[2 * E], z);                                  // ext[0] = 2 x[0] - x[edge]
-        for (int i = 0; i < E; ++i) w[i] = cascade(f, 2.0 * x0 - s[2 * (E - i)], z);
-        for (int i = 0; i < L; ++i) w[E + i] = cascade(f, s[2 * i], z);
-        init_state(f, w[len - 1], z);
-        for (int i = len - 1; i >= E; --i) {
-            const double v = cascade(f, w[i], z);
-            if (i - E < K) yr[2 * (long long)(i - E)] = v;
-        }
-    } else {
-        const double xl = s[2 * (L - 1)];
-        init_state(f, s[0], z);
-        for (int i = 0; i < L; ++i) w[i] = cascade(f, s[2 * i], z);
-        for (int m = 0; m < E; ++m) w[L + m] = cascade(f, 2.0 * xl - s[2 * (L - 2 - m)], z);
-        init_state(f, w[len - 1], z);
-        for (int i = len - 1; i >= L - K; --i) {
-            const double v = cascade(f, w[i], z);
-            if (i < L) yr[2 * (n - L + i)] = v;
-        }
-    }
-}
-
 int make_sos(Sos& f, const double* sos, int S, double* rho_out, std::string& err) {
     if (S < 1 || S > MAX_SECTIONS) { err = "n_sections must be in [1, 8]"; return SSFM_ERR_INVALID; }
     std::memset(&f, 0, sizeof(f));
@@ -144,66 +115,383 @@ int make_sos(Sos& f, const double* sos, int S, double* rho_out, std::string& err
     return SSFM_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Photodetector front end fused in front of the filter (reference PD, devices.py:1514-1552, followed by LPF 1363-1368)
+// and sampler behind it (SAMPLER, devices.py:1871-1891: output[instant :: sps]).
+//   signal current  i_sig  = r sum_pol |E|^2                                  (devices.py:1514-1517)
+//   noise current   i_n    = r sum_pol (2 Re(E n*) + |n|^2) + extra + i_dark  (typing.py:1341-1342 product rule; 1530-1545)
+// packed as (re, im) = R_load (i_sig, i_n) of ONE complex row, so that one transform filters both separately, as the
+// reference does (devices.py:1365-1368).
+struct PdSrc {
+    const double2* field;     // [rows][n_pol][n]
+    const double2* noise;     // same shape or null
+    const double* extra;      // [rows][n] additive noise current (thermal + shot) or null
+    double r, r_load, i_dark;
+    int n_pol;
+    int noise_out;            // 1: a noise row is produced (im part), 0: im = 0
+};
+__device__ __forceinline__ double2 pd_sample(const PdSrc& s, long long row, long long n, long long i) {
+    double sig = 0.0, noi = 0.0;
+    for (int p = 0; p < s.n_pol; ++p) {
+        const double2 e = s.field[(row * s.n_pol + p) * n + i];
+        sig += e.x * e.x + e.y * e.y;
+        if (s.noise) {
+            const double2 z = s.noise[(row * s.n_pol + p) * n + i];
+            noi += 2.0 * (e.x * z.x + e.y * z.y) + (z.x * z.x + z.y * z.y);
+        }
+    }
+    double2 o;
+    o.x = s.r_load * (s.r * sig);
+    o.y = s.noise_out ? s.r_load * (s.r * noi + (s.extra ? s.extra[row * n + i] : 0.0) + s.i_dark) : 0.0;
+    return o;
+}
+__global__ void k_pd_pack(PdSrc s, double2* __restrict__ dst, long long row0, long long rows, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * n) return;
+    dst[i] = pd_sample(s, row0 + i / n, n, i % n);
+}
+// end segments of the PACKED rows straight from the optical field (so that they can be saved before any chunk is packed)
+__global__ void k_pd_save_edges(PdSrc s, double2* __restrict__ seg, long long rows, long long n, int L) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 2 * L) return;
+    const long long row = i / (2 * L);
+    const int side = (int)((i / L) & 1), j = (int)(i % L);
+    seg[i] = pd_sample(s, row, n, side ? n - L + j : j);
+}
+// filtered packed rows -> real outputs, decimated: out[row][j] = re/im of y[row][offset + j*stride]
+__global__ void k_unpack_real(const double2* __restrict__ y, double* __restrict__ out_sig, double* __restrict__ out_noise,
+                              long long row0, long long rows, long long n, long long offset, long long stride, long long m) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * m) return;
+    const long long row = i / m, j = i % m;
+    const double2 v = y[row * n + offset + j * stride];
+    out_sig[(row0 + row) * m + j] = v.x;
+    if (out_noise) out_noise[(row0 + row) * m + j] = v.y;
+}
+
+// ---- FFT path: exact recursion on the two end segments of every row, results into edge_out[rows][2][K] (complex).
+// One thread per (row, side, component).  Head: exact forward pass from the true start (odd extension,
+// zi*ext[0]); the backward pass starts at the cut with the steady-state guess, whose error has decayed
+// by rho^(L-K) when it reaches sample K.  Tail: mirror image (approximate forward start at the cut, exact
+// odd extension and backward pass from the true end).
+__global__ void k_filtfilt_edges_out(const double* __restrict__ seg, double* __restrict__ edge_out, double* __restrict__ ws,
+                                     long long rows, int L, int K, Sos f) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= rows * 4) return;
+    const long long row = tid >> 2;
+    const int side = (int)((tid >> 1) & 1), comp = (int)(tid & 1);
+    const double* s = seg + ((row * 2 + side) * (long long)L) * 2 + comp;   // s[2*i]: sample i of the segment
+    const int E = f.edge, len = L + E;
+    double* w = ws + tid * (long long)len;
+    double* o = edge_out + ((row * 2 + side) * (long long)K) * 2 + comp;    // o[2*i]: output sample i of this end
+    double z[MAX_SECTIONS][2];
+    if (side == 0) {
+        const double x0 = s[0];
+        init_state(f, 2.0 * x0 - s[2 * E], z);                                  // ext[0] = 2 x[0] - x[edge]
+        for (int i = 0; i < E; ++i) w[i] = cascade(f, 2.0 * x0 - s[2 * (E - i)], z);
+        for (int i = 0; i < L; ++i) w[E + i] = cascade(f, s[2 * i], z);
+        init_state(f, w[len - 1], z);
+        for (int i = len - 1; i >= E; --i) {
+            const double v = cascade(f, w[i], z);
+            if (i - E < K) o[2 * (i - E)] = v;                                  // sample i - E of the row
+        }
+    } else {
+        const double xl = s[2 * (L - 1)];
+        init_state(f, s[0], z);
+        for (int i = 0; i < L; ++i) w[i] = cascade(f, s[2 * i], z);
+        for (int m = 0; m < E; ++m) w[L + m] = cascade(f, 2.0 * xl - s[2 * (L - 2 - m)], z);
+        init_state(f, w[len - 1], z);
+        for (int i = len - 1; i >= L - K; --i) {
+            const double v = cascade(f, w[i], z);
+            if (i < L) o[2 * (i - (L - K))] = v;                                // sample n - K + (i - (L - K)) of the row
+        }
+    }
+}
+// exact end samples over the circular ones: complex output rows, or the decimated real outputs of the photodetector path
+__global__ void k_scatter_edges(const double2* __restrict__ edge_out, double2* __restrict__ y, double* __restrict__ out_sig,
+                                double* __restrict__ out_noise, long long rows, long long n, int K, long long offset,
+                                long long stride, long long m) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 2 * K) return;
+    const long long row = i / (2 * K);
+    const int side = (int)((i / K) & 1), j = (int)(i % K);
+    const long long pos = side ? n - K + j : j;
+    const double2 v = edge_out[i];
+    if (y) { y[row * n + pos] = v; return; }
+    if (pos < offset || (pos - offset) % stride) return;
+    const long long jj = (pos - offset) / stride;
+    if (jj >= m) return;
+    out_sig[row * m + jj] = v.x;
+    if (out_noise) out_noise[row * m + jj] = v.y;
+}
+
+// Philox4x32-10 counter-based generator + Box-Muller: N(0, 1) doubles, reproducible from (seed, element index) alone,
+// whatever the launch geometry (the reference draws its noise from NumPy's global stream: devices.py:933, 1523, 1527 --
+// a device-side generator can only be validated statistically).
+__device__ __forceinline__ void philox4x32_10(unsigned int (&c)[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c[0], p1 = (unsigned long long)0xCD9E8D57u * c[2];
+        const unsigned int n0 = (unsigned int)(p1 >> 32) ^ c[1] ^ k0, n1 = (unsigned int)p1;
+        const unsigned int n2 = (unsigned int)(p0 >> 32) ^ c[3] ^ k1, n3 = (unsigned int)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// two independent N(0,1) values for counter `idx` of stream (seed, sub)
+__device__ __forceinline__ double2 philox_normal2(unsigned long long seed, unsigned int sub, unsigned long long idx) {
+    unsigned int c[4] = {(unsigned int)idx, (unsigned int)(idx >> 32), sub, 0u};
+    philox4x32_10(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+    const unsigned long long a = ((unsigned long long)c[0] << 32) | c[1], b = ((unsigned long long)c[2] << 32) | c[3];
+    const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);     // (0, 1)
+    const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    double2 o; o.x = rad * cs; o.y = rad * sn;
+    return o;
+}
+// out[i] = mean + sigma * N(0,1), i < count (real doubles; pairs share one Philox call)
+__global__ void k_gaussian(double* __restrict__ out, long long count, double mean, double sigma, unsigned long long seed, unsigned int sub) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * i >= count) return;
+    const double2 g = philox_normal2(seed, sub, (unsigned long long)i);
+    out[2 * i] = mean + sigma * g.x;
+    if (2 * i + 1 < count) out[2 * i + 1] = mean + sigma * g.y;
+}
+// EDFA: out[row][pol][i] = sqrt(G) in[row or 0][pol][i] + sigma (n1 + j n2)   (devices.py:921-936; y polarisation of a
+// one-polarisation input is zero signal + ASE).  in_rows = 1 broadcasts one input waveform to every realisation.
+__global__ void k_edfa(const double2* __restrict__ in, double2* __restrict__ out, long long rows, long long in_rows, int in_pol,
+                       int out_pol, long long n, double g_amp, double sigma, unsigned long long seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * out_pol * n) return;
+    const long long row = i / (out_pol * n);
+    const int pol = (int)((i / n) % out_pol);
+    const long long k = i % n;
+    double2 e; e.x = 0.0; e.y = 0.0;
+    if (pol < in_pol) { const double2 a = in[((in_rows == 1 ? 0 : row) * in_pol + pol) * n + k]; e.x = g_amp * a.x; e.y = g_amp * a.y; }
+    const double2 g = philox_normal2(seed, 0x45444641u, (unsigned long long)i);
+    e.x += sigma * g.x; e.y += sigma * g.y;
+    out[i] = e;
+}
+
 }  // namespace ssfm_filt
 
-extern "C" int ssfm_filtfilt_sos(void* x_dev, void* y_dev, int64_t n_rows, int64_t n, const double* sos_host,
-                                 int32_t n_sections, int32_t device, void* stream) {
-    using namespace ssfm_filt;
-    std::string err;
-    if (!x_dev || !y_dev || !sos_host) { ssfm_err_slot = "null buffer or sos"; return SSFM_ERR_INVALID; }
-    if (n_rows < 1 || n < 1) { ssfm_err_slot = "n_rows and n_samples must be >= 1"; return SSFM_ERR_INVALID; }
-    Sos f;
-    double rho = 0;
-    int rc = make_sos(f, sos_host, n_sections, &rho, err);
-    if (rc) { ssfm_err_slot = err; return rc; }
-    if (n <= f.edge) {
-        ssfm_err_slot = "The length of the input vector x must be greater than padlen, which is " + std::to_string(f.edge) + ".";
-        return SSFM_ERR_INVALID;
-    }
-    cudaError_t e = cudaSetDevice(device);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (e != cudaSuccess) { ssfm_err_slot = std::string("filtfilt: ") + cudaGetErrorString(e); return SSFM_ERR_CUDA; }
+namespace {
 
+using namespace ssfm_filt;
+
+void pool_keeps_memory(int device) {                 // stream-ordered workspaces: do not give the memory back at every sync
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+SideStream& side_of(int device) {
+    static SideStream s[64];
+    SideStream& x = s[(device >= 0 && device < 64) ? device : 0];
+    if (!x.st) {
+        cudaStreamCreateWithFlags(&x.st, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
+    }
+    return x;
+}
+
+// One chunk of rows stays L2-resident across the passes over it: 24 ... 40 MiB, and within that range the row count whose
+// transform launches (n / 4096 CTAs per row, two 256-thread CTAs per SM) come closest to whole waves of CTAs -- a launch of
+// 1.7 waves leaves the chip 15 % idle, and every chunk pays that three times.
+long long chunk_rows(long long rows, long long n, int device) {
+    const size_t row_bytes = 16 * (size_t)n;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const double slots = 2.0 * sms, per_row = (double)std::max<long long>(1, n / 4096);
+    const long long lo = std::max<long long>(1, (long long)((24u << 20) / row_bytes)), hi = std::max<long long>(lo, (long long)((40u << 20) / row_bytes));
+    long long best = lo;
+    double best_eff = 0.0;
+    for (long long r = lo; r <= hi; ++r) {
+        const double w = r * per_row / slots, eff = w / std::ceil(w);
+        if (eff >= best_eff - 1e-12) { best_eff = std::max(best_eff, eff); best = r; }
+    }
+    return std::max<long long>(1, std::min(rows, best));
+}
+
+// The whole zero-phase filter of `rows` rows of n samples.  Source: complex rows x (pd == null) or the photodetector
+// front end *pd; destination: complex rows y (may alias x), or -- out_sig != null -- real rows out_sig / out_noise
+// holding samples offset, offset + stride, ... (m per row).  `y` is then a scratch buffer of >= chunk rows.
+int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, double2* y, double* out_sig, double* out_noise,
+               long long rows, long long n, long long offset, long long stride, long long m, int device, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    int rc = SSFM_OK;
+    pool_keeps_memory(device);
     // transient length: rho^K < 1e-19, with head-room for the polynomial factors of clustered Bessel poles
     long long K = -1;
     if (rho > 0 && rho < 1) K = (long long)std::ceil(1.3 * std::log(1e-19) / std::log(rho)) + 64;
     else if (rho == 0) K = 64;
     const bool pow2 = (n & (n - 1)) == 0 && n >= 256 && n <= (1ll << 22);
     const bool fft_path = pow2 && K > 0 && 4 * K + 2 * f.edge <= n && !getenv("SSFM_FILTFILT_SEQUENTIAL");
+    const bool real_out = out_sig != nullptr;
+    const long long chunk = fft_path ? chunk_rows(rows, n, device) : rows;
 
     double* ws = nullptr;
-    double2* seg = nullptr;
+    double2 *seg = nullptr, *edge_out = nullptr, *scratch = nullptr;
+    auto cleanup = [&]() {
+        if (ws) cudaFreeAsync(ws, st);
+        if (seg) cudaFreeAsync(seg, st);
+        if (edge_out) cudaFreeAsync(edge_out, st);
+        if (scratch) cudaFreeAsync(scratch, st);
+    };
+    auto cuda_fail = [&](cudaError_t err) { cleanup(); ssfm_err_slot = std::string("filtfilt: ") + cudaGetErrorString(err); return SSFM_ERR_CUDA; };
+
+    if (real_out || (!fft_path && pd)) {               // packed rows live in a scratch buffer (one chunk; all rows on the sequential path)
+        e = cudaMallocAsync((void**)&scratch, sizeof(double2) * (size_t)chunk * n, st);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
     if (fft_path) {
         const int L = (int)(2 * K), Ki = (int)K;
-        e = cudaMallocAsync((void**)&seg, sizeof(double2) * (size_t)n_rows * 2 * L, st);
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)n_rows * 4 * (L + f.edge), st);
-        if (e == cudaSuccess) {
-            const long long cnt = n_rows * 2 * L;
-            k_save_edges<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>((const double2*)x_dev, seg, n_rows, n, L);
-            if (y_dev != x_dev) e = cudaMemcpyAsync(y_dev, x_dev, sizeof(double2) * (size_t)n_rows * n, cudaMemcpyDeviceToDevice, st);
+        static std::mutex enqueue_mu;                  // the side stream and its two events are shared by the callers of a device
+        std::lock_guard<std::mutex> lock(enqueue_mu);
+        SideStream& sd = side_of(device);
+        e = cudaMallocAsync((void**)&seg, sizeof(double2) * (size_t)rows * 2 * L, st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&edge_out, sizeof(double2) * (size_t)rows * 2 * Ki, st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&ws, sizeof(double) * (size_t)rows * 4 * (L + f.edge), st);
+        if (e != cudaSuccess) return cuda_fail(e);
+        {   // end segments of every row, then their recursions on the side stream while the chunks go through
+            const long long cnt = rows * 2 * L;
+            if (pd) k_pd_save_edges<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(*pd, seg, rows, n, L);
+            else k_save_edges<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(x, seg, rows, n, L);
+            cudaEventRecord(sd.fork, st);
+            cudaStreamWaitEvent(sd.st, sd.fork, 0);
+            const long long threads = rows * 4;
+            k_filtfilt_edges_out<<<(unsigned)((threads + 63) / 64), 64, 0, sd.st>>>((const double*)seg, (double*)edge_out, ws, rows, L, Ki, f);
+            cudaEventRecord(sd.join, sd.st);
         }
-        if (e == cudaSuccess) {
-            rc = ssfm_internal_zero_phase_circular(device, n, n_rows, f, y_dev, st);
-            if (!rc) {
-                const long long threads = n_rows * 4;
-                k_filtfilt_edges<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>((const double*)seg, (double*)y_dev, ws,
-                                                                              n_rows, n, L, Ki, f);
-                e = cudaGetLastError();
-            }
+        void* plan = nullptr;
+        rc = ssfm_internal_transfer_prepare(device, n, chunk, f, &plan, st);
+        for (long long r0 = 0; r0 < rows && !rc; r0 += chunk) {
+            const long long nr = std::min(chunk, rows - r0);
+            double2* buf = real_out ? scratch : y + (size_t)r0 * n;
+            if (pd) k_pd_pack<<<(unsigned)((nr * n + 255) / 256), 256, 0, st>>>(*pd, buf, r0, nr, n);
+            else if (buf != x + (size_t)r0 * n) e = cudaMemcpyAsync(buf, x + (size_t)r0 * n, sizeof(double2) * (size_t)nr * n, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return cuda_fail(e);
+            rc = ssfm_internal_transfer_apply(plan, buf, nr, st);
+            if (!rc && real_out)
+                k_unpack_real<<<(unsigned)((nr * m + 255) / 256), 256, 0, st>>>(buf, out_sig, out_noise, r0, nr, n, offset, stride, m);
+        }
+        cudaStreamWaitEvent(st, sd.join, 0);             // (also on the error path: the workspaces are freed on `st`)
+        if (!rc) {
+            const long long cnt = rows * 2 * Ki;
+            k_scatter_edges<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(edge_out, real_out ? nullptr : y, out_sig, out_noise, rows, n, Ki,
+                                                                        offset, stride, m);
+            e = cudaGetLastError();
         }
     } else {
         const size_t len = (size_t)n + 2 * (size_t)f.edge;
-        e = cudaMallocAsync((void**)&ws, sizeof(double) * len * (size_t)n_rows * 2, st);
-        if (e == cudaSuccess) {
-            const long long threads = n_rows * 2;
-            k_filtfilt_seq<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>((const double*)x_dev, (double*)y_dev, ws, n_rows, n, f);
-            e = cudaGetLastError();
-        }
+        e = cudaMallocAsync((void**)&ws, sizeof(double) * len * (size_t)rows * 2, st);
+        if (e != cudaSuccess) return cuda_fail(e);
+        const double2* src = x;
+        if (pd) { k_pd_pack<<<(unsigned)((rows * n + 255) / 256), 256, 0, st>>>(*pd, scratch, 0, rows, n); src = scratch; }
+        double2* dst = real_out ? scratch : y;
+        if (real_out && !pd) { cleanup(); ssfm_err_slot = "filtfilt: real outputs need the photodetector front end"; return SSFM_ERR_INVALID; }
+        const long long threads = rows * 2;
+        k_filtfilt_seq<<<(unsigned)((threads + 63) / 64), 64, 0, st>>>((const double*)src, (double*)dst, ws, rows, n, f);
+        if (real_out) k_unpack_real<<<(unsigned)((rows * m + 255) / 256), 256, 0, st>>>(dst, out_sig, out_noise, 0, rows, n, offset, stride, m);
+        e = cudaGetLastError();
     }
-    if (ws) cudaFreeAsync(ws, st);
-    if (seg) cudaFreeAsync(seg, st);
+    cleanup();
     if (rc) return rc;
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { ssfm_err_slot = std::string("filtfilt: ") + cudaGetErrorString(e); return SSFM_ERR_CUDA; }
+    return SSFM_OK;
+}
+
+int parse_filter(Sos& f, double* rho, const double* sos_host, int n_sections, long long n) {
+    std::string err;
+    if (!sos_host) { ssfm_err_slot = "null sos"; return SSFM_ERR_INVALID; }
+    int rc = make_sos(f, sos_host, n_sections, rho, err);
+    if (rc) { ssfm_err_slot = err; return rc; }
+    if (n <= f.edge) {
+        ssfm_err_slot = "The length of the input vector x must be greater than padlen, which is " + std::to_string(f.edge) + ".";
+        return SSFM_ERR_INVALID;
+    }
+    return SSFM_OK;
+}
+
+}  // namespace
+
+extern "C" int ssfm_filtfilt_sos(void* x_dev, void* y_dev, int64_t n_rows, int64_t n, const double* sos_host,
+                                 int32_t n_sections, int32_t device, void* stream) {
+    if (!x_dev || !y_dev || !sos_host) { ssfm_err_slot = "null buffer or sos"; return SSFM_ERR_INVALID; }
+    if (n_rows < 1 || n < 1) { ssfm_err_slot = "n_rows and n_samples must be >= 1"; return SSFM_ERR_INVALID; }
+    Sos f;
+    double rho = 0;
+    int rc = parse_filter(f, &rho, sos_host, n_sections, n);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { ssfm_err_slot = std::string("filtfilt: ") + cudaGetErrorString(e); return SSFM_ERR_CUDA; }
+    return zero_phase(f, rho, (const double2*)x_dev, nullptr, (double2*)y_dev, nullptr, nullptr, n_rows, n, 0, 1, n, device,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int ssfm_pd_lpf(const void* field_dev, const void* noise_dev, const double* extra_noise_dev, double* out_signal_dev,
+                           double* out_noise_dev, int64_t n_rows, int32_t n_pol, int64_t n, double responsivity, double r_load,
+                           double i_dark, const double* sos_host, int32_t n_sections, int64_t sample_offset,
+                           int64_t sample_stride, int32_t device, void* stream) {
+    if (!field_dev || !out_signal_dev) { ssfm_err_slot = "null field or output"; return SSFM_ERR_INVALID; }
+    if (n_rows < 1 || n < 1 || (n_pol != 1 && n_pol != 2)) { ssfm_err_slot = "n_rows, n_samples >= 1 and n_pol in {1, 2} expected"; return SSFM_ERR_INVALID; }
+    if (sample_stride < 1 || sample_offset < 0 || sample_offset >= n) { ssfm_err_slot = "sampler: 0 <= offset < n_samples and stride >= 1 expected"; return SSFM_ERR_INVALID; }
+    if ((noise_dev || extra_noise_dev) && !out_noise_dev) { ssfm_err_slot = "noise inputs need out_noise"; return SSFM_ERR_INVALID; }
+    Sos f;
+    double rho = 0;
+    int rc = parse_filter(f, &rho, sos_host, n_sections, n);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { ssfm_err_slot = std::string("pd_lpf: ") + cudaGetErrorString(e); return SSFM_ERR_CUDA; }
+    PdSrc s;
+    s.field = (const double2*)field_dev; s.noise = (const double2*)noise_dev; s.extra = extra_noise_dev;
+    s.r = responsivity; s.r_load = r_load; s.i_dark = out_noise_dev ? i_dark : 0.0; s.n_pol = n_pol;
+    s.noise_out = out_noise_dev ? 1 : 0;
+    const long long m = (n - sample_offset + sample_stride - 1) / sample_stride;
+    return zero_phase(f, rho, nullptr, &s, nullptr, out_signal_dev, out_noise_dev, n_rows, n, sample_offset, sample_stride, m, device,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int ssfm_gaussian_noise(double* out_dev, int64_t count, double mean, double sigma, uint64_t seed, uint32_t substream,
+                                   int32_t device, void* stream) {
+    if (!out_dev || count < 0) { ssfm_err_slot = "null buffer or negative count"; return SSFM_ERR_INVALID; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess && count > 0) {
+        const long long pairs = (count + 1) / 2;
+        ssfm_filt::k_gaussian<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, count, mean, sigma, seed, substream);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { ssfm_err_slot = std::string("gaussian_noise: ") + cudaGetErrorString(e); return SSFM_ERR_CUDA; }
+    return SSFM_OK;
+}
+
+extern "C" int ssfm_edfa(const void* in_dev, void* out_dev, int64_t n_rows, int64_t in_rows, int32_t in_pol, int32_t out_pol,
+                         int64_t n, double gain_db, double p_ase_w, uint64_t seed, int32_t device, void* stream) {
+    if (!in_dev || !out_dev) { ssfm_err_slot = "null buffer"; return SSFM_ERR_INVALID; }
+    if (n_rows < 1 || n < 1 || (in_rows != 1 && in_rows != n_rows) || in_pol < 1 || in_pol > 2 || out_pol < in_pol || out_pol > 2) {
+        ssfm_err_slot = "edfa: rows >= 1, in_rows in {1, rows}, 1 <= in_pol <= out_pol <= 2 expected"; return SSFM_ERR_INVALID;
+    }
+    if (p_ase_w < 0) { ssfm_err_slot = "edfa: negative ASE power"; return SSFM_ERR_INVALID; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        const long long cnt = n_rows * out_pol * n;
+        const double g_amp = std::sqrt(std::pow(10.0, gain_db / 10.0));          // np.sqrt(idb(G)), devices.py:921
+        const double sigma = std::sqrt(p_ase_w / 4.0);                            // np.sqrt(P_ase/4), devices.py:933
+        ssfm_filt::k_edfa<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const double2*)in_dev, (double2*)out_dev, n_rows, in_rows,
+                                                                                        in_pol, out_pol, n, g_amp, sigma, seed);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) { ssfm_err_slot = std::string("edfa: ") + cudaGetErrorString(e); return SSFM_ERR_CUDA; }
     return SSFM_OK;
 }

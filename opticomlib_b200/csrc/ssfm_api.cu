@@ -161,6 +161,8 @@ struct ssfm_plan_s {
     cudaEvent_t wf_ev[2] = {nullptr, nullptr};
     cudaStream_t wf_side = nullptr;   // k_wf: side stream of the launch that fills the slots the clusters leave
     cudaEvent_t wf_ev_side = nullptr;
+    cudaStream_t peek_stream = nullptr;   // ssfm_peek_state: a copy stream of its own + one pinned record
+    Ctrl* peek_host = nullptr;
     int last_kind = 0;           // schedule of the last propagate: 0 none, 1 multi-launch, 2 k_wf
     int last_teams = 0;
     int lo_bits = 0;             // split of the four-step twiddle tables (0 = log2 n2)
@@ -630,19 +632,33 @@ __global__ void k_transpose_xfer(typename cx_of<R>::type* out, const typename cx
 }
 
 template <typename R>
-int apply_transfer_t(ssfm_plan_t pl, void* field, cudaStream_t st) {
+Params<R> transfer_params(ssfm_plan_t pl, void* field, long long rows) {
     typedef typename cx_of<R>::type C;
     ssfm_fiber_params prm{};
-    prm.dt_s = 1.0; prm.length_km = 1e30; prm.phi_max_rad = 0.01; prm.h_km = 1.0;   // linear, one "step"
+    prm.dt_s = 1.0; prm.length_km = 1e30; prm.phi_max_rad = 0.01; prm.h_km = 1.0;   // linear, one "step" per application
     bool fixed, single;
     Params<R> p = base_params<R>(pl, prm, fixed, single);
     p.field = (C*)field; p.stash = nullptr; p.ctrl = pl->ctrl; p.active = pl->active; p.hlog = nullptr;
-    p.ticket = pl->ticket; p.batch = (int)pl->batch; p.xfer = (const C*)pl->xfer;
+    p.ticket = pl->ticket; p.batch = (int)rows; p.xfer = (const C*)pl->xfer;
+    return p;
+}
+// controller records of a transfer plan: fixed step 1 towards an unreachable length, so every application is "one more step"
+// of every row and nothing has to be re-armed between applications (the filter pipeline applies the plan once per chunk)
+template <typename R>
+int transfer_arm(ssfm_plan_t pl, cudaStream_t st) {
+    Params<R> p = transfer_params<R>(pl, nullptr, pl->batch);
     const int nb = (int)pl->batch;
     CU_TRY(cudaMemcpyAsync(p.active, &nb, sizeof(int), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(Ctrl) * (size_t)nb, st));
     k_ctrl_init<R><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(p, 1, (R)1, 0);
     ++ssfm_launches;
+    CU_TRY(cudaGetLastError());
+    return SSFM_OK;
+}
+template <typename R>
+int apply_transfer_rows(ssfm_plan_t pl, void* field, long long rows, cudaStream_t st, bool arm = true) {
+    if (arm) { const int ra = transfer_arm<R>(pl, st); if (ra) return ra; }
+    const Params<R> p = transfer_params<R>(pl, field, rows);
     int rc = enqueue_col<R>(p, COL_FWD, st);
     if (!rc) rc = enqueue_row<R>(p, st);
     if (!rc) rc = enqueue_col<R>(p, COL_INV, st);
@@ -651,6 +667,8 @@ int apply_transfer_t(ssfm_plan_t pl, void* field, cudaStream_t st) {
     pl->have_state = false;
     return SSFM_OK;
 }
+template <typename R>
+int apply_transfer_t(ssfm_plan_t pl, void* field, cudaStream_t st) { return apply_transfer_rows<R>(pl, field, pl->batch, st); }
 
 int ensure_xfer(ssfm_plan_t pl) {
     if (pl->xfer) return SSFM_OK;
@@ -664,10 +682,12 @@ std::map<std::tuple<int, long long, long long>, ssfm_plan_t> g_filter_plans;   /
 
 }  // namespace
 
-int ssfm_internal_zero_phase_circular(int device, long long n, long long rows, const ssfm_filt::Sos& f, void* y_dev,
-                                      cudaStream_t st) {
+int ssfm_internal_pass_tables_f64(void** out, int M, cudaStream_t st) { return build_pass_tables<double>(out, M, st); }
+
+int ssfm_internal_transfer_prepare(int device, long long n, long long max_rows, const ssfm_filt::Sos& f, void** plan_out,
+                                   cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_filter_mu);
-    const auto key = std::make_tuple(device, n, rows);
+    const auto key = std::make_tuple(device, n, max_rows);
     ssfm_plan_t pl = nullptr;
     auto it = g_filter_plans.find(key);
     if (it == g_filter_plans.end()) {
@@ -675,7 +695,7 @@ int ssfm_internal_zero_phase_circular(int device, long long n, long long rows, c
             ssfm_plan_destroy(g_filter_plans.begin()->second);
             g_filter_plans.erase(g_filter_plans.begin());
         }
-        int rc = plan_create_impl(&pl, n, 1, rows, SSFM_C128, device, false);
+        int rc = plan_create_impl(&pl, n, 1, max_rows, SSFM_C128, device, false);
         if (rc) return rc;
         g_filter_plans[key] = pl;
     } else {
@@ -686,7 +706,16 @@ int ssfm_internal_zero_phase_circular(int device, long long n, long long rows, c
     if (rc) return rc;
     k_fill_xfer_sos<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((double2*)pl->xfer, (int)n, pl->n1, pl->n2, f);
     ++ssfm_launches;
-    return apply_transfer_t<double>(pl, y_dev, st);
+    rc = transfer_arm<double>(pl, st);
+    if (rc) return rc;
+    *plan_out = pl;
+    return SSFM_OK;
+}
+
+int ssfm_internal_transfer_apply(void* plan, void* y_dev, long long rows, cudaStream_t st) {
+    ssfm_plan_t pl = (ssfm_plan_t)plan;
+    if (!pl || rows < 1 || rows > pl->batch) return fail(SSFM_ERR_INVALID, "transfer_apply: bad plan or row count");
+    return apply_transfer_rows<double>(pl, y_dev, rows, st, false);
 }
 
 extern "C" {
@@ -834,6 +863,8 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     for (int r = 0; r < 8; ++r)
         if (pl->peer_base[r] && pl->peer_base[r] != pl->xbuf) cudaIpcCloseMemHandle(pl->peer_base[r]);
     cudaFree(pl->xbuf); cudaFree(pl->d_peer_flags); cudaFree(pl->dim_tab);
+    if (pl->peek_stream) cudaStreamDestroy(pl->peek_stream);
+    if (pl->peek_host) cudaFreeHost(pl->peek_host);
     if (pl->wf_side) cudaStreamDestroy(pl->wf_side);
     if (pl->wf_ev_side) cudaEventDestroy(pl->wf_ev_side);
     if (pl->inner) ssfm_plan_destroy(pl->inner);
@@ -890,6 +921,41 @@ int ssfm_get_state(ssfm_plan_t pl, int32_t* steps, double* z, double* h_next, in
         if (h_next) h_next[i] = h[i].h;
         if (done) done[i] = h[i].done;
     }
+    return SSFM_OK;
+}
+
+int ssfm_plan_get_option(ssfm_plan_t pl, const char* name, int64_t* value) {
+    if (!pl || !name || !value) return fail(SSFM_ERR_INVALID, "null plan, option name or value");
+    const std::string k(name);
+    if (k == "hlog_cap") *value = pl->hlog_cap;
+    else if (k == "chunk_waveforms") *value = pl->chunk;
+    else if (k == "burst_steps") *value = pl->burst;
+    else if (k == "fused") *value = pl->fused;
+    else if (k == "persistent") *value = pl->persistent;
+    else if (k == "cluster") *value = pl->cluster;
+    else if (k == "placement") *value = pl->placement;
+    else if (k == "teams") *value = pl->teams_cap;
+    else if (k == "n1") *value = pl->n1;
+    else if (k == "n2") *value = pl->n2;
+    else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
+    return SSFM_OK;
+}
+
+int ssfm_peek_state(ssfm_plan_t pl, int64_t row, int32_t* steps, double* z, int32_t* done) {
+    if (!pl || row < 0 || row >= pl->batch) return fail(SSFM_ERR_INVALID, "null plan or row out of range");
+    CU_TRY(cudaSetDevice(pl->device));
+    if (!pl->peek_stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&pl->peek_stream, cudaStreamNonBlocking));
+        CU_TRY(cudaHostAlloc((void**)&pl->peek_host, sizeof(Ctrl), cudaHostAllocDefault));
+    }
+    // a copy on its own stream: it does not wait for the propagation running on the caller's stream; the controller record is
+    // rewritten once per step by one thread (z, h, steps, done: each an aligned word, so a torn read shows at worst the
+    // previous step's value of one field -- good enough for a progress display, which is all this is for)
+    CU_TRY(cudaMemcpyAsync(pl->peek_host, pl->ctrl + row, sizeof(Ctrl), cudaMemcpyDeviceToHost, pl->peek_stream));
+    CU_TRY(cudaStreamSynchronize(pl->peek_stream));
+    if (steps) *steps = pl->peek_host->steps;
+    if (z) *z = pl->peek_host->z;
+    if (done) *done = pl->peek_host->done;
     return SSFM_OK;
 }
 

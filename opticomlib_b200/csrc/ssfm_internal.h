@@ -15,8 +15,15 @@ struct Sos {
 
 extern thread_local std::string ssfm_err_slot;
 
-// y[rows][n] (complex128, device) <- circular convolution of each row with the zero-phase response
-// |H(e^{jw})|^2 of the cascade `f`, computed as IFFT(|H|^2 FFT(y)) with the SSFM transform kernels.
-// n must be a power of two in [2^8, 2^22].  Returns an SSFM_* code.
-int ssfm_internal_zero_phase_circular(int device, long long n, long long rows, const ssfm_filt::Sos& f,
-                                      void* y_dev, cudaStream_t st);
+// Circular convolution of rows of n complex128 samples with the zero-phase response |H(e^{jw})|^2 of the cascade `f`,
+// computed as IFFT(|H|^2 FFT(y)) with the SSFM transform kernels (n a power of two in [2^8, 2^22]).
+// prepare: tables and the response for rows of n samples, for at most `max_rows` rows per apply (cached per device, n and
+// max_rows).  apply: in place on `rows` <= max_rows rows at y_dev; three launches, no synchronisation.  SSFM_* codes.
+int ssfm_internal_transfer_prepare(int device, long long n, long long max_rows, const ssfm_filt::Sos& f, void** plan_out,
+                                   cudaStream_t st);
+int ssfm_internal_transfer_apply(void* plan, void* y_dev, long long rows, cudaStream_t st);
+
+// Pass tables (+ the 256-entry sincos table behind them) of the M-point complex128 transform of fft_core.cuh, device memory owned
+// by the caller.
+int ssfm_internal_pass_tables_f64(void** out, int M, cudaStream_t st);
+

@@ -102,16 +102,32 @@ def fiber_batch(field, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
     if x.ndim not in (2, 3):
         raise ValueError("field must have shape [B, N] or [B, P, N]")
     B, P, N = (x.shape[0], 1, x.shape[1]) if x.ndim == 2 else tuple(x.shape)
+    _check_length(N)
     plan = engine.get_plan(N, P, B, tdtype, dev)
-    plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
-    _set_schedule(plan, fused, persistent)
+    _set_schedule(plan, fused, persistent, chunk_waveforms)
     info = plan.propagate(x, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, want_log=want_log)
     return x, info
 
 
-def _set_schedule(plan, fused=True, persistent=None):
+def _set_schedule(plan, fused=True, persistent=None, chunk_waveforms=None):
+    plan.reset_schedule()                                  # cached plans are shared: no option survives from an earlier caller
+    plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
     plan.set_option("fused", 1 if fused else 0)
     plan.set_option("persistent", int(bool(fused)) if persistent is None else int(bool(persistent)))
+
+
+MAX_TWO_PASS = 1 << 22          # longest waveform of one two-pass transform; longer ones are split N0 x N_l (longwave.py)
+MAX_CHIRP = 1 << 21             # longest waveform whose length is not a power of two (chirp-z transforms of 2^22 points)
+
+
+def _check_length(n):
+    """The reference accepts any N (numpy.fft).  Here: any N in [2, 2^21]; powers of two up to 2^30.  Anything else is refused
+    up front with the supported lengths spelled out, not from inside the plan layer."""
+    n = int(n)
+    pow2 = n >= 2 and (n & (n - 1)) == 0
+    if n < 2 or (not pow2 and n > MAX_CHIRP) or n > (1 << 30):
+        raise ValueError("opticomlib_b200 supports waveforms of 2 ... 2^21 samples of any length and power-of-two lengths up to 2^30; "
+                         "got %d samples%s" % (n, "" if n < 2 or n > (1 << 30) else " (pad or crop to a power of two, or to at most 2^21 samples)"))
 
 
 HOST_PIPELINE = "auto"          # "async": ONE host thread enqueues, per chunk and round-robin over HOST_LANES streams, H2D copy ->
@@ -156,6 +172,7 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
         raise ValueError("field must have shape [B, N] or [B, P, N]")
     B = host.shape[0]
     P, N = (1, host.shape[1]) if host.ndim == 2 else (host.shape[1], host.shape[2])
+    _check_length(N)
     if out is None:
         out = torch.empty(host.shape, dtype=tdtype, pin_memory=host.is_pinned())
     elif out.shape != host.shape or out.dtype != tdtype or out.is_cuda:
@@ -180,8 +197,7 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
                         r0, r1 = chunks[ci]
                         x = host[r0:r1].to(dev, non_blocking=True).to(tdtype).contiguous()
                         plan = engine.get_plan(N, P, r1 - r0, tdtype, dev, lane=lane)
-                        plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
-                        _set_schedule(plan, fused, persistent)
+                        _set_schedule(plan, fused, persistent, chunk_waveforms)
                         info = plan.propagate(x, *args, want_log=want_log)
                         out[r0:r1].copy_(x, non_blocking=True)
                         steps[r0:r1], z[r0:r1], hn[r0:r1], done[r0:r1] = info.steps, info.z, info.h_next, info.done
@@ -239,8 +255,7 @@ def _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, row
                 else:
                     x.copy_(host[r0:r1], non_blocking=True)
                 plan = engine.get_plan(N, P, m, tdtype, dev, lane=ci % lanes)
-                plan.set_option("chunk_waveforms", 0 if chunk_waveforms is None else int(chunk_waveforms))
-                _set_schedule(plan, True, True)
+                _set_schedule(plan, True, True, chunk_waveforms)
                 plan.propagate(x, *args, state_out=rec[r0 * engine.STATE_RECORD:r1 * engine.STATE_RECORD])
                 out[r0:r1].copy_(x, non_blocking=True)
         for stream, _, _ in ln:
@@ -259,11 +274,39 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
 
     Units: km, dB/km, ps^2/km, ps^3/km, 1/(W km), rad.  Returns an ``optical_signal`` (noise NULL),
     or ``(z, A_z)`` with ``return_steps=True`` exactly like devices.py:1201-1202.
+    ``show_progress``: the reference refreshes a tqdm bar after every step (devices.py:1164-1170, 1188-1191); here the
+    propagation is one kernel, so the bar polls the device-side controller record (position reached, steps taken) while the
+    kernel runs.
     """
     tic()
-    if _kind(input) != "optical":
-        toc()
-        raise TypeError("`input` must be of type 'optical_signal'.")
+    try:
+        if _kind(input) != "optical":
+            raise TypeError("`input` must be of type 'optical_signal'.")
+        return _fiber(input, length, alpha, beta_2, beta_3, gamma, phi_max, h, show_progress, return_steps, precision, device)
+    except Exception:
+        toc()                                               # never leave a tic behind (the reference leaks its own on errors)
+        raise
+
+
+def _progress_bar(show):
+    if not show:
+        return None
+    try:
+        from tqdm.auto import tqdm
+        return tqdm(total=100, desc="Propagando", bar_format="{l_bar}{bar}|[{elapsed}{postfix}]", postfix={"FFTs": 0})
+    except Exception:
+        return None
+
+
+def _bar_set(bar, z, length, steps):
+    if bar is None:
+        return
+    bar.set_postfix(FFTs=2 * int(steps))
+    bar.n = round(min(100.0, 100.0 * float(z) / float(length)) if length else 100.0, 1)
+    bar.refresh()
+
+
+def _fiber(input, length, alpha, beta_2, beta_3, gamma, phi_max, h, show_progress, return_steps, precision, device):
     torch = engine._torch()
     tdtype, ndtype = _complex_dtype(precision)
     dev = engine.require_cuda(device)
@@ -271,7 +314,8 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
     a = np.asarray(input.to_numpy())                      # signal + noise (typing.py:1596)
     n_pol = 1 if a.ndim == 1 else a.shape[0]
     n = a.shape[-1]
-    if n > (1 << 22):                                      # beyond one two-pass transform: N = N0 x N_l stages (longwave.py)
+    _check_length(n)
+    if n > MAX_TWO_PASS:                                   # beyond one two-pass transform: N = N0 x N_l stages (longwave.py)
         from . import longwave
         if return_steps:
             z, traj = longwave.fiber_long(a, dt, length, alpha, beta_2, beta_3, gamma, phi_max, h, return_steps=True,
@@ -286,17 +330,9 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
         return output
     x = _to_device(a.reshape(1, n_pol, n), tdtype, dev)    # cast to the compute dtype on the device
     plan = engine.get_plan(n, n_pol, 1, tdtype, dev)
-    plan.set_option("chunk_waveforms", 0)
     _set_schedule(plan, True, None)
     args = (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h)
-
-    bar = None
-    if show_progress:
-        try:
-            from tqdm.auto import tqdm
-            bar = tqdm(total=100, desc="Propagando", bar_format="{l_bar}{bar}|[{elapsed}{postfix}]", postfix={"FFTs": 0})
-        except Exception:
-            bar = None
+    bar = _progress_bar(show_progress)
 
     if return_steps:
         # one step per call, resuming the device-side controller; snapshots stay on the device
@@ -307,8 +343,7 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
                 break
             z_list.append(np.float32(info.z[0]) if ndtype is np.complex64 else np.float64(info.z[0]))
             snaps.append(x.clone())
-            if bar is not None:
-                bar.set_postfix(FFTs=2 * int(info.steps[0])); bar.n = min(100.0, 100.0 * info.z[0] / length); bar.refresh()
+            _bar_set(bar, info.z[0], length, info.steps[0])
             if info.done[0]:
                 break
             info = plan.propagate(x, *args, max_steps=1, resume=True)
@@ -318,9 +353,22 @@ def FIBER(input, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0
         traj = torch.stack(snaps).cpu().numpy().reshape((len(snaps),) + a.shape)
         return np.array(z_list), traj
 
-    info = plan.propagate(x, *args)
+    if bar is not None and plan.get_option("persistent"):
+        # asynchronous launch + polling of the controller record the kernel rewrites after every step (ssfm_peek_state)
+        import time
+        rec = torch.empty(engine.STATE_RECORD, dtype=torch.uint8, pin_memory=True)
+        stream = torch.cuda.current_stream(dev)
+        plan.propagate(x, *args, state_out=rec)
+        while not stream.query():
+            steps_now, z_now, _ = plan.peek(0)
+            _bar_set(bar, z_now, length, steps_now)
+            time.sleep(0.02)
+        stream.synchronize()
+        info = engine.decode_state(rec.numpy())
+    else:
+        info = plan.propagate(x, *args)
     if bar is not None:
-        bar.set_postfix(FFTs=2 * int(info.steps[0])); bar.update(100); bar.close()
+        _bar_set(bar, length, length, info.steps[0]); bar.close()
     out = x.cpu().numpy().reshape(a.shape)
     output = type(input)(out)
     output.execution_time = toc()
@@ -365,6 +413,13 @@ def DM(input, D, retH=False, *, device=None):
     dev = engine.require_cuda(device)
     D = D * 1e-12 ** 2                                        # devices.py:1023 (the reference rebinds its argument the same way)
     n = input.size
+    try:
+        _check_length(n)
+        if n > MAX_TWO_PASS:
+            raise ValueError("opticomlib_b200.DM supports waveforms of up to 2^22 samples; got %d" % n)
+    except Exception:
+        toc()
+        raise
     w = np.fft.fftfreq(n, _gv_of(input).dt) * 2 * np.pi      # input.w(), typing.py:1641
     H = np.exp(1j * w ** 2 * D / 2)
     sig = np.asarray(input.signal, dtype=np.complex128)
@@ -474,6 +529,137 @@ def BPF(input, BW, n=4, *, device=None):
     return output
 
 
+# ---- N2 / N3: EDFA noise realisations and the photodetector chain on the device -------------
+PLANCK = 6.62607015e-34
+K_BOLTZMANN = 1.380649e-23
+Q_ELECTRON = 1.602176634e-19
+
+
+def edfa_batch(field, rows, G, NF, *, n_pol_out=2, seed=0, fs=None, f0=None, device=None):
+    """``rows`` independent EDFA outputs ``sqrt(G) E + ASE`` generated ON the device (reference EDFA, devices.py:921-936,
+    gain and noise; follow with ``filtfilt_batch`` for its optional BPF).  ``field``: one waveform ``[N]`` / ``[P, N]`` (NumPy
+    or CUDA tensor) amplified into ``rows`` noise realisations -- the Monte-Carlo batch of BASELINE config #3 without moving a
+    single noise sample over PCIe -- or a batch ``[rows, (P,) N]``.  ``G``, ``NF`` in dB; ASE power
+    ``idb(NF) h f0 (idb(G) - 1) fs`` (devices.py:930) split over four real components; the generator is the extension's
+    Philox (a function of ``seed`` and the element index), not NumPy's global stream.  ``n_pol_out`` = 2 like the reference
+    (a polarisation the input does not have carries ASE only), 1 keeps a one-polarisation batch ``[rows, N]``.
+    Returns a CUDA complex128 tensor."""
+    torch = engine._torch()
+    dev = engine.require_cuda(field.device if torch.is_tensor(field) and field.is_cuda else device)
+    x = (field if torch.is_tensor(field) else torch.from_numpy(np.ascontiguousarray(field))).to(dev).to(torch.complex128).contiguous()
+    fs = gv.fs if fs is None else fs
+    f0 = gv.f0 if f0 is None else f0
+    p_ase = 10 ** (NF / 10) * PLANCK * f0 * (10 ** (G / 10) - 1) * fs
+    return engine.edfa(x, rows, G, p_ase, seed, out_pol=n_pol_out)
+
+
+def pd_lpf_batch(field, sos, *, noise=None, extra_noise=None, responsivity=1.0, r_load=50.0, i_dark=0.0,
+                 sample_offset=0, sample_stride=1, device=None):
+    """Square-law detection, zero-phase low-pass and sampling of a batch ``field[B, (P,) N]`` in one pass over the field
+    (the chain PD -> LPF -> SAMPLER of devices.py:1514-1552 and 1871-1891).  Returns ``(signal, noise)`` float64 ``[B, m]``
+    (CUDA tensors for CUDA input, NumPy arrays otherwise; ``noise`` is None when no noise input is given)."""
+    torch = engine._torch()
+    as_tensor = torch.is_tensor(field)
+    dev = engine.require_cuda(field.device if as_tensor and field.is_cuda else device)
+
+    def dev_c(a, dt):
+        if a is None:
+            return None
+        t = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(dev).to(dt).contiguous()
+
+    s, nz = engine.pd_lpf(dev_c(field, torch.complex128), sos, dev_c(noise, torch.complex128), dev_c(extra_noise, torch.float64),
+                          responsivity, r_load, i_dark, sample_offset, sample_stride)
+    if as_tensor:
+        return s, nz
+    return s.cpu().numpy(), (None if nz is None else nz.cpu().numpy())
+
+
+def psd_batch(x, fs=None, nperseg=None, *, device=None):
+    """``(f, psd)`` of every row of ``x[..., N]`` exactly as ``utils.get_psd`` returns them for one signal (utils.py:2048-2079:
+    Welch, ``nperseg = min(2048, N)``, Hann, 50 % overlap, scaling='spectrum', two-sided, fftshift).  NumPy in, NumPy out; CUDA
+    tensor in, CUDA tensor out (``f`` is always a NumPy array)."""
+    torch = engine._torch()
+    as_tensor = torch.is_tensor(x)
+    dev = engine.require_cuda(x.device if as_tensor and x.is_cuda else device)
+    t = (x if as_tensor else torch.from_numpy(np.ascontiguousarray(x))).to(dev).to(torch.complex128).contiguous()
+    nper = min(2048, t.shape[-1]) if nperseg is None else int(nperseg)
+    psd = engine.welch_psd(t, nper)
+    f = np.fft.fftshift(np.fft.fftfreq(nper, 1.0 / (gv.fs if fs is None else fs)))
+    return f, (psd if as_tensor else psd.cpu().numpy())
+
+
+_PD_MODES = {            # include_noise -> (ase, thermal, shot)        devices.py:1530-1545
+    "ase-only": (1, 0, 0), "thermal-only": (0, 1, 0), "shot-only": (0, 0, 1), "ase-shot": (1, 0, 1),
+    "ase-thermal": (1, 1, 0), "thermal-shot": (0, 1, 1), "all": (1, 1, 1), "none": (0, 0, 0),
+}
+
+
+def PD(input, BW, r=1.0, T=300.0, R_load=50.0, include_noise="all", i_dark=10e-9, Fn=0, *, device=None):
+    """P-I-N photodetector -- reference signature and semantics, devices.py:1377-1556: square law, thermal / shot / ASE beat
+    noise and dark current kept as the ``noise`` of the returned ``electrical_signal``, then ``LPF(output, BW)``.
+    The thermal and shot samples are drawn on the host with ``np.random.normal`` in the reference's order (so a seeded script
+    sees the same values); square law, noise assembly and the zero-phase filter run in one device call."""
+    tic()
+    try:
+        if _kind(input) != "optical":
+            raise TypeError("`input` must be of type 'optical_signal'.")
+        for name, val in (("r", r), ("T", T), ("R_load", R_load)):
+            if isinstance(val, bool) or not isinstance(val, (int, float, np.integer, np.floating)):
+                raise TypeError("`%s` must be a scalar value." % name)
+        if r <= 0 or r > 1:
+            raise ValueError("`r` must be in the range (0,1]")
+        if T < 0:
+            raise ValueError("`T` must be a positive value.")
+        if R_load < 0:
+            raise ValueError("`R_load` must be a positive value.")
+        if not isinstance(include_noise, str):
+            raise TypeError("`include_noise` must be a string.")
+        mode = include_noise.lower()
+        torch = engine._torch()
+        dev = engine.require_cuda(device)
+        g = _gv_of(input)
+        sig = np.asarray(input.signal, dtype=np.complex128)
+        n = sig.shape[-1]
+        has_ase_in = not _is_null(input.noise)
+        noi = np.asarray(input.noise, dtype=np.complex128) if has_ase_in else None
+        thermal = shot = None
+        if "thermal" in mode or "all" in mode:                                # same draws, same order as devices.py:1521-1527
+            S_T = 4 * K_BOLTZMANN * T * g.fs / 2 * 10 ** (Fn / 10) / R_load
+            thermal = np.random.normal(0, S_T ** 0.5, n)
+        if "shot" in mode or "all" in mode:
+            tot = sig if noi is None else sig + noi
+            i_mean = (r * (tot * tot.conj()).real).sum(axis=0).mean() if tot.ndim == 2 else (r * (tot * tot.conj()).real).mean()
+            S_N = 2 * Q_ELECTRON * (i_mean + i_dark) * g.fs / 2
+            shot = np.random.normal(0, S_N ** 0.5, n)
+        if mode not in _PD_MODES:
+            raise ValueError("The argument `include_noise` must be one of the following: 'ase-only','thermal-only','shot-only',"
+                             "'ase-thermal','ase-shot','thermal-shot','all', 'none'.")
+        use_ase, use_t, use_n = _PD_MODES[mode]
+        sos = _bessel_sos(4, BW, g.fs)
+        f = torch.from_numpy(np.ascontiguousarray(sig.reshape(1, -1, n))).to(dev)
+        nz = torch.from_numpy(np.ascontiguousarray(noi.reshape(1, -1, n))).to(dev) if (use_ase and has_ase_in) else None
+        extra = None
+        if mode != "none":
+            e = np.zeros(n)
+            if use_n:
+                e = e + shot
+            if use_t:
+                e = e + thermal
+            extra = torch.from_numpy(e.reshape(1, n)).to(dev)
+        s_f, n_f = engine.pd_lpf(f, sos, nz, extra, r, R_load, i_dark if mode != "none" else 0.0)
+        klass = electrical_signal
+        mod = sys.modules.get(type(input).__module__)
+        if mod is not None and hasattr(mod, "electrical_signal"):
+            klass = mod.electrical_signal                                       # the reference's own class for its objects
+        output = klass(s_f[0].cpu().numpy()) if n_f is None else klass(s_f[0].cpu().numpy(), n_f[0].cpu().numpy())
+    except Exception:
+        toc()
+        raise
+    output.execution_time = toc()
+    return output
+
+
 # ---- drop-in installation -----------------------------------------------------------------------
 _SAVED: dict = {}
 
@@ -490,7 +676,7 @@ def install(precision: str | None = None):
     if precision is not None:
         _complex_dtype(precision)
         DEFAULT_PRECISION = precision
-    for name, fn in (("FIBER", FIBER), ("DBP", DBP), ("LPF", LPF), ("BPF", BPF), ("DM", DM)):
+    for name, fn in (("FIBER", FIBER), ("DBP", DBP), ("LPF", LPF), ("BPF", BPF), ("DM", DM), ("PD", PD)):
         _SAVED.setdefault(("opticomlib.devices", name), getattr(dv, name))
         setattr(dv, name, fn)
     for modname in ("opticomlib.ook", "opticomlib.ppm"):

@@ -76,6 +76,24 @@ class Plan:
     def set_option(self, name: str, value: int):
         _lib.check(self.lib.ssfm_plan_set_option(self.handle, name.encode(), int(value)))
 
+    def get_option(self, name: str) -> int:
+        v = ctypes.c_int64(0)
+        _lib.check(self.lib.ssfm_plan_get_option(self.handle, name.encode(), ctypes.byref(v)))
+        return int(v.value)
+
+    def reset_schedule(self):
+        """Every scheduling knob back to its default (a cached plan is shared by whoever asks for the same shape: an option
+        left behind by one caller must not steer the next)."""
+        for name, value in (("chunk_waveforms", 0), ("fused", 1), ("persistent", 1), ("teams", 0), ("cluster", -1),
+                            ("placement", -1), ("burst_steps", 8), ("debug", 0), ("tw_full", 1), ("l2_ahead", 0), ("async", 0)):
+            self.set_option(name, value)
+
+    def peek(self, row=0):
+        """(steps, z, done) of waveform ``row`` while an asynchronous propagation is running (``ssfm_peek_state``)."""
+        steps, z, done = ctypes.c_int32(0), ctypes.c_double(0.0), ctypes.c_int32(0)
+        _lib.check(self.lib.ssfm_peek_state(self.handle, int(row), ctypes.byref(steps), ctypes.byref(z), ctypes.byref(done)))
+        return int(steps.value), float(z.value), bool(done.value)
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.ssfm_plan_destroy(self.handle)
@@ -161,8 +179,15 @@ class Plan:
         log = None
         if want_log:
             cap = int(max(1, steps.max()))
-            log = np.zeros((B, cap), np.float64)
+            kept = self.get_option("hlog_cap")
+            if cap > kept:                                   # the device keeps the first `kept` step sizes of every waveform
+                import warnings
+                warnings.warn("opticomlib_b200: %d steps were taken but the step-size log holds %d entries per waveform; "
+                              "h_log[:, %d:] is NaN" % (cap, kept, kept), RuntimeWarning)
+            log = np.full((B, cap), np.nan, np.float64)
             _lib.check(self.lib.ssfm_get_step_log(self.handle, log.ctypes.data, cap))
+            for b in range(B):                               # beyond a waveform's own step count the row is zero, as before
+                log[b, min(int(steps[b]), kept):kept] = 0.0
         return StepInfo(steps, z, hn, done.astype(bool), log)
 
 
@@ -179,11 +204,14 @@ def get_plan(n, n_pol, batch, complex_dtype, device=None, lane=0) -> Plan:
     cd = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
     key = (int(n), int(n_pol), int(batch), cd, dev.index, int(lane))
     with _PLANS_LOCK:
-        pl = _PLANS.get(key)
+        pl = _PLANS.pop(key, None)
         if pl is None:
-            if len(_PLANS) >= 12:  # plans own O(B*N) device memory: keep the cache small
-                _PLANS.pop(next(iter(_PLANS))).close()
-            pl = _PLANS[key] = Plan(n, n_pol, batch, cd, dev)
+            while len(_PLANS) >= 12:  # plans own O(B*N) device memory: keep the cache small (least recently used goes first)
+                # Dropped from the cache, NOT destroyed: another lane thread may be inside ssfm_propagate with this plan; the
+                # handle is released by Plan.__del__ when the last reference is gone.
+                _PLANS.pop(next(iter(_PLANS)))
+            pl = Plan(n, n_pol, batch, cd, dev)
+        _PLANS[key] = pl                                     # (re)insert at the most-recently-used end
     return pl
 
 
@@ -214,3 +242,103 @@ def filtfilt_sos(x, sos: np.ndarray, out=None):
         _lib.check(lib.ssfm_filtfilt_sos(x.data_ptr(), y.data_ptr(), rows, n, sos.ctypes.data, sos.shape[0],
                                          x.device.index, ctypes.c_void_p(stream)))
     return y
+
+
+def pd_lpf(field, sos: np.ndarray, noise=None, extra_noise=None, responsivity=1.0, r_load=50.0, i_dark=0.0,
+           sample_offset=0, sample_stride=1):
+    """Photodetector square law + zero-phase low-pass + sampler in one pass over the field (C-ABI ``ssfm_pd_lpf``).
+
+    ``field`` (and ``noise``): CUDA complex128 ``[rows, N]`` or ``[rows, P, N]``; ``extra_noise``: CUDA float64 ``[rows, N]``
+    noise current.  Returns ``(signal, noise)`` float64 CUDA tensors ``[rows, m]`` (``noise`` is None without noise inputs)."""
+    torch = _torch()
+    lib = _lib.load()
+    if field.dtype != torch.complex128 or not field.is_cuda or not field.is_contiguous() or field.ndim not in (2, 3):
+        raise ValueError("field must be a contiguous CUDA complex128 tensor [rows, N] or [rows, P, N]")
+    rows, n_pol, n = (field.shape[0], 1, field.shape[1]) if field.ndim == 2 else tuple(field.shape)
+    for name, t, dt, shape in (("noise", noise, torch.complex128, tuple(field.shape)), ("extra_noise", extra_noise, torch.float64, (rows, n))):
+        if t is not None and (t.dtype != dt or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shape):
+            raise ValueError("%s must be a contiguous CUDA %s tensor of shape %s" % (name, dt, shape))
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise ValueError("sos must have shape (n_sections, 6)")
+    m = -(-(n - int(sample_offset)) // int(sample_stride)) if 0 <= sample_offset < n and sample_stride >= 1 else 0
+    want_noise = noise is not None or extra_noise is not None
+    out_s = torch.empty((rows, max(m, 0)), dtype=torch.float64, device=field.device)
+    out_n = torch.empty_like(out_s) if want_noise else None
+    stream = torch.cuda.current_stream(field.device).cuda_stream
+    with torch.cuda.device(field.device):
+        _lib.check(lib.ssfm_pd_lpf(field.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                   extra_noise.data_ptr() if extra_noise is not None else None, out_s.data_ptr(),
+                                   out_n.data_ptr() if out_n is not None else None, rows, n_pol, n, float(responsivity),
+                                   float(r_load), float(i_dark), sos.ctypes.data, sos.shape[0], int(sample_offset),
+                                   int(sample_stride), field.device.index, ctypes.c_void_p(stream)))
+    return out_s, out_n
+
+
+def gaussian_noise(shape, sigma, seed, substream=0, device=None, mean=0.0):
+    """float64 CUDA tensor of ``mean + sigma N(0,1)`` values from the extension's Philox generator (``ssfm_gaussian_noise``):
+    a pure function of (seed, substream, element index)."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = require_cuda(device)
+    out = torch.empty(shape, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(lib.ssfm_gaussian_noise(out.data_ptr(), out.numel(), float(mean), float(sigma), int(seed) & (2 ** 64 - 1),
+                                           int(substream) & 0xffffffff, dev.index, ctypes.c_void_p(stream)))
+    return out
+
+
+def edfa(field, rows, gain_db, p_ase_w, seed, out_pol=None, out=None):
+    """``sqrt(G) field + ASE`` for ``rows`` independent noise realisations (``ssfm_edfa``; reference devices.py:921-936).
+    ``field``: CUDA complex128 ``[N]`` / ``[P, N]`` (one waveform, broadcast) or ``[rows, N]`` / ``[rows, P, N]``.
+    Returns CUDA complex128 ``[rows, out_pol, N]`` (``[rows, N]`` when the input has no polarisation axis and out_pol is 1)."""
+    torch = _torch()
+    lib = _lib.load()
+    if field.dtype != torch.complex128 or not field.is_cuda or not field.is_contiguous():
+        raise ValueError("field must be a contiguous CUDA complex128 tensor")
+    rows = int(rows)
+    n = field.shape[-1]
+    if field.ndim == 1:
+        in_rows, in_pol, flat = 1, 1, True
+    elif field.ndim == 2 and field.shape[0] == rows and rows > 2:
+        in_rows, in_pol, flat = rows, 1, True
+    elif field.ndim == 2:
+        in_rows, in_pol, flat = 1, field.shape[0], False
+    elif field.ndim == 3:
+        in_rows, in_pol, flat = field.shape[0], field.shape[1], False
+    else:
+        raise ValueError("field must have shape [N], [P, N], [rows, N] or [rows, P, N]")
+    out_pol = int(out_pol) if out_pol is not None else (1 if flat else 2)
+    shape = (rows, n) if (flat and out_pol == 1) else (rows, out_pol, n)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.complex128, device=field.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.complex128 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError("out must be a contiguous CUDA complex128 tensor of shape %s" % (shape,))
+    stream = torch.cuda.current_stream(field.device).cuda_stream
+    with torch.cuda.device(field.device):
+        _lib.check(lib.ssfm_edfa(field.data_ptr(), out.data_ptr(), rows, in_rows, in_pol, out_pol, n, float(gain_db),
+                                 float(p_ase_w), int(seed) & (2 ** 64 - 1), field.device.index, ctypes.c_void_p(stream)))
+    return out
+
+
+def welch_psd(x, nperseg=None):
+    """Welch PSD of every row of a CUDA complex128 tensor ``[..., N]`` (``ssfm_welch_psd``): the estimate the reference plots
+    and returns (typing.py:1899-1902, utils.py:2074-2079), bins in fftshift order.  Returns a float64 CUDA tensor
+    ``[..., nperseg]``."""
+    torch = _torch()
+    lib = _lib.load()
+    if x.dtype != torch.complex128 or not x.is_cuda or not x.is_contiguous():
+        raise ValueError("x must be a contiguous CUDA complex128 tensor")
+    n = x.shape[-1]
+    nperseg = min(2048, n) if nperseg is None else int(nperseg)
+    rows = x.numel() // n
+    out = torch.empty(tuple(x.shape[:-1]) + (nperseg,), dtype=torch.float64, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    with torch.cuda.device(x.device):
+        for r0 in range(0, rows, 65535):                      # grid.y limit
+            r1 = min(rows, r0 + 65535)
+            _lib.check(lib.ssfm_welch_psd(x.view(-1, n)[r0:r1].data_ptr(), out.view(-1, nperseg)[r0:r1].data_ptr(), r1 - r0, n,
+                                          nperseg, x.device.index, ctypes.c_void_p(stream)))
+    return out
+

@@ -352,11 +352,12 @@ def get_long_plan(n_global, complex_dtype, device=None, group=None, n_outer=None
     dev = engine.require_cuda(device)
     cd = torch.complex64 if complex_dtype in (torch.complex64, np.complex64, "fp32") else torch.complex128
     key = (int(n_global), cd, dev.index, id(group) if group is not None else None, n_outer, bool(fused_exchange), int(pol))
-    pl = _PLANS.get(key)
+    pl = _PLANS.pop(key, None)
     if pl is None:
-        if len(_PLANS) >= 4:                                # long plans own O(N) device memory
-            _PLANS.pop(next(iter(_PLANS))).close()
-        pl = _PLANS[key] = LongPlan(n_global, cd, dev, group, n_outer, fused_exchange=fused_exchange)
+        while len(_PLANS) >= 4:                             # long plans own O(N) device memory; least recently used goes first.
+            _PLANS.pop(next(iter(_PLANS)))                  # Dropped, not destroyed: LongPlan.__del__ closes it with the last reference
+        pl = LongPlan(n_global, cd, dev, group, n_outer, fused_exchange=fused_exchange)
+    _PLANS[key] = pl
     return pl
 
 

@@ -164,6 +164,39 @@ def test_example_chain_ook_transmission(ref):
     assert rel_l2(got_pd.signal, want_pd.signal) <= 2e-4
 
 
+@pytest.mark.parametrize("mode", ["all", "none", "ase-only", "thermal-shot", "ase-shot"])
+def test_pd_drop_in_with_seeded_noise(ref, mode):
+    """PD (devices.py:1377-1556) redirected as a whole: the thermal and shot samples come from np.random.normal in the
+    reference's order, so with the same seed the two implementations must agree sample for sample (signal AND noise)."""
+    opticomlib, rdv = ref
+    from opticomlib_b200 import devices as dv
+    _, sig = _tx(opticomlib, rdv, nbits=128, sps=32)
+    rng = np.random.default_rng(11)
+    for pols in (1, 2):
+        s = sig.signal if pols == 1 else np.stack([sig.signal, 0.5j * sig.signal])
+        nz = 2e-3 * np.abs(sig.signal).max() * (rng.standard_normal(s.shape) + 1j * rng.standard_normal(s.shape))
+        x = opticomlib.optical_signal(s, nz)
+        np.random.seed(5)
+        want = rdv.PD(x, BW=7.5e9, r=0.9, include_noise=mode, Fn=3)
+        dv.install()
+        try:
+            assert rdv.PD is dv.PD
+            np.random.seed(5)
+            got = rdv.PD(x, BW=7.5e9, r=0.9, include_noise=mode, Fn=3)
+        finally:
+            dv.uninstall()
+        assert type(got) is opticomlib.electrical_signal and got.signal.shape == want.signal.shape
+        assert rel_l2(got.signal, want.signal) <= 1e-10
+        if mode == "none":
+            assert got.noise is opticomlib.NULL and want.noise is opticomlib.NULL
+        else:
+            assert rel_l2(got.noise, want.noise) <= 1e-10
+    with pytest.raises(ValueError):
+        dv.PD(x, BW=7.5e9, include_noise="bogus")
+    with pytest.raises(ValueError):
+        dv.PD(x, BW=7.5e9, r=1.5)
+
+
 def test_errors_match_the_reference(ref, installed):
     opticomlib, rdv = ref
     with pytest.raises(TypeError):
