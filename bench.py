@@ -409,10 +409,20 @@ def main():
         alg_bytes = step_bytes * per_launch_units
         launch_ms = kern_ms / a.steps
         achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-        tps = traffic_tab.get("k_wf_%s_dram_bytes_per_sample_step" % a.precision)
+        # DRAM bytes of one launch: an ncu capture (dram__bytes_read.sum + dram__bytes_write.sum) of THIS command at THIS size when
+        # profiles/traffic.json holds one (rows per GPU must match), else the capture's bytes per sample*step scaled to this launch
+        # and labelled as such.  One read + one write of the field is the floor for a batch that does not fit in L2.
+        cap = traffic_tab.get("k_wf_%s_launch" % a.precision) or {}
+        traffic, traffic_src = None, None
+        if cap.get("rows") == rows and cap.get("samples_per_row") == n:
+            traffic, traffic_src = cap["dram_bytes"], "measured: " + cap.get("source", "ncu capture of the same command and size")
+        elif cap.get("dram_bytes") and cap.get("sample_steps"):
+            traffic = cap["dram_bytes"] / cap["sample_steps"] * per_launch_units
+            traffic_src = "extrapolated from a %d-row capture (%s)" % (cap.get("rows", 0), cap.get("source", "ncu"))
         roofline = {
             "bound": "hbm", "kernel": "k_wf", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": (tps * per_launch_units) if tps is not None else None,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "field_bytes_1r_1w": 2 * csize * rows * n,
             "peak_source": peak_src,
             "kernel_ms": {"k_wf": launch_ms}, "kernel_share_of_step": {"k_wf": launch_ms / (ms_total / a.steps)},
             "teams_in_flight": teams,

@@ -34,7 +34,7 @@ int wf_fail(int code, const std::string& msg) { ssfm_err_slot = msg; return code
 template <typename R, int M1, int M2, bool SMALL>
 int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st, int coop_ctas) {
     typedef wf_geom<R, M1, M2> GEO;
-    auto kern = k_wf<R, M1, M2, SMALL, true>;
+    auto kern = k_wf<R, M1, M2, SMALL, 1>;
     const int total = p.n_pol * (p.n2 / GEO::T);
     static int max_clusters_dev[64][17] = {{0}};                 // per instantiation, device and cluster size
     int dev = 0;
@@ -97,7 +97,7 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
         b.slots = (unsigned long long*)(sb + head + (size_t)fill * 256);
         b.n_teams = (int)fill;
         WF_TRY(cudaStreamWaitEvent(l.side, l.ev0, 0));
-        k_wf<R, M1, M2, SMALL, false><<<(unsigned)(fill * total), GEO::NT, GEO::smem, l.side>>>(p, b);
+        k_wf<R, M1, M2, SMALL, 0><<<(unsigned)(fill * total), GEO::NT, GEO::smem, l.side>>>(p, b);
         WF_TRY(cudaGetLastError());
         WF_TRY(cudaEventRecord(l.ev_side, l.side));
         WF_TRY(cudaStreamWaitEvent(st, l.ev_side, 0));
@@ -108,10 +108,84 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     return SSFM_OK;
 }
 
+// multi-cluster teams (32 .. 256 CTAs): clusters of 8 CTAs, hardware barrier inside a cluster, one flag hop between the cluster
+// leaders.  All clusters of a team must be resident at once, so the launch is cooperative and no larger than the number of
+// clusters that fit on the chip (33 clusters of 8 with two 256-thread CTAs per SM on a B200: four teams of 2^18 samples, one of
+// 2^20).
+template <typename R, int M1, int M2, bool SMALL>
+int wf_launch_mc(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
+    typedef wf_geom<R, M1, M2> GEO;
+    constexpr int CS = 8;
+    auto kern = k_wf<R, M1, M2, SMALL, 2>;
+    const long long total = (long long)p.n_pol * (p.n2 / GEO::T);
+    if (total <= 16 || total % CS) return SSFM_ERR_UNSUPPORTED;
+    static int max_clusters_dev[64];
+    static bool init = false;
+    if (!init) { for (int& v : max_clusters_dev) v = 0; init = true; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& max_clusters = max_clusters_dev[(dev >= 0 && dev < 64) ? dev : 0];
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(GEO::NT); cfg.dynamicSmemBytes = GEO::smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    if (max_clusters == 0) {
+        WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
+        cfg.gridDim = dim3((unsigned)(CS * 64));
+        int n = 0;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        cfg.numAttrs = 2;
+        if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+        max_clusters = n > 0 ? n : -1;
+    }
+    const long long ncl = total / CS;
+    long long teams = max_clusters / ncl;
+    if (getenv("SSFM_DEBUG"))
+        fprintf(stderr, "[ssfm] k_wf multi-cluster<%d,%d,%d>: %lld clusters of %d per team, %d clusters fit -> %lld teams\n", (int)sizeof(R), M1, M2,
+                ncl, CS, max_clusters, teams);
+    if (teams < 1) return SSFM_ERR_UNSUPPORTED;
+    if (teams > p.batch) teams = p.batch;
+    if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
+    const size_t head = 4096 + 256;
+    const size_t ts = (size_t)teams;
+    const size_t need = head + ts * 256 + ts * 2 * total * 16;
+    if (need > WF_SYNC_BYTES) return SSFM_ERR_UNSUPPORTED;
+    WF_TRY(cudaMemsetAsync(l.sync_buf, 0, need, st));
+    WfArgs<R> a;
+    std::memset(&a, 0, sizeof(a));
+    char* sb = (char*)l.sync_buf;
+    a.next_wf = (unsigned int*)(sb + 4096 + 128);
+    a.bar = (unsigned int*)(sb + head);
+    a.mail = (unsigned long long*)(sb + head + ts * 128);
+    a.slots = (unsigned long long*)(sb + head + ts * 256);
+    a.budget = l.budget;
+    a.n_teams = (int)teams;
+    a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
+    a.h_fixed = (R)l.h_fixed;
+    a.occ = 1; a.placement = 0;
+    cfg.gridDim = dim3((unsigned)(teams * total));
+    if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, a);
+    if (e != cudaSuccess) {                                  // e.g. cooperative + cluster launch refused: the flag-based teams take over
+        (void)cudaGetLastError();
+        if (getenv("SSFM_DEBUG")) fprintf(stderr, "[ssfm] multi-cluster launch refused: %s\n", cudaGetErrorString(e));
+        return SSFM_ERR_UNSUPPORTED;
+    }
+    ++ssfm_launches;
+    if (l.ev1) WF_TRY(cudaEventRecord(l.ev1, st));
+    if (teams_out) *teams_out = (int)teams;
+    return SSFM_OK;
+}
+
 template <typename R, int M1, int M2, bool SMALL>
 int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
     typedef wf_geom<R, M1, M2> GEO;
-    auto kern = k_wf<R, M1, M2, SMALL, false>;
+    auto kern = k_wf<R, M1, M2, SMALL, 0>;
     static int per_sm_dev[64];                                  // per instantiation and device (function attributes are per device)
     static bool per_sm_init = false;
     if (!per_sm_init) { for (int& v : per_sm_dev) v = -1; per_sm_init = true; }
@@ -134,6 +208,15 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     if constexpr (M2 <= 256) {                                           // teams of <= 16 CTAs can be thread-block clusters
         if (l.cluster != 0 && total <= 16 && total >= 2 && (total & (total - 1)) == 0) {
             const int rc = wf_launch_cluster<R, M1, M2, SMALL>(p, l, teams_out, st, per_sm * l.num_sms);
+            if (rc != SSFM_ERR_UNSUPPORTED) return rc;
+        }
+    }
+    if constexpr (M1 * M2 >= (1 << 16)) {                                // (2^16 with two polarisations, 2^17 .. 2^20)
+        // measured on B200 (scripts/exp_mc.py): one 2^20-sample waveform, fp32: 4.97 ms against 6.18 ms with flag-based teams
+        // (+24 %); fp64: 7.57 against 7.40 ms (its phases are longer, the barrier is a smaller share, and clusters of 8 leave the
+        // chip 32 CTAs short of the cooperative grid) -- so "auto" (-1) takes this path for fp32 only, cluster = 1 forces it
+        if ((l.cluster > 0 || (l.cluster < 0 && sizeof(R) == 4)) && total > 16 && total <= l.num_sms * (long long)per_sm) {
+            const int rc = wf_launch_mc<R, M1, M2, SMALL>(p, l, teams_out, st);
             if (rc != SSFM_ERR_UNSUPPORTED) return rc;
         }
     }

@@ -16,7 +16,11 @@
 // -> controller -> merged Kerr rotation of the second half step of step s and the first half step of
 // step s+1 -> forward transform).  The phases of one waveform are separated by team barriers.
 //
-// Two variants of the team synchronisation (template parameter CL):
+// Three variants of the team synchronisation (template parameter TM; CL := TM == 1, MC := TM == 2):
+//   MC          teams of 32 .. 256 CTAs (N = 2^17 .. 2^20) made of thread-block clusters of 8: the team barrier is the hardware
+//               barrier inside every cluster plus ONE flag hop between the cluster leaders (4 .. 32 arrivals on the counter in
+//               L2 instead of 32 .. 256, and only the leaders poll); the maxima travel through st.async inside a cluster and as
+//               self-validating words between the leaders.  Launched cooperatively (all clusters of a team must be resident).
 //   CL = true   teams of <= 16 CTAs are thread-block clusters: hardware cluster barrier (arrive.release /
 //               wait.acquire by every thread), per-CTA maxima and the waveform index through distributed shared
 //               memory.  1.4x (fp64) .. 1.6x (fp32) faster per team, but 16-CTA clusters must sit inside one GPC, so
@@ -141,9 +145,10 @@ __device__ __forceinline__ void st_async_u64(void* local_slot, unsigned long lon
 // CL = true: the team is one thread-block cluster (teams of <= 16 CTAs): the team barrier is the hardware cluster barrier
 // (arrive.release / wait.acquire, executed by every thread), the per-CTA maxima and the waveform index travel through
 // distributed shared memory, and no cooperative launch, registration or global-memory flag is needed.
-template <typename R, int M1, int M2, bool SMALL, bool CL>
+template <typename R, int M1, int M2, bool SMALL, int TM>
 __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> p, WfArgs<R> a) {
     typedef typename cx_of<R>::type C;
+    constexpr bool CL = (TM == 1), MC = (TM == 2);
     typedef wf_geom<R, M1, M2> GEO;
     constexpr int E = GEO::E, NT = GEO::NT, T = GEO::T, G = GEO::G, PM = GEO::PM;
     static_assert(points_per_thread<R>::value == 16, "k_wf assumes 16 points per thread");
@@ -176,9 +181,19 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     // spread by blockIdx.
     __shared__ unsigned int s_slot, s_rank;
     int team, me;
-    if (CL) {
-        team = (int)cluster_id_x();
-        me = (int)cluster_ctarank();
+    unsigned csz = 1u, crank = 0u, ncl = 1u, sub = 0u;       // CTAs per cluster, my rank in it; clusters per team, my cluster's index
+    if (CL || MC) {
+        crank = cluster_ctarank();
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csz));
+        if (CL) {
+            team = (int)cluster_id_x();
+            me = (int)crank;
+        } else {
+            ncl = total / csz;
+            team = (int)(cluster_id_x() / ncl);
+            sub = cluster_id_x() % ncl;
+            me = (int)(sub * csz + crank);
+        }
         if (tid == 0) {
             mbar_init(&mb_max, 1u);                            // one arrival per exchange: thread 0's expect_tx
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -244,6 +259,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     int state = WF_GRAB;
     auto bar_arrive = [&]() {
         if (CL) { cluster_arrive_release(); return; }           // every thread releases its own stores
+        if (MC) { cluster_arrive_release(); bar_target += ncl; return; }
         if (total == 1u) return;                                // a team of one CTA: the CTA barrier in bar_wait is enough
         __syncthreads();                                        // every thread's stores are ordered before the release
         bar_target += total;                                  // (one arrival per WARP instead -- no CTA barrier, each warp releases
@@ -251,6 +267,17 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     };
     auto bar_wait = [&]() {
         if (CL) { cluster_wait_acquire(); return; }
+        if (MC) {                                               // hardware barrier in the cluster, one flag hop between the leaders,
+            cluster_wait_acquire();                             // hardware barrier again to pass the news on
+            if (crank == 0u && tid == 0) {
+                red_release_add_u32(bar, 1u);                   // (cumulative: covers the stores the cluster barrier made visible to me)
+                while ((int)(ld_relaxed_u32(bar) - bar_target) < 0) { }
+                fence_acq_rel_gpu();
+            }
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            return;
+        }
         if (total == 1u) { __syncthreads(); return; }           // stores (write-through) -> bar.sync -> ld.global.cg of the same CTA
         if (tid == 0) {
             while ((int)(ld_relaxed_u32(bar) - bar_target) < 0) { if (total > 32u) __nanosleep(20); }   // big teams: ease off L2
@@ -268,22 +295,53 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
         unsigned long long bits = ord_bits(pm);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, bits, o); bits = x > bits ? x : bits; }
-        if (CL) {
-            // Every WARP sends its maximum to slot [me][warp] of every CTA of the cluster with st.async; the bytes are counted
-            // by the destination's mbarrier, whose phase completes when thread 0's expect_tx and all total x 8 words are in.
+        if (CL || MC) {
+            // Every WARP sends its maximum to slot [rank][warp] of every CTA of the cluster with st.async; the bytes are counted
+            // by the destination's mbarrier, whose phase completes when thread 0's expect_tx and all csz x 8 words are in.
             // No CTA barrier, no cluster barrier, no fence.  (Two exchanges are always separated by a cluster barrier that
             // every thread passes after it has read cl_max, so one buffer and one barrier are enough.)
             constexpr int NWARP = NT / 32;
             const unsigned par = xchg & 1u;
             ++xchg;
-            if (tid == 0) mbar_expect_tx(&mb_max, total * NWARP * 8u);
-            if (lane < (int)total) st_async_u64(&cl_max[me * NWARP + warp], &mb_max, (unsigned)lane, bits);
+            if (tid == 0) mbar_expect_tx(&mb_max, csz * NWARP * 8u);
+            if (lane < (int)csz) st_async_u64(&cl_max[crank * NWARP + warp], &mb_max, (unsigned)lane, bits);
             mbar_wait(&mb_max, par);
             unsigned long long m = 0ull;
-            for (int i = lane; i < (int)total * NWARP; i += 32) { const unsigned long long x = cl_max[i]; m = x > m ? x : m; }
+            for (int i = lane; i < (int)csz * NWARP; i += 32) { const unsigned long long x = cl_max[i]; m = x > m ? x : m; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, m, o); m = x > m ? x : m; }
-            return from_bits<R>(m);
+            if (CL) return from_bits<R>(m);
+            // MC: m is the maximum of my cluster; the cluster leaders publish it as self-validating words and warp 0 of every
+            // CTA polls the ncl words of the team
+            const unsigned long long tag = (unsigned long long)xchg;
+            volatile unsigned long long* wf = a.slots + ((size_t)(team * 2 + (xchg & 1u)) * total) * 2;
+            if (warp == 0) {
+                if (crank == 0u && lane < NW) {
+                    const unsigned long long part = (NW == 1) ? (m & 0xffffffffull) : (lane == 0 ? (m >> 32) : (m & 0xffffffffull));
+                    wf[sub * 2 + lane] = (part << 32) | tag;
+                }
+                const int nwords = (int)ncl * NW;
+                unsigned long long best = 0ull;
+                for (int base = 0; base < nwords; base += 32) {
+                    const int idx = base + lane;
+                    const bool have = idx < nwords;
+                    unsigned long long x = tag;
+                    if (have) { for (;;) { x = wf[(idx / NW) * 2 + (idx % NW)]; if ((x & 0xffffffffull) == tag) break; } }
+                    unsigned long long val = have ? (x >> 32) : 0ull;
+                    if (NW == 2) {
+                        const unsigned long long other = __shfl_xor_sync(0xffffffffu, val, 1);
+                        val = (lane & 1) ? 0ull : ((val << 32) | other);
+                    }
+                    best = val > best ? val : best;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
+                if (lane == 0) red[0] = best;
+            }
+            __syncthreads();
+            const unsigned long long all = red[0];
+            __syncthreads();                                    // red[0] is free for the next exchange
+            return from_bits<R>(all);
         }
         ++xchg;
         const unsigned long long tag = (unsigned long long)xchg;

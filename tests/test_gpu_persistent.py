@@ -104,33 +104,45 @@ def test_more_waveforms_than_teams_with_diverging_step_counts(ob, precision):
     scales = 0.2 + 2.3 * np.random.default_rng(3).random(rows)
     x = np.stack([np.sqrt(s) * np.roll(base, 997 * i) for i, s in enumerate(scales)])
     kw = dict(length=8.0, alpha=0.2, beta_2=-20.0, beta_3=0.1, gamma=2.0, phi_max=0.01)
-    out, info = ob.fiber_batch(x, DT, precision=precision, persistent=True, **kw)
+    import torch
+    from opticomlib_b200 import engine
+    td = torch.complex64 if precision == "fp32" else torch.complex128
+    xd = torch.from_numpy(x).cuda().to(td)                      # device-resident batch: ONE plan / one launch for all 45 rows
+    out_t, info = ob.fiber_batch(xd, DT, precision=precision, persistent=True, **kw)
+    out = out_t.cpu().numpy()
     kind, teams, ms = _kind(ob, n, 1, rows, precision)
     assert kind == 2 and 1 <= teams < rows and ms > 0
-    out_m, info_m = ob.fiber_batch(x, DT, precision=precision, persistent=False, **kw)
+    out_m, info_m = ob.fiber_batch(xd, DT, precision=precision, persistent=False, **kw)
     assert np.array_equal(info.steps, info_m.steps) and info.done.all()
     assert len(set(info.steps.tolist())) > 5
-    assert rel_l2(out, out_m) <= (2e-6 if precision == "fp32" else 1e-13)
+    assert rel_l2(out, out_m.cpu().numpy()) <= (2e-6 if precision == "fp32" else 1e-13)
     for i in (0, 7, 44):
         with np.errstate(all="ignore"):
             ref = oracle_fiber(x[i], DT, real=REAL[precision], **kw)
         assert int(info.steps[i]) == ref["steps"]
         assert rel_l2(out[i], ref["out"]) <= TOL[precision]
-    # capping the number of teams changes the schedule, not the numbers
-    from opticomlib_b200 import engine
-    import torch
-    td = torch.complex64 if precision == "fp32" else torch.complex128
+    # the same rows from pageable host memory (threaded lanes, several chunks) give the same numbers
+    out_h, info_h = ob.fiber_batch(x, DT, precision=precision, **kw)
+    assert np.array_equal(out_h, out) and np.array_equal(info_h.steps, info.steps)
+    # capping the number of teams changes the schedule, not the numbers (options are set on the plan and the plan is driven
+    # directly: fiber_batch resets every scheduling option of the cached plan it uses)
     plan = engine.get_plan(n, 1, rows, td, torch.device("cuda", 0))
     # (cluster = 1: each team is a thread-block cluster with hardware barriers; 0: cooperative launch, barriers through L2)
     for teams_cap, placement, cluster in ((3, -1, 0), (5, 0, 0), (5, 1, 0), (0, 0, 0), (0, 1, 0), (0, -1, 1), (3, -1, 1)):
+        plan.reset_schedule()                                           # (the multi-launch call above left persistent = 0)
         plan.set_option("teams", teams_cap); plan.set_option("placement", placement); plan.set_option("cluster", cluster)
         try:
-            out_3, info_3 = ob.fiber_batch(x, DT, precision=precision, persistent=True, **kw)
+            w = xd.clone()
+            info_3 = plan.propagate(w, DT, **kw)
             if teams_cap:
                 assert plan.last_timing()[1] == teams_cap               # waveforms in flight
         finally:
-            plan.set_option("teams", 0); plan.set_option("placement", -1); plan.set_option("cluster", -1)
-        assert np.array_equal(out_3, out) and np.array_equal(info_3.steps, info.steps)
+            plan.reset_schedule()
+        assert np.array_equal(w.cpu().numpy(), out) and np.array_equal(info_3.steps, info.steps)
+    # ... and fiber_batch does not inherit an option another caller left on the cached plan
+    plan.set_option("teams", 2)
+    ob.fiber_batch(xd, DT, precision=precision, persistent=True, **kw)
+    assert plan.last_timing()[1] > 2 and plan.get_option("teams") == 0
 
 
 def test_persistent_step_budget_and_resume(ob):
@@ -185,3 +197,39 @@ def test_degenerate_step_rules(ob, log2n):
             assert int(info.steps[0]) == ref["steps"], (precision, kw)
             assert rel_l2(out[0], ref["out"]) <= TOL[precision], (precision, kw)
             np.testing.assert_allclose(info.z[0], ref["z"][-1], rtol=1e-6 if precision == "fp32" else 1e-12)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("log2n,n_pol", [(17, 1), (16, 2), (18, 1)], ids=["2^17", "2^16x2pol", "2^18"])
+def test_multi_cluster_teams_match_oracle_and_flag_teams(ob, log2n, n_pol, precision):
+    """Teams of 32 / 64 CTAs as clusters of 8 with one flag hop between the cluster leaders (plan option cluster = 1) against
+    the oracle and against the flag-based cooperative teams (cluster = 0): several adaptive steps, rows with different step
+    counts, more rows than teams, a step budget with resume."""
+    import torch
+    from opticomlib_b200 import engine
+    n = 1 << log2n
+    rows = 11
+    kw = dict(length=2.5, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.004)
+    base = _wave(n, 40 + log2n, power=8e-3, n_pol=n_pol)
+    x = np.stack([base * (1.0 + 0.07 * b) for b in range(rows)])
+    td = torch.complex64 if precision == "fp32" else torch.complex128
+    dev = torch.device("cuda", 0)
+    with np.errstate(all="ignore"):
+        refs = [oracle_fiber(x[b], DT, real=REAL[precision], **kw) for b in (0, rows - 1)]
+    assert refs[0]["steps"] >= 4 and refs[1]["steps"] > refs[0]["steps"]
+    outs = {}
+    for cluster in (1, 0):
+        plan = engine.get_plan(n, n_pol, rows, td, dev, lane=5)
+        plan.set_option("cluster", cluster)
+        f = torch.from_numpy(x).to(dev).to(td).contiguous()
+        info = plan.propagate(f, DT, max_steps=3, **kw)
+        while not info.done.all():
+            info = plan.propagate(f, DT, max_steps=3, resume=True, **kw)
+        assert plan.last_timing()[0] == 2
+        for ref, b in zip(refs, (0, rows - 1)):
+            assert int(info.steps[b]) == ref["steps"]
+            assert rel_l2(f[b].cpu().numpy().reshape(ref["out"].shape), ref["out"]) <= TOL[precision]
+        outs[cluster] = (f.cpu().numpy(), info.steps.copy())
+        plan.set_option("cluster", -1)
+    np.testing.assert_array_equal(outs[1][1], outs[0][1])
+    np.testing.assert_array_equal(outs[1][0], outs[0][0])          # same arithmetic, only the synchronisation differs
