@@ -377,6 +377,12 @@ def main():
             extra = secondary(torch, engine, dev, a) if world == 1 else {}
         except Exception as e:                                          # secondary numbers never break the line
             extra = {"error": repr(e)}
+        if a.workload == "cfg3":
+            try:
+                extra["e2e_edfa_on_device"] = extra_generated(torch, dist, dev, rank, world, a, w, rows, tdtype, csize)
+            except Exception as e:
+                extra["e2e_edfa_on_device"] = {"error": repr(e)}
+            barrier()
         for name, fn in (("cfg4_receiver_1024x2^18_fp64", extra_cfg4), ("cfg5_2^26_fp64", extra_cfg5)):
             if name.startswith("cfg5") and world == 1:
                 continue                                                # one GPU: secondary() already ran the 2^26 waveform
@@ -618,6 +624,42 @@ def cupy_note():
 
 def _events(torch):
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def extra_generated(torch, dist, dev, rank, world, a, w, rows, tdtype, csize):
+    """Config #3 end to end with the EDFA noise realisations generated ON the device: the host sends one
+    waveform (1 MiB) and receives the propagated batch; generation, propagation and the D2H copies of different chunks
+    overlap (opticomlib_b200.edfa_fiber_batch).  Same rows per GPU, same fibre, same metric as the headline."""
+    from opticomlib_b200 import devices, engine
+    import opticomlib_b200 as ob
+    ob.gv(sps=w["sps"], R=w["rate"])
+    n = w["n"]
+    out_h = torch.empty((rows, n), dtype=tdtype, pin_memory=True)
+    base = torch.from_numpy(w["base"]).pin_memory()
+    from opticomlib_b200.scheduler import row_shard
+    first = row_shard(w["rows"], world, rank).start                  # this rank's rows of the global batch: global noise indices
+    kw = dict(seed=1000, precision=a.precision, out=out_h, first_row=first, **w["fiber"])
+    devices.edfa_fiber_batch(base, rows, w["gain_db"], w["nf_db"], w["dt"], **kw)      # warm
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    units, t0 = 0, time.perf_counter()
+    for _ in range(a.steps):
+        _, info = devices.edfa_fiber_batch(base, rows, w["gain_db"], w["nf_db"], w["dt"], **kw)
+        units += info.sample_steps(n)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    agg = torch.tensor([t, float(units)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = agg.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t, units = float(mx[0]), float(sm[1])
+    del out_h
+    engine.clear_plans(); torch.cuda.empty_cache()
+    return {"value": units / t, "unit": UNIT, "n_gpus": world, "ms_per_step": t * 1e3 / a.steps, "bytes_per_unit": 4 * csize,
+            "h2d_bytes_per_step": int(base.numel() * 16) * world, "d2h_bytes_per_step": int(rows * n * csize) * world,
+            "api": "opticomlib_b200.edfa_fiber_batch(one pinned complex128 waveform -> pinned host batch): ASE realisations from the "
+                   "extension's Philox generator on the device (reference EDFA devices.py:921-936), then FIBER, then D2H"}
 
 
 def extra_cfg4(torch, dist, dev, rank, world):

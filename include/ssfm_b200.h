@@ -200,9 +200,11 @@ SSFM_API int ssfm_gaussian_noise(double* out_dev, int64_t count, double mean, do
  * in_dev: complex128 [in_rows][in_pol][n_samples] with in_rows == n_rows, or in_rows == 1 to amplify ONE waveform into n_rows
  * independent noise realisations (the Monte-Carlo batch of BASELINE config #3 without any host->device copy);
  * out_dev: complex128 [n_rows][out_pol][n_samples], out_pol >= in_pol (the reference always returns two polarisations: a
- * polarisation the input does not have carries ASE only).  p_ase_w = idb(NF) h f0 (idb(G) - 1) fs (devices.py:930). */
+ * polarisation the input does not have carries ASE only).  p_ase_w = idb(NF) h f0 (idb(G) - 1) fs (devices.py:930).
+ * first_row: index of out_dev's first row in the whole batch (the noise of row b is a function of seed and first_row + b
+ * only, so a batch produced in chunks equals the batch produced at once). */
 SSFM_API int ssfm_edfa(const void* in_dev, void* out_dev, int64_t n_rows, int64_t in_rows, int32_t in_pol, int32_t out_pol,
-              int64_t n_samples, double gain_db, double p_ase_w, uint64_t seed, int32_t device, void* stream);
+              int64_t n_samples, double gain_db, double p_ase_w, uint64_t seed, int64_t first_row, int32_t device, void* stream);
 
 /* Welch power spectral density of every row, as the reference computes it for `signal.psd()` (typing.py:1899-1902) and
  * `utils.get_psd` (utils.py:2074-2079): scipy.signal.welch(x, nperseg, scaling='spectrum', return_onesided=False,

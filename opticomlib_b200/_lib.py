@@ -72,7 +72,8 @@ PROTOTYPES = {
     "ssfm_welch_psd": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_void_p]),
     "ssfm_edfa": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
-                                 ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int32, ctypes.c_void_p]),
+                                 ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32,
+                                 ctypes.c_void_p]),
 }
 
 _lib = None

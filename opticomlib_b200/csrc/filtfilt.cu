@@ -263,7 +263,7 @@ __global__ void k_gaussian(double* __restrict__ out, long long count, double mea
 // EDFA: out[row][pol][i] = sqrt(G) in[row or 0][pol][i] + sigma (n1 + j n2)   (devices.py:921-936; y polarisation of a
 // one-polarisation input is zero signal + ASE).  in_rows = 1 broadcasts one input waveform to every realisation.
 __global__ void k_edfa(const double2* __restrict__ in, double2* __restrict__ out, long long rows, long long in_rows, int in_pol,
-                       int out_pol, long long n, double g_amp, double sigma, unsigned long long seed) {
+                       int out_pol, long long n, double g_amp, double sigma, unsigned long long seed, long long first_row) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * out_pol * n) return;
     const long long row = i / (out_pol * n);
@@ -271,7 +271,8 @@ __global__ void k_edfa(const double2* __restrict__ in, double2* __restrict__ out
     const long long k = i % n;
     double2 e; e.x = 0.0; e.y = 0.0;
     if (pol < in_pol) { const double2 a = in[((in_rows == 1 ? 0 : row) * in_pol + pol) * n + k]; e.x = g_amp * a.x; e.y = g_amp * a.y; }
-    const double2 g = philox_normal2(seed, 0x45444641u, (unsigned long long)i);
+    // the counter is the element's index in the WHOLE batch, so a batch generated chunk by chunk equals the batch generated at once
+    const double2 g = philox_normal2(seed, 0x45444641u, (unsigned long long)(first_row * out_pol * n + i));
     e.x += sigma * g.x; e.y += sigma * g.y;
     out[i] = e;
 }
@@ -477,7 +478,7 @@ extern "C" int ssfm_gaussian_noise(double* out_dev, int64_t count, double mean, 
 }
 
 extern "C" int ssfm_edfa(const void* in_dev, void* out_dev, int64_t n_rows, int64_t in_rows, int32_t in_pol, int32_t out_pol,
-                         int64_t n, double gain_db, double p_ase_w, uint64_t seed, int32_t device, void* stream) {
+                         int64_t n, double gain_db, double p_ase_w, uint64_t seed, int64_t first_row, int32_t device, void* stream) {
     if (!in_dev || !out_dev) { ssfm_err_slot = "null buffer"; return SSFM_ERR_INVALID; }
     if (n_rows < 1 || n < 1 || (in_rows != 1 && in_rows != n_rows) || in_pol < 1 || in_pol > 2 || out_pol < in_pol || out_pol > 2) {
         ssfm_err_slot = "edfa: rows >= 1, in_rows in {1, rows}, 1 <= in_pol <= out_pol <= 2 expected"; return SSFM_ERR_INVALID;
@@ -489,7 +490,7 @@ extern "C" int ssfm_edfa(const void* in_dev, void* out_dev, int64_t n_rows, int6
         const double g_amp = std::sqrt(std::pow(10.0, gain_db / 10.0));          // np.sqrt(idb(G)), devices.py:921
         const double sigma = std::sqrt(p_ase_w / 4.0);                            // np.sqrt(P_ase/4), devices.py:933
         ssfm_filt::k_edfa<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const double2*)in_dev, (double2*)out_dev, n_rows, in_rows,
-                                                                                        in_pol, out_pol, n, g_amp, sigma, seed);
+                                                                                        in_pol, out_pol, n, g_amp, sigma, seed, first_row);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) { ssfm_err_slot = std::string("edfa: ") + cudaGetErrorString(e); return SSFM_ERR_CUDA; }

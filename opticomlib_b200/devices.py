@@ -553,6 +553,56 @@ def edfa_batch(field, rows, G, NF, *, n_pol_out=2, seed=0, fs=None, f0=None, dev
     return engine.edfa(x, rows, G, p_ase, seed, out_pol=n_pol_out)
 
 
+def edfa_fiber_batch(field, rows, G, NF, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0, phi_max=0.01, h=None, *,
+                     seed=0, precision=None, out=None, fs=None, f0=None, device=None, first_row=0):
+    """Monte-Carlo batch end to end WITHOUT moving the noise realisations over PCIe: ``rows`` EDFA outputs of ONE waveform
+    ``field[N]`` (gain ``G`` dB, noise figure ``NF`` dB, x polarisation kept: BASELINE config #3) are generated on the device
+    chunk by chunk (``ssfm_edfa``, Philox), propagated through FIBER and copied to the pinned host tensor ``out[rows, N]``;
+    generation, propagation and the D2H copy of different chunks overlap on ``HOST_LANES`` streams, one enqueueing host
+    thread (the pipeline of ``fiber_batch`` with the H2D copy replaced by the generator).  Row b is the same whatever the
+    chunking: its noise depends on ``seed`` and ``first_row + b`` only.  Returns ``(out, StepInfo)``."""
+    torch = engine._torch()
+    tdtype, ndtype = _complex_dtype(precision)
+    dev = engine.require_cuda(device)
+    x = (field if torch.is_tensor(field) else torch.from_numpy(np.ascontiguousarray(field))).to(dev).to(torch.complex128).contiguous()
+    if x.ndim != 1:
+        raise ValueError("field must be one waveform [N]")
+    N, B = x.shape[0], int(rows)
+    _check_length(N)
+    fs = gv.fs if fs is None else fs
+    f0 = gv.f0 if f0 is None else f0
+    p_ase = 10 ** (NF / 10) * PLANCK * f0 * (10 ** (G / 10) - 1) * fs
+    if out is None:
+        out = torch.empty((B, N), dtype=tdtype, pin_memory=True)
+    elif tuple(out.shape) != (B, N) or out.dtype != tdtype or out.is_cuda:
+        raise ValueError("out must be a host tensor of shape (%d, %d) and dtype %s" % (B, N, tdtype))
+    crows = host_chunk_rows(B, 1, N, tdtype)
+    chunks = [(r0, min(B, r0 + crows)) for r0 in range(0, B, crows)]
+    lanes = min(HOST_LANES, len(chunks))
+    args = (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h)
+    rec = torch.empty(B * engine.STATE_RECORD, dtype=torch.uint8, pin_memory=True)
+    with torch.cuda.device(dev):
+        ln = [(torch.cuda.Stream(device=dev), torch.empty((crows, N), dtype=torch.complex128, device=dev),
+               torch.empty((crows, N), dtype=tdtype, device=dev) if tdtype != torch.complex128 else None) for _ in range(lanes)]
+        torch.cuda.current_stream(dev).synchronize()
+        for ci, (r0, r1) in enumerate(chunks):
+            stream, gen, cast = ln[ci % lanes]
+            m = r1 - r0
+            with torch.cuda.stream(stream):
+                engine.edfa(x, m, G, p_ase, seed, out_pol=1, out=gen[:m], first_row=first_row + r0)
+                w = gen[:m]
+                if cast is not None:
+                    cast[:m].copy_(w)
+                    w = cast[:m]
+                plan = engine.get_plan(N, 1, m, tdtype, dev, lane=ci % lanes)
+                _set_schedule(plan, True, True)
+                plan.propagate(w, *args, state_out=rec[r0 * engine.STATE_RECORD:r1 * engine.STATE_RECORD])
+                out[r0:r1].copy_(w, non_blocking=True)
+        for stream, _, _ in ln:
+            stream.synchronize()
+    return out, engine.decode_state(rec.numpy())
+
+
 def pd_lpf_batch(field, sos, *, noise=None, extra_noise=None, responsivity=1.0, r_load=50.0, i_dark=0.0,
                  sample_offset=0, sample_stride=1, device=None):
     """Square-law detection, zero-phase low-pass and sampling of a batch ``field[B, (P,) N]`` in one pass over the field

@@ -289,10 +289,11 @@ def gaussian_noise(shape, sigma, seed, substream=0, device=None, mean=0.0):
     return out
 
 
-def edfa(field, rows, gain_db, p_ase_w, seed, out_pol=None, out=None):
+def edfa(field, rows, gain_db, p_ase_w, seed, out_pol=None, out=None, first_row=0):
     """``sqrt(G) field + ASE`` for ``rows`` independent noise realisations (``ssfm_edfa``; reference devices.py:921-936).
     ``field``: CUDA complex128 ``[N]`` / ``[P, N]`` (one waveform, broadcast) or ``[rows, N]`` / ``[rows, P, N]``.
-    Returns CUDA complex128 ``[rows, out_pol, N]`` (``[rows, N]`` when the input has no polarisation axis and out_pol is 1)."""
+    Returns CUDA complex128 ``[rows, out_pol, N]`` (``[rows, N]`` when the input has no polarisation axis and out_pol is 1).
+    ``first_row``: index of the first produced row in the whole batch (chunked generation gives the same noise as one call)."""
     torch = _torch()
     lib = _lib.load()
     if field.dtype != torch.complex128 or not field.is_cuda or not field.is_contiguous():
@@ -318,7 +319,7 @@ def edfa(field, rows, gain_db, p_ase_w, seed, out_pol=None, out=None):
     stream = torch.cuda.current_stream(field.device).cuda_stream
     with torch.cuda.device(field.device):
         _lib.check(lib.ssfm_edfa(field.data_ptr(), out.data_ptr(), rows, in_rows, in_pol, out_pol, n, float(gain_db),
-                                 float(p_ase_w), int(seed) & (2 ** 64 - 1), field.device.index, ctypes.c_void_p(stream)))
+                                 float(p_ase_w), int(seed) & (2 ** 64 - 1), int(first_row), field.device.index, ctypes.c_void_p(stream)))
     return out
 
 

@@ -210,3 +210,24 @@ def test_batch_containers_chain_stays_on_device(ob):
     lp = ob.electrical_batch(np.abs(fld) ** 2, 0.1 * np.abs(fld) ** 2).lpf(BW=7.5e9)
     assert rel_l2(lp.signal.cpu().numpy(), oracle_sosfiltfilt(sos_l, np.abs(fld) ** 2)) <= TOL
     assert rel_l2(lp.noise.cpu().numpy(), oracle_sosfiltfilt(sos_l, 0.1 * np.abs(fld) ** 2)) <= TOL
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_generated_monte_carlo_pipeline_equals_monolithic(ob, monkeypatch, precision):
+    """edfa_fiber_batch (chunks generated, propagated and copied out on three streams) against edfa_batch + fiber_batch on the
+    whole batch at once: the noise of a row depends on (seed, global row index) only, so the rows are bit-identical."""
+    import torch
+    from opticomlib_b200 import devices
+    ob.gv(sps=16, R=10e9)
+    n, rows = 1 << 13, 29
+    base = _field(1, 1, n, 12)[0, 0] * 3.0
+    kw = dict(length=8.0, alpha=0.2, beta_2=-20.0, gamma=2.0, phi_max=0.01)
+    monkeypatch.setattr(devices, "HOST_CHUNK_BYTES", 4 * n * 16)              # 8 chunks, ragged last one
+    got, info = ob.edfa_fiber_batch(base, rows, 10.0, 5.0, ob.gv.dt, seed=77, precision=precision, **kw)
+    assert got.is_pinned() and tuple(got.shape) == (rows, n)
+    whole = ob.edfa_batch(base, rows, 10.0, 5.0, n_pol_out=1, seed=77)
+    want, iw = ob.fiber_batch(whole, ob.gv.dt, precision=precision, **kw)
+    np.testing.assert_array_equal(info.steps, iw.steps)
+    np.testing.assert_array_equal(got.numpy(), want.cpu().numpy())
+    part, _ = ob.edfa_fiber_batch(base, 5, 10.0, 5.0, ob.gv.dt, seed=77, precision=precision, first_row=11, **kw)
+    np.testing.assert_array_equal(part.numpy(), got.numpy()[11:16])            # rows 11..15 of the same global batch
