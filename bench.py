@@ -235,6 +235,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not os.environ.get("SSFM_NO_NUMA_BIND"):
+        from opticomlib_b200.scheduler import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local)                          # before any pinned allocation: host buffers NUMA-local
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -485,6 +489,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "exposed_copy_ms": e2e_ms - ms_total / a.steps,
                 "chunks_per_gpu": -(-rows // devices.host_chunk_rows(rows, 1, n, tdtype)),
+                "numa_node_of_rank0": (numa[0] if numa else None),
                 "api": "opticomlib_b200.fiber_batch(pinned host complex128 -> pinned host %s), rows streamed in chunks over %d "
                        "streams (H2D / propagate / D2H overlapped, one enqueueing host thread); exposed_copy_ms = e2e ms per step "
                        "- device-resident ms per step (the first chunk's H2D and the last chunk's D2H)"

@@ -93,3 +93,38 @@ def propagate_sharded(rows_fn, total_rows: int, propagate_fn, gather: bool = Tru
     if gather and world > 1:
         return gather_rows(out, total_rows, group), gather_rows(steps, total_rows, group)
     return out, steps
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that host buffers it allocates afterwards (first
+    touch, and the pinned allocations of the host pipelines) live in that node's memory.  ``torchrun`` does not do this; with
+    eight ranks whose pinned buffers all land on one socket the H2D + D2H streams of the end-to-end path share that socket's
+    memory controllers and the inter-socket link (measured on the 8-GPU box: 64.8 ms per propagation end to end against 47.9 ms
+    device-resident; the run with the noise generated on the device, i.e. D2H only, sits at 51.0 ms).
+    Returns ``(node, cpus)`` or None when the topology cannot be read (no sysfs, no permission): then nothing is changed."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node, sorted(allowed)
+    except Exception:
+        return None
+
