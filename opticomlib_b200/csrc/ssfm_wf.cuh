@@ -298,8 +298,10 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
         if (CL || MC) {
             // Every WARP sends its maximum to slot [rank][warp] of every CTA of the cluster with st.async; the bytes are counted
             // by the destination's mbarrier, whose phase completes when thread 0's expect_tx and all csz x 8 words are in.
-            // No CTA barrier, no cluster barrier, no fence.  (Two exchanges are always separated by a cluster barrier that
-            // every thread passes after it has read cl_max, so one buffer and one barrier are enough.)
+            // No CTA barrier, no cluster barrier, no fence.  Two exchanges of a cluster are always separated by a cluster barrier
+            // that every thread passes after it has read cl_max (every phase boundary is one; between the last exchange of a
+            // waveform and the first of the next one the waveform draw provides it), so one buffer and one barrier are enough --
+            // without that separation a fast CTA's words of round r+1 could land in a slow CTA that still waits for round r.
             constexpr int NWARP = NT / 32;
             const unsigned par = xchg & 1u;
             ++xchg;
@@ -443,6 +445,10 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 __syncthreads();
                 const unsigned int w = s_w;
                 __syncthreads();
+                if (MC) {                                       // the draw of a multi-cluster team goes through the mailbox and is no
+                    cluster_arrive_release();                   // barrier: separate the previous waveform's last max exchange from
+                    cluster_wait_acquire();                     // this one's first inside every cluster (see team_max)
+                }
                 if (w >= (unsigned int)p.batch) { state = WF_END; continue; }
                 xchg = ((const volatile WfShared<R>*)&sh[ver & 1u])->xchg;
 

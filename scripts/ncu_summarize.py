@@ -54,7 +54,14 @@ def main():
             cur["hdr"] = r
         elif cur is not None and cur["hdr"] and len(r) >= len(cur["hdr"]):
             cur["rows"].append(r)
+    done = set()
     for b in blocks:
+        if b["hdr"] is None or not b["rows"]:
+            continue
+        key = (b["name"], len(b["rows"]), sum(int(r[b["hdr"].index("# Samples")] or 0) for r in b["rows"]))
+        if key in done:                                     # ncu repeats the source page of a kernel for every launch of it
+            continue
+        done.add(key)
         h = b["hdr"]; col = {n: i for i, n in enumerate(h)}
         sc = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
         tot, byop, samples = collections.Counter(), collections.defaultdict(collections.Counter), 0

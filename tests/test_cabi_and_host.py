@@ -118,3 +118,46 @@ def test_reference_objects_are_accepted_by_duck_typing(have_reference):
     finally:
         dv.uninstall()
     assert rdv.FIBER is original
+
+
+def test_host_chunk_rule_and_length_validation():
+    """Host-side logic of the end-to-end pipeline (no GPU): at least 12 chunks for large batches, a few rows per team in flight,
+    never above the byte cap; lengths the kernels do not support are refused up front with the supported set spelled out."""
+    import torch
+    from opticomlib_b200 import devices as dv
+    n = 1 << 16
+    for B in (4096, 2048, 1024, 512):
+        rows = dv.host_chunk_rows(B, 1, n, torch.complex128)
+        assert -(-B // rows) >= 12 and rows * n * 16 <= dv.HOST_CHUNK_BYTES
+        assert rows >= 36                                     # two rows per team in flight (18 teams of 16 CTAs)
+    assert dv.host_chunk_rows(3, 1, n, torch.complex128) == 3 and dv.host_chunk_rows(1, 2, n, torch.complex64) == 1
+    assert -(-44 // dv.host_chunk_rows(44, 1, n, torch.complex128)) == dv.HOST_LANES
+    for ok in (2, 3, 1000, 60000, (1 << 21) - 1, 1 << 21, 1 << 22, 1 << 26, 1 << 30):
+        dv._check_length(ok)
+    for bad in (0, 1, (1 << 21) + 1, 3 << 20, (1 << 30) + 1, 1 << 31):
+        with pytest.raises(ValueError, match="supports waveforms"):
+            dv._check_length(bad)
+
+
+def test_pd_argument_validation_matches_the_reference_without_a_gpu():
+    """PD validates before it touches the device: same exception types and messages as devices.py:1493-1512."""
+    import opticomlib_b200 as ob
+    x = ob.optical_signal(np.ones(64, complex))
+    with pytest.raises(TypeError, match="optical_signal"):
+        ob.PD(np.ones(8), BW=1e9)
+    with pytest.raises(ValueError, match=r"`r` must be in the range \(0,1\]"):
+        ob.PD(x, BW=1e9, r=0.0)
+    with pytest.raises(TypeError, match="`T` must be a scalar"):
+        ob.PD(x, BW=1e9, T="hot")
+    with pytest.raises(ValueError, match="`R_load` must be a positive"):
+        ob.PD(x, BW=1e9, R_load=-1.0)
+    with pytest.raises(TypeError, match="`include_noise` must be a string"):
+        ob.PD(x, BW=1e9, include_noise=3)
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    from opticomlib_b200.scheduler import bind_to_gpu_numa_node
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None                   # no CUDA device here: nothing is changed
+    assert os.sched_getaffinity(0) == before
