@@ -354,7 +354,17 @@ int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, doub
     const bool pow2 = (n & (n - 1)) == 0 && n >= 256 && n <= (1ll << 22);
     const bool fft_path = pow2 && K > 0 && 4 * K + 2 * f.edge <= n && !getenv("SSFM_FILTFILT_SEQUENTIAL");
     const bool real_out = out_sig != nullptr;
-    const long long chunk = fft_path ? chunk_rows(rows, n, device) : rows;
+    // rows of 2^12 .. 2^20 samples go through the persistent kernel in ONE launch (it keeps the rows in flight L2-resident by
+    // itself; at most 8 GiB of packed rows at a time); other lengths through the three streaming kernels in L2-sized chunks
+    // (small batches leave most teams of the persistent kernel idle: measured on B200, 16 rows of 2^18 samples take 0.57 ms in
+    // one launch against 0.48 ms in chunks, 1024 rows 8.3 against 11.2 ms -- so the one-launch path starts at 2^25 samples)
+    // (the photodetector path packs the whole batch first, which costs it the chunks' L2 residency: 128 rows of 2^18 take 2.06 ms
+    // in one launch against 1.75 ms in chunks, 1024 rows 10.1 against 12.4 ms -- its threshold is 2^27 samples)
+    const bool one_launch = fft_path && n >= 4096 && n <= (1ll << 20) && rows * n >= (pd ? (1ll << 27) : (1ll << 25)) &&
+                            !getenv("SSFM_TRANSFER_MULTILAUNCH");
+    const long long chunk = !fft_path ? rows
+                          : one_launch ? std::max<long long>(1, std::min<long long>(rows, (long long)((8ull << 30) / (16 * (size_t)n))))
+                                       : chunk_rows(rows, n, device);
 
     double* ws = nullptr;
     double2 *seg = nullptr, *edge_out = nullptr, *scratch = nullptr;
@@ -394,10 +404,10 @@ int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, doub
         for (long long r0 = 0; r0 < rows && !rc; r0 += chunk) {
             const long long nr = std::min(chunk, rows - r0);
             double2* buf = real_out ? scratch : y + (size_t)r0 * n;
+            const double2* src = nullptr;
             if (pd) k_pd_pack<<<(unsigned)((nr * n + 255) / 256), 256, 0, st>>>(*pd, buf, r0, nr, n);
-            else if (buf != x + (size_t)r0 * n) e = cudaMemcpyAsync(buf, x + (size_t)r0 * n, sizeof(double2) * (size_t)nr * n, cudaMemcpyDeviceToDevice, st);
-            if (e != cudaSuccess) return cuda_fail(e);
-            rc = ssfm_internal_transfer_apply(plan, buf, nr, st);
+            else if (buf != x + (size_t)r0 * n) src = x + (size_t)r0 * n;      // out of place: the transfer reads the source itself
+            rc = ssfm_internal_transfer_apply(plan, buf, nr, st, src, one_launch ? 1 : 0);
             if (!rc && real_out)
                 k_unpack_real<<<(unsigned)((nr * m + 255) / 256), 256, 0, st>>>(buf, out_sig, out_noise, r0, nr, n, offset, stride, m);
         }

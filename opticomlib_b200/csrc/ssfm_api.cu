@@ -655,8 +655,35 @@ int transfer_arm(ssfm_plan_t pl, cudaStream_t st) {
     CU_TRY(cudaGetLastError());
     return SSFM_OK;
 }
+// y = IFFT(H FFT(x)) for `rows` rows: ONE launch of the persistent kernel when the geometry has one (2^12 .. 2^20 samples) --
+// teams carry a row through forward column transforms, row transforms x H x inverse row transforms and inverse column
+// transforms with the rows in flight L2-resident, so HBM sees one read (from `src` when given: out of place) and one write per
+// row -- else the three streaming kernels (then `src` is copied into `field` first).  Nothing is synchronised.
 template <typename R>
-int apply_transfer_rows(ssfm_plan_t pl, void* field, long long rows, cudaStream_t st, bool arm = true) {
+int apply_transfer_rows(ssfm_plan_t pl, void* field, long long rows, cudaStream_t st, bool arm = true, const void* src = nullptr,
+                        bool one_launch = true) {
+    typedef typename cx_of<R>::type C;
+    if (one_launch && pl->persistent && pl->wf_sync && pl->n >= 4096 && pl->n <= (1ll << 20) && !getenv("SSFM_TRANSFER_MULTILAUNCH")) {
+        ssfm_fiber_params prm{};
+        prm.dt_s = 1.0; prm.length_km = 1.0; prm.phi_max_rad = 0.01; prm.h_km = 1.0;   // linear, exactly one "step" of length 1
+        bool fixed, single;
+        Params<R> p = base_params<R>(pl, prm, fixed, single);
+        p.field = (C*)field; p.field_in = (src && src != field) ? (const C*)src : nullptr;
+        p.stash = nullptr; p.ctrl = pl->ctrl; p.active = pl->active; p.hlog = nullptr;
+        p.ticket = pl->ticket; p.slots = pl->slots; p.batch = (int)rows; p.xfer = (const C*)pl->xfer;
+        WfLaunch l{};
+        l.sync_buf = pl->wf_sync; l.num_sms = pl->num_sms;
+        l.fixed = 1; l.single = 0; l.resume = 0; l.h_fixed = 1.0;
+        l.budget = 1; l.teams_cap = pl->teams_cap; l.placement = pl->placement; l.cluster = pl->cluster;
+        l.ev0 = pl->wf_ev[0]; l.ev1 = pl->wf_ev[1];
+        l.side = pl->wf_side; l.ev_side = pl->wf_ev_side;
+        int teams = 0;
+        const int rc = wf_propagate<R>(p, l, &teams, st);
+        if (rc == SSFM_OK) { pl->have_state = false; pl->last_kind = 2; pl->last_teams = teams; return SSFM_OK; }
+        if (rc != SSFM_ERR_UNSUPPORTED) return rc;
+    }
+    if (src && src != field)
+        CU_TRY(cudaMemcpyAsync(field, src, sizeof(C) * (size_t)rows * (size_t)pl->n, cudaMemcpyDeviceToDevice, st));
     if (arm) { const int ra = transfer_arm<R>(pl, st); if (ra) return ra; }
     const Params<R> p = transfer_params<R>(pl, field, rows);
     int rc = enqueue_col<R>(p, COL_FWD, st);
@@ -665,10 +692,14 @@ int apply_transfer_rows(ssfm_plan_t pl, void* field, long long rows, cudaStream_
     if (rc) return rc;
     CU_TRY(cudaGetLastError());
     pl->have_state = false;
+    pl->last_kind = 1;
     return SSFM_OK;
 }
 template <typename R>
-int apply_transfer_t(ssfm_plan_t pl, void* field, cudaStream_t st) { return apply_transfer_rows<R>(pl, field, pl->batch, st); }
+int apply_transfer_t(ssfm_plan_t pl, void* field, cudaStream_t st) {
+    const bool big = pl->batch * pl->n_pol * pl->n >= (1ll << 25);          // small batches: the three streaming kernels are faster
+    return apply_transfer_rows<R>(pl, field, pl->batch, st, true, nullptr, big);
+}
 
 int ensure_xfer(ssfm_plan_t pl) {
     if (pl->xfer) return SSFM_OK;
@@ -712,10 +743,10 @@ int ssfm_internal_transfer_prepare(int device, long long n, long long max_rows, 
     return SSFM_OK;
 }
 
-int ssfm_internal_transfer_apply(void* plan, void* y_dev, long long rows, cudaStream_t st) {
+int ssfm_internal_transfer_apply(void* plan, void* y_dev, long long rows, cudaStream_t st, const void* src_dev, int one_launch) {
     ssfm_plan_t pl = (ssfm_plan_t)plan;
     if (!pl || rows < 1 || rows > pl->batch) return fail(SSFM_ERR_INVALID, "transfer_apply: bad plan or row count");
-    return apply_transfer_rows<double>(pl, y_dev, rows, st, false);
+    return apply_transfer_rows<double>(pl, y_dev, rows, st, false, src_dev, one_launch != 0);
 }
 
 extern "C" {
@@ -811,9 +842,9 @@ static int plan_create_impl(ssfm_plan_t* out, int64_t n, int32_t n_pol, int64_t 
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&pl->active_host, 2 * sizeof(int), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev[1], cudaEventDisableTiming);
-    if (e == cudaSuccess && with_stash) e = cudaMalloc(&pl->wf_sync, WF_SYNC_BYTES);
-    if (e == cudaSuccess && with_stash) e = cudaStreamCreateWithFlags(&pl->wf_side, cudaStreamNonBlocking);
-    if (e == cudaSuccess && with_stash) e = cudaEventCreateWithFlags(&pl->wf_ev_side, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->wf_sync, WF_SYNC_BYTES);          // (transfer plans run through k_wf too)
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->wf_side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->wf_ev_side, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&pl->wf_ev[1]);
     if (e != cudaSuccess) {

@@ -39,6 +39,7 @@ template <typename R>
 struct Params {
     typedef typename cx_of<R>::type C;
     C* field;            // [B][P][N], updated in place
+    const C* field_in;   // k_wf only: read the waveforms from here instead (out-of-place transfer functions); null = field
     R* stash;            // [B][P][N] Kerr phase of the current step
     Ctrl* ctrl;          // [B]
     int* active;         // number of waveforms with done == 0

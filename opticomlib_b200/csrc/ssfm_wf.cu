@@ -268,7 +268,6 @@ int wf_launch_small(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaS
 
 template <typename R>
 int wf_propagate(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st) {
-    if (p.xfer) return SSFM_ERR_UNSUPPORTED;
 #define WF_CASE(A, B) if (p.n1 == A && p.n2 == B) return wf_launch_small<R, A, B>(p, l, teams_out, st);
     WF_CASE(64, 64) WF_CASE(64, 128)      // 2^12, 2^13: teams of one / two CTAs (per polarisation)
     WF_CASE(128, 128) WF_CASE(128, 256) WF_CASE(256, 256) WF_CASE(256, 512) WF_CASE(512, 512) WF_CASE(512, 1024)

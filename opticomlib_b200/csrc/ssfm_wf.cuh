@@ -462,9 +462,10 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                     z0 = (R)cs.z; h_first = (R)cs.h; steps0 = cs.steps;
                 }
                 C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + pol) * NN;
+                const C* __restrict__ inp = p.field_in ? p.field_in + ((size_t)w * p.n_pol + pol) * NN : rowp;   // out-of-place transfer
                 C v[E];
 #pragma unroll
-                for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + n2);
+                for (int q = 0; q < E; ++q) v[q] = __ldcg(inp + (size_t)(t + q * (M1 / E)) * M2 + n2);
                 if (!a.resume) {
                     R h0;
                     if (a.fixed) h0 = a.h_fixed;
@@ -526,7 +527,11 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
 #pragma unroll
                 for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
                 fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
-                {
+                if (p.xfer) {                                   // an arbitrary transfer function H[k] in transposed order: zero-phase
+                    const C* __restrict__ hrow = p.xfer + (size_t)k1 * M2;      // filters (|H|^2), DM, FBG -- one pass over the rows,
+#pragma unroll                                                  // FFT -> x H -> IFFT with the waveforms in flight L2-resident
+                    for (int q = 0; q < E; ++q) v[q] = cmul(v[q], __ldg(hrow + tr + q * (M2 / E)));
+                } else {
                     const R* __restrict__ drow = p.dim_tab + (size_t)k1 * M2;   // imag(D~) of my row's bins (k_fill_dim)
 #pragma unroll
                     for (int q = 0; q < E; ++q) {

@@ -16,7 +16,7 @@ def timed(fn):
         e0.record(); fn(); e1.record(); e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-for frames, n in ((1, 1 << 16), (1, 1 << 18), (16, 1 << 18), (128, 1 << 18), (1024, 1 << 18)):
+for frames, n in ((1, 1 << 16), (1, 1 << 18), (16, 1 << 18), (128, 1 << 18), (1024, 1 << 18), (4096, 1 << 16), (512, 1 << 16)):
     x = base[:n].repeat(frames, 1).contiguous()
     y = torch.empty_like(x)
     t_b = timed(lambda: engine.filtfilt_sos(x, sos_b, out=y))
