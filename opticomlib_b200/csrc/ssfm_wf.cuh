@@ -11,6 +11,9 @@
 //   * pass tables and the sincos table are loaded once per CTA; there are no launches, tickets or host
 //     polls inside a propagation, and the step-size controller runs redundantly in every CTA.
 //
+// The same kernel applies an arbitrary transfer function (zero-phase filters, DM): one fixed step with gamma = alpha = 0 and the
+// row phase multiplying by a table (Params::xfer) is  FFT -> x H -> IFFT  in one pass, out of place if Params::field_in is set.
+//
 // Per step each CTA runs a ROW phase (G rows of the N1 x N2 matrix: forward transform, exp(D~ h),
 // inverse transform) and a COLUMN phase (T columns: inverse transform, 1/N, max|A|^2 -> team exchange
 // -> controller -> merged Kerr rotation of the second half step of step s and the first half step of
@@ -21,11 +24,12 @@
 //               barrier inside every cluster plus ONE flag hop between the cluster leaders (4 .. 32 arrivals on the counter in
 //               L2 instead of 32 .. 256, and only the leaders poll); the maxima travel through st.async inside a cluster and as
 //               self-validating words between the leaders.  Launched cooperatively (all clusters of a team must be resident).
-//   CL = true   teams of <= 16 CTAs are thread-block clusters: hardware cluster barrier (arrive.release /
-//               wait.acquire by every thread), per-CTA maxima and the waveform index through distributed shared
-//               memory.  1.4x (fp64) .. 1.6x (fp32) faster per team, but 16-CTA clusters must sit inside one GPC, so
-//               fewer teams are co-resident than the chip has CTA slots;
-//   CL = false  any team size: a monotonic arrival counter in L2 (red.release.gpu / relaxed poll + fence.acq_rel.gpu),
+//   CL          teams of <= 16 CTAs are thread-block clusters: hardware cluster barrier (arrive.release /
+//               wait.acquire by every thread); per-WARP maxima to every CTA of the cluster with st.async, counted by the
+//               destination's mbarrier (no barrier and no fence in the middle of the column phase); the waveform index
+//               through distributed shared memory.  1.4x (fp64) .. 1.6x (fp32) faster per team, but a 16-CTA cluster needs
+//               16 distinct SMs of one GPC, so fewer teams are co-resident than the chip has CTA slots;
+//   TM == 0     any team size: a monotonic arrival counter in L2 (red.release.gpu / relaxed poll + fence.acq_rel.gpu),
 //               maxima as self-validating 64-bit words {value bits | exchange tag}, waveform index through a mailbox
 //               word; launched cooperatively over every CTA slot, or as the second launch that fills the slots the
 //               clusters leave (ssfm_wf.cu).
