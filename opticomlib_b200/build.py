@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "_ssfm_b200.so")
-SOURCES = ["ssfm_api.cu", "ssfm_wf.cu", "filtfilt.cu", "spectrum.cu"]
+SOURCES = ["ssfm_api.cu", "ssfm_wf_f64.cu", "ssfm_wf_f32.cu", "filtfilt.cu", "spectrum.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

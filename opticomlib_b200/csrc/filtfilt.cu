@@ -18,6 +18,13 @@
 //     first and their recursions run on a side stream while the chunks go through (one launch, one wave of
 //     threads, latency-bound: ~0.4 ms that used to sit on the critical path); a last small kernel writes
 //     the exact end samples over the circular ones.
+//   * overlap-save path (any row length >= 4096 when K <= 1024 -- the receiver filters of the reference's examples have
+//     K = 360 .. 850): the zero-phase response is K samples long on either side, so nothing forces a transform of the whole
+//     row.  Every CTA filters ONE block of 4096 samples on its own -- 4096-point transform, x |H|^2, inverse transform, all in
+//     registers and shared memory (fft_core.cuh) -- and keeps the 4096 - 2K samples in the middle, whose circular wrap-around
+//     is below rho^K < 1e-19.  No team of CTAs, no barrier between CTAs, no second pass: HBM sees one read of the input (the
+//     halos of neighbouring blocks hit L2) and one write of the output, and the photodetector square law and the sampler
+//     run in the load and the store of the same kernel (k_ols).  The ends of a row are handled as above.
 //   * sequential path (any other length, or K too large for the row): one thread per
 //     (row, real|imag) walks the whole recursion, same operation order as the SciPy loop.
 #include <algorithm>
@@ -28,6 +35,7 @@
 #include <string>
 
 #include "../../include/ssfm_b200.h"
+#include "fft_core.cuh"
 #include "ssfm_internal.h"
 
 namespace ssfm_filt {
@@ -241,6 +249,149 @@ __global__ void k_scatter_edges(const double2* __restrict__ edge_out, double2* _
     if (out_noise) out_noise[row * m + jj] = v.y;
 }
 
+// ---- overlap-save path: one CTA = one block of OLS_M samples of one row ---------------------------------------------------
+// Block b of a row filters samples [b L - K, b L - K + OLS_M) (indices wrap around the row: only the first and last K outputs of
+// a row see the wrap, and those are replaced by the exact end segments) and stores outputs [b L, (b + 1) L), L = OLS_M - 2 K.
+constexpr int OLS_M = 4096, OLS_E = 16, OLS_NT = OLS_M / OLS_E;
+struct OlsArgs {
+    const double2* x;        // complex rows [rows][n] (pd == 0)
+    PdSrc pd;                // photodetector front end (PD == true)
+    double2* y;              // complex output rows [rows][n], or null:
+    double* out_sig;         //   decimated real outputs [row0 + rows][m]: samples offset, offset + stride, ...
+    double* out_noise;
+    const double2* tw;       // pass tables of the OLS_M-point transform (global memory, L1-resident)
+    const double* h2;        // |H(e^{j 2 pi k / OLS_M})|^2 / OLS_M
+    long long n, row0, offset, stride, m;
+    int K, L, nb;            // halo, outputs per block, blocks per row
+    int wave;                // CTAs resident at once (L2 prefetch distance)
+};
+__global__ void k_fill_h2(double* out, Sos f) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= OLS_M) return;
+    double s, c;
+    sincospi(2.0 * (double)k / (double)OLS_M, &s, &c);          // z^-1 = (c, -s), z^-2 = (c2, -s2)
+    const double c2 = c * c - s * s, s2 = 2.0 * s * c;
+    double g = 1.0 / (double)OLS_M;
+    for (int i = 0; i < f.n_sections; ++i) {
+        const double* q = f.c[i];
+        const double nr = q[0] + q[1] * c + q[2] * c2, ni = -(q[1] * s + q[2] * s2);
+        const double dr = q[3] + q[4] * c + q[5] * c2, di = -(q[4] * s + q[5] * s2);
+        g *= (nr * nr + ni * ni) / (dr * dr + di * di);
+    }
+    out[k] = g;
+}
+template <bool PD>
+__global__ void __launch_bounds__(OLS_NT, 2) k_ols(OlsArgs a) {
+    typedef ssfm::RowExchange<OLS_M, OLS_E> X;
+    extern __shared__ __align__(16) unsigned char ols_smem[];
+    double2* sm = reinterpret_cast<double2*>(ols_smem);
+    const int tid = threadIdx.x;
+    const long long row = blockIdx.x / a.nb;
+    const int b = (int)(blockIdx.x % a.nb);
+    const long long s0 = (long long)b * a.L - a.K;
+    double2 v[OLS_E];
+    if (!PD) {
+#pragma unroll
+        for (int q = 0; q < OLS_E; ++q) {
+            long long i = s0 + tid + q * OLS_NT;
+            i = i < 0 ? i + a.n : (i >= a.n ? i - a.n : i);
+            v[q] = a.x[row * a.n + i];
+        }
+        // the block that this CTA slot runs next (one grid wave ahead) goes to L2 while this one computes
+        const long long ahead = (long long)blockIdx.x + a.wave;
+        if ((tid & 7) == 0 && ahead < (long long)gridDim.x) {
+            const long long r2 = ahead / a.nb, st2 = (ahead % a.nb) * (long long)a.L - a.K;
+#pragma unroll
+            for (int q = 0; q < OLS_E; ++q) {
+                const long long i = st2 + tid + q * OLS_NT;
+                if (i >= 0 && i < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + r2 * a.n + i));
+            }
+        }
+    } else {
+        // square law and beat terms of pd_sample(), four samples at a time with their loads issued together (one sample at
+        // a time the block waits for 16 dependent trips to memory)
+        const PdSrc& s = a.pd;
+        const long long r = a.row0 + row;
+        if (!s.noise) {                                                 // no optical noise: the 16 loads of a polarisation together
+            long long idx[OLS_E];
+            double sig[OLS_E];
+#pragma unroll
+            for (int q = 0; q < OLS_E; ++q) {
+                const long long i = s0 + tid + q * OLS_NT;
+                idx[q] = i < 0 ? i + a.n : (i >= a.n ? i - a.n : i);
+                sig[q] = 0.0;
+            }
+            for (int p = 0; p < s.n_pol; ++p) {
+                const double2* fp = s.field + (r * s.n_pol + p) * a.n;
+                double2 e[OLS_E];
+#pragma unroll
+                for (int q = 0; q < OLS_E; ++q) e[q] = fp[idx[q]];
+#pragma unroll
+                for (int q = 0; q < OLS_E; ++q) sig[q] += e[q].x * e[q].x + e[q].y * e[q].y;
+            }
+#pragma unroll
+            for (int q = 0; q < OLS_E; ++q) {
+                v[q].x = s.r_load * (s.r * sig[q]);
+                v[q].y = s.noise_out ? s.r_load * (s.r * 0.0 + (s.extra ? s.extra[r * a.n + idx[q]] : 0.0) + s.i_dark) : 0.0;
+            }
+        } else
+#pragma unroll
+        for (int q0 = 0; q0 < OLS_E; q0 += 4) {
+            long long idx[4];
+            double sig[4] = {0.0, 0.0, 0.0, 0.0}, noi[4] = {0.0, 0.0, 0.0, 0.0}, ex[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                long long i = s0 + tid + (q0 + k) * OLS_NT;
+                idx[k] = i < 0 ? i + a.n : (i >= a.n ? i - a.n : i);
+            }
+            if (s.extra && s.noise_out) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ex[k] = s.extra[r * a.n + idx[k]];
+            }
+            for (int p = 0; p < s.n_pol; ++p) {
+                const double2* fp = s.field + (r * s.n_pol + p) * a.n;
+                double2 e[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) e[k] = fp[idx[k]];
+                if (s.noise) {
+                    const double2* zp = s.noise + (r * s.n_pol + p) * a.n;
+                    double2 z[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) z[k] = zp[idx[k]];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) noi[k] += 2.0 * (e[k].x * z[k].x + e[k].y * z[k].y) + (z[k].x * z[k].x + z[k].y * z[k].y);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sig[k] += e[k].x * e[k].x + e[k].y * e[k].y;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[q0 + k].x = s.r_load * (s.r * sig[k]);
+                v[q0 + k].y = s.noise_out ? s.r_load * (s.r * noi[k] + ex[k] + s.i_dark) : 0.0;
+            }
+        }
+    }
+    ssfm::fft_passes<double, OLS_M, -1, X, OLS_E>::run(v, sm, a.tw, tid);
+#pragma unroll
+    for (int q = 0; q < OLS_E; ++q) {
+        const double g = __ldg(a.h2 + tid + q * OLS_NT);
+        v[q].x *= g; v[q].y *= g;
+    }
+    ssfm::fft_passes<double, OLS_M, +1, X, OLS_E>::run(v, sm, a.tw, tid);
+#pragma unroll
+    for (int q = 0; q < OLS_E; ++q) {
+        const int j = tid + q * OLS_NT;
+        const long long pos = s0 + j;
+        if (j < a.K || j >= a.K + a.L || pos >= a.n) continue;
+        if (!PD || a.y) { a.y[row * a.n + pos] = v[q]; continue; }
+        if (pos < a.offset || (pos - a.offset) % a.stride) continue;
+        const long long jj = (pos - a.offset) / a.stride;
+        if (jj >= a.m) continue;
+        a.out_sig[(a.row0 + row) * a.m + jj] = v[q].x;
+        if (a.out_noise) a.out_noise[(a.row0 + row) * a.m + jj] = v[q].y;
+    }
+}
+
 // Philox4x32-10 counter-based generator + Box-Muller: N(0, 1) doubles, reproducible from (seed, element index) alone,
 // whatever the launch geometry (the reference draws its noise from NumPy's global stream: devices.py:933, 1523, 1527 --
 // a device-side generator can only be validated statistically).
@@ -339,6 +490,22 @@ long long chunk_rows(long long rows, long long n, int device) {
     return std::max<long long>(1, std::min(rows, best));
 }
 
+constexpr size_t OLS_SMEM = sizeof(double2) * (size_t)ssfm::RowExchange<OLS_M, OLS_E>::size;
+// pass tables of the OLS_M-point transform, one copy per device (64 KB, read through L1 by k_ols: measured on B200, a folded
+// 8 KB table of the unit circle in shared memory was slower -- BPF of 1024 x 2^18 samples 3.84 against 3.47 ms)
+const double2* ols_tables(int device, cudaStream_t st) {
+    static std::mutex mu;
+    static void* tab[64] = {nullptr};
+    std::lock_guard<std::mutex> lock(mu);
+    void*& t = tab[(device >= 0 && device < 64) ? device : 0];
+    if (!t) {
+        if (ssfm_internal_pass_tables_f64(&t, OLS_M, st) != SSFM_OK) { t = nullptr; return nullptr; }
+        cudaFuncSetAttribute(k_ols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OLS_SMEM);
+        cudaFuncSetAttribute(k_ols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OLS_SMEM);
+    }
+    return (const double2*)t;
+}
+
 // The whole zero-phase filter of `rows` rows of n samples.  Source: complex rows x (pd == null) or the photodetector
 // front end *pd; destination: complex rows y (may alias x), or -- out_sig != null -- real rows out_sig / out_noise
 // holding samples offset, offset + stride, ... (m per row).  `y` is then a scratch buffer of >= chunk rows.
@@ -352,7 +519,12 @@ int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, doub
     if (rho > 0 && rho < 1) K = (long long)std::ceil(1.3 * std::log(1e-19) / std::log(rho)) + 64;
     else if (rho == 0) K = 64;
     const bool pow2 = (n & (n - 1)) == 0 && n >= 256 && n <= (1ll << 22);
-    const bool fft_path = pow2 && K > 0 && 4 * K + 2 * f.edge <= n && !getenv("SSFM_FILTFILT_SEQUENTIAL");
+    const bool ends_fit = K > 0 && 4 * K + 2 * f.edge <= n && !getenv("SSFM_FILTFILT_SEQUENTIAL");
+    // overlap-save (k_ols): blocks of 4096 samples with a halo of Kp >= K on either side, any row length; taken while at
+    // least half of every block is output (Kp <= 1024)
+    const long long Kp = (K + 7) & ~7ll;
+    const bool ols = ends_fit && Kp <= 1024 && n >= OLS_M && !getenv("SSFM_FILTFILT_NO_OLS");
+    const bool fft_path = ends_fit && (pow2 || ols);
     const bool real_out = out_sig != nullptr;
     // rows of 2^12 .. 2^20 samples go through the persistent kernel in ONE launch (it keeps the rows in flight L2-resident by
     // itself; at most 8 GiB of packed rows at a time); other lengths through the three streaming kernels in L2-sized chunks
@@ -360,9 +532,10 @@ int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, doub
     // one launch against 0.48 ms in chunks, 1024 rows 8.3 against 11.2 ms -- so the one-launch path starts at 2^25 samples)
     // (the photodetector path packs the whole batch first, which costs it the chunks' L2 residency: 128 rows of 2^18 take 2.06 ms
     // in one launch against 1.75 ms in chunks, 1024 rows 10.1 against 12.4 ms -- its threshold is 2^27 samples)
-    const bool one_launch = fft_path && n >= 4096 && n <= (1ll << 20) && rows * n >= (pd ? (1ll << 27) : (1ll << 25)) &&
+    const bool one_launch = fft_path && !ols && n >= 4096 && n <= (1ll << 20) && rows * n >= (pd ? (1ll << 27) : (1ll << 25)) &&
                             !getenv("SSFM_TRANSFER_MULTILAUNCH");
     const long long chunk = !fft_path ? rows
+                          : ols ? std::max<long long>(1, std::min<long long>(rows, (long long)((32u << 20) / (16 * (size_t)n))))
                           : one_launch ? std::max<long long>(1, std::min<long long>(rows, (long long)((8ull << 30) / (16 * (size_t)n))))
                                        : chunk_rows(rows, n, device);
 
@@ -376,7 +549,9 @@ int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, doub
     };
     auto cuda_fail = [&](cudaError_t err) { cleanup(); ssfm_err_slot = std::string("filtfilt: ") + cudaGetErrorString(err); return SSFM_ERR_CUDA; };
 
-    if (real_out || (!fft_path && pd)) {               // packed rows live in a scratch buffer (one chunk; all rows on the sequential path)
+    const bool in_place = !pd && !real_out && (const void*)x == (const void*)y;
+    if (ols ? in_place : (real_out || (!fft_path && pd))) {   // packed rows live in a scratch buffer (one chunk; all rows on the sequential
+                                                       // path); overlap-save needs one only in place (blocks read their neighbours' halos)
         e = cudaMallocAsync((void**)&scratch, sizeof(double2) * (size_t)chunk * n, st);
         if (e != cudaSuccess) return cuda_fail(e);
     }
@@ -400,8 +575,42 @@ int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, doub
             cudaEventRecord(sd.join, sd.st);
         }
         void* plan = nullptr;
+        if (ols) {
+            const double2* tw = ols_tables(device, st);
+            double* h2 = nullptr;
+            if (!tw) rc = SSFM_ERR_CUDA;
+            if (!rc && (e = cudaMallocAsync((void**)&h2, sizeof(double) * OLS_M, st)) != cudaSuccess) { cudaStreamWaitEvent(st, sd.join, 0); return cuda_fail(e); }
+            if (!rc) {
+                k_fill_h2<<<OLS_M / 256, 256, 0, st>>>(h2, f);
+                OlsArgs a{};
+                a.tw = tw; a.h2 = h2; a.n = n; a.offset = offset; a.stride = stride; a.m = m;
+                a.K = (int)Kp; a.L = OLS_M - 2 * (int)Kp; a.nb = (int)((n + a.L - 1) / a.L);
+                const size_t smem = OLS_SMEM;
+                {
+                    int sms = 148;
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+                    a.wave = 2 * sms;
+                }
+                const long long per = in_place ? chunk : std::max<long long>(1, std::min<long long>(rows, (long long)(0x7fffffffll / a.nb)));
+                for (long long r0 = 0; r0 < rows; r0 += per) {
+                    const long long nr = std::min(per, rows - r0);
+                    a.row0 = r0;
+                    if (pd) {
+                        a.pd = *pd; a.y = nullptr; a.out_sig = out_sig; a.out_noise = out_noise;
+                        k_ols<true><<<(unsigned)(nr * a.nb), OLS_NT, smem, st>>>(a);
+                    } else {
+                        a.x = x + (size_t)r0 * n; a.y = in_place ? scratch : y + (size_t)r0 * n;
+                        k_ols<false><<<(unsigned)(nr * a.nb), OLS_NT, smem, st>>>(a);
+                        if (in_place) cudaMemcpyAsync(y + (size_t)r0 * n, scratch, sizeof(double2) * (size_t)nr * n, cudaMemcpyDeviceToDevice, st);
+                    }
+                }
+                e = cudaGetLastError();
+                cudaFreeAsync(h2, st);
+                if (e != cudaSuccess) { cudaStreamWaitEvent(st, sd.join, 0); return cuda_fail(e); }
+            }
+        } else
         rc = ssfm_internal_transfer_prepare(device, n, chunk, f, &plan, st);
-        for (long long r0 = 0; r0 < rows && !rc; r0 += chunk) {
+        for (long long r0 = 0; r0 < rows && !rc && !ols; r0 += chunk) {
             const long long nr = std::min(chunk, rows - r0);
             double2* buf = real_out ? scratch : y + (size_t)r0 * n;
             const double2* src = nullptr;

@@ -155,6 +155,8 @@ struct ssfm_plan_s {
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
     int placement = -1;          // k_wf: SM-aware team placement (-1 = auto)
     void* dim_tab = nullptr;     // k_wf: imag(D~) per bin (transposed order), refilled by every propagation
+    void* tstash = nullptr;      // k_wf, multi-tile cluster teams: Kerr phase of the waveforms in flight (allocated on first use)
+    size_t tstash_bytes = 0;
     int async_mode = 0;          // 1: ssfm_propagate returns once the persistent kernel is enqueued (host pipelines)
     int cluster = -1;            // k_wf: teams as thread-block clusters (-1 = auto, 0 = never, 1 = always when possible)
     void* wf_sync = nullptr;     // k_wf barriers / mailboxes / max words
@@ -445,6 +447,17 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         l.budget = budget; l.teams_cap = pl->teams_cap; l.placement = pl->placement; l.cluster = pl->cluster;
         l.ev0 = pl->wf_ev[0]; l.ev1 = pl->wf_ev[1];
         l.side = pl->wf_side; l.ev_side = pl->wf_ev_side;
+        {   // waveforms of 32 .. 64 tiles without adaptive step control run as 16-CTA clusters with several tiles per CTA
+            const long long units = (long long)pl->n_pol * (pl->n / 4096);
+            if ((fixed || single) && p.has_nl && units > 16 && units <= 64 && pl->n <= (1ll << 18) && pl->cluster != 0) {
+                if (!pl->tstash) {
+                    const size_t bytes = (size_t)16 * (size_t)units * 4096 * sizeof(R);
+                    if (cudaMalloc(&pl->tstash, bytes) == cudaSuccess) pl->tstash_bytes = bytes;
+                    else { (void)cudaGetLastError(); pl->tstash = nullptr; }
+                }
+                l.tstash = pl->tstash; l.tstash_bytes = pl->tstash_bytes;
+            }
+        }
         int teams = 0;
         const int rc = wf_propagate<R>(p, l, &teams, st);
         if (rc == SSFM_OK) {
@@ -893,7 +906,7 @@ int ssfm_plan_destroy(ssfm_plan_t pl) {
     cudaFree(pl->wb); cudaFree(pl->wtab); cudaFree(pl->xf_fwd); cudaFree(pl->xf_inv);
     for (int r = 0; r < 8; ++r)
         if (pl->peer_base[r] && pl->peer_base[r] != pl->xbuf) cudaIpcCloseMemHandle(pl->peer_base[r]);
-    cudaFree(pl->xbuf); cudaFree(pl->d_peer_flags); cudaFree(pl->dim_tab);
+    cudaFree(pl->xbuf); cudaFree(pl->d_peer_flags); cudaFree(pl->dim_tab); cudaFree(pl->tstash);
     if (pl->peek_stream) cudaStreamDestroy(pl->peek_stream);
     if (pl->peek_host) cudaFreeHost(pl->peek_host);
     if (pl->wf_side) cudaStreamDestroy(pl->wf_side);

@@ -32,7 +32,7 @@
 //   TM == 0     any team size: a monotonic arrival counter in L2 (red.release.gpu / relaxed poll + fence.acq_rel.gpu),
 //               maxima as self-validating 64-bit words {value bits | exchange tag}, waveform index through a mailbox
 //               word; launched cooperatively over every CTA slot, or as the second launch that fills the slots the
-//               clusters leave (ssfm_wf.cu).
+//               clusters leave (ssfm_wf_impl.inl).
 //
 // Tried and dropped (measured on B200): letting a team multiplex two or three waveforms
 // ("slots") so that it runs a phase of waveform B while the barrier of waveform A completes.  The barrier waits
@@ -62,6 +62,7 @@ struct WfArgs {
     int n_teams;
     int fixed, single, resume;
     R h_fixed;
+    R* tstash;                    // TM == 3: Kerr phase of the waveforms in flight, [n_teams][units][16][256] (L2-resident)
 };
 
 __host__ __device__ constexpr int wf_cmax(int a, int b) { return a > b ? a : b; }
@@ -96,6 +97,9 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 enum { WF_GRAB = 0, WF_ROW = 1, WF_COL = 2, WF_END = 3 };
+#ifndef SSFM_WF_CTAS_F32
+#define SSFM_WF_CTAS_F32 3      // resident CTAs per SM asked of the compiler for complex64 (80 registers per thread)
+#endif
 
 // State of the team's current waveform, uniform over the CTA and over the team.  Its home is SHARED memory (two versions,
 // written by thread 0 before a team barrier and read by everyone after it): carried in registers across a phase it gets
@@ -150,9 +154,9 @@ __device__ __forceinline__ void st_async_u64(void* local_slot, unsigned long lon
 // (arrive.release / wait.acquire, executed by every thread), the per-CTA maxima and the waveform index travel through
 // distributed shared memory, and no cooperative launch, registration or global-memory flag is needed.
 template <typename R, int M1, int M2, bool SMALL, int TM>
-__global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> p, WfArgs<R> a) {
+__global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) k_wf(Params<R> p, WfArgs<R> a) {
     typedef typename cx_of<R>::type C;
-    constexpr bool CL = (TM == 1), MC = (TM == 2);
+    constexpr bool CL = (TM == 1 || TM == 3), MC = (TM == 2), MT = (TM == 3);
     typedef wf_geom<R, M1, M2> GEO;
     constexpr int E = GEO::E, NT = GEO::NT, T = GEO::T, G = GEO::G, PM = GEO::PM;
     static_assert(points_per_thread<R>::value == 16, "k_wf assumes 16 points per thread");
@@ -174,7 +178,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
     const int tid = threadIdx.x;
     constexpr int tiles = M2 / T;                              // column tiles (= row groups) per polarisation (p.n2 == M2, p.n == M1*M2)
     constexpr int NN = M1 * M2;
-    const unsigned total = (unsigned)(tiles * p.n_pol);        // CTAs per team
+    const unsigned units = (unsigned)(tiles * p.n_pol);        // 4096-point tiles of one waveform
+    unsigned total = units;                                    // CTAs per team (TM == 3: the cluster size, set below)
 
     // ---- team placement.  A team is bulk-synchronous, so its CTAs should run at the same speed, and a CTA's
     // speed depends on what the OTHER CTAs of its SM are doing.  The grid fills every CTA slot of the chip; each
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
         if (CL) {
             team = (int)cluster_id_x();
             me = (int)crank;
+            if (MT) total = csz;                               // every CTA carries units / csz tiles through each phase
         } else {
             ncl = total / csz;
             team = (int)(cluster_id_x() / ncl);
@@ -465,6 +471,53 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                     if (cs.done) { grab_fence(); continue; }    // stays in WF_GRAB: next waveform
                     z0 = (R)cs.z; h_first = (R)cs.h; steps0 = cs.steps;
                 }
+                if constexpr (MT) {
+                    // several tiles per CTA (fixed step or one step only: the host never picks this variant for adaptive
+                    // step control, whose maximum would have to be known before any tile's Kerr rotation)
+                    if (!a.resume) {
+                        const R h0 = a.fixed ? a.h_fixed : p.length;
+                        h_first = (p.length < h0) ? p.length : h0;
+                        const int done0 = !((R)0 < p.length) || a.budget <= 0;
+                        if (me == 0 && tid == 0) {
+                            Ctrl& cs = p.ctrl[w];
+                            cs.z = 0.0; cs.h = (double)h_first; cs.pmax = 0ull; cs.steps = 0; cs.arrived = 0u; cs.done = !((R)0 < p.length);
+                        }
+                        if (done0) { grab_fence(); continue; }
+                    }
+                    if (tid == 0) {
+                        WfShared<R>& o = sh[(ver ^ 1u) & 1u];
+                        o.w = w; o.xchg = xchg; o.steps = steps0; o.taken = 0; o.z = z0; o.h = h_first;
+                    }
+                    ver ^= 1u;
+                    const R hh = h_first / (R)2;
+#pragma unroll 1
+                    for (unsigned u = (unsigned)me; u < units; u += total) {
+                        const int un2 = (int)(u % (unsigned)tiles) * T + c;
+                        C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + u / (unsigned)tiles) * NN;
+                        const C* __restrict__ inp = p.field_in ? p.field_in + ((size_t)w * p.n_pol + u / (unsigned)tiles) * NN : rowp;
+                        R* __restrict__ ts = a.tstash + ((size_t)team * units + u) * (size_t)(E * NT);
+                        C v[E];
+#pragma unroll
+                        for (int q = 0; q < E; ++q) v[q] = __ldcg(inp + (size_t)(t + q * (M1 / E)) * M2 + un2);
+                        if (p.has_nl) {
+#pragma unroll
+                            for (int q = 0; q < E; ++q) {
+                                const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                                const R ph = mul_rn(hh, mul_rn(p.gamma, pw));
+                                ts[q * NT + tid] = ph;
+                                R sn, co; kerr_sincos<SMALL>(ph, sct, &sn, &co);
+                                v[q] = cmul(v[q], mk<R>(co, sn));
+                            }
+                        }
+                        fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                        apply_fourstep<false, R, E, M1>(p, v, un2, t);
+#pragma unroll
+                        for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
+                    }
+                    bar_arrive();
+                    state = WF_ROW;
+                    continue;
+                }
                 C* __restrict__ rowp = p.field + ((size_t)w * p.n_pol + pol) * NN;
                 const C* __restrict__ inp = p.field_in ? p.field_in + ((size_t)w * p.n_pol + pol) * NN : rowp;   // out-of-place transfer
                 C v[E];
@@ -525,6 +578,38 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
                 bar_wait();
                 WF_ACC(0, t_r0);
                 const WfShared<R> S = sh_read(ver);
+                if constexpr (MT) {
+                    const R h = S.h;
+#pragma unroll 1
+                    for (unsigned u = (unsigned)me; u < units; u += total) {
+                        const int uk1 = (int)(u % (unsigned)tiles) * G + g;
+                        C* __restrict__ rbase = p.field + ((size_t)S.w * p.n_pol + u / (unsigned)tiles) * NN + (size_t)uk1 * M2;
+                        C v[E];
+#pragma unroll
+                        for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
+                        fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+                        if (p.xfer) {
+                            const C* __restrict__ hrow = p.xfer + (size_t)uk1 * M2;
+#pragma unroll
+                            for (int q = 0; q < E; ++q) v[q] = cmul(v[q], __ldg(hrow + tr + q * (M2 / E)));
+                        } else {
+                            const R* __restrict__ drow = p.dim_tab + (size_t)uk1 * M2;
+#pragma unroll
+                            for (int q = 0; q < E; ++q) {
+                                const R ph = mul_rn(__ldg(drow + tr + q * (M2 / E)), h);
+                                R sn, co; sincos_r(ph, sct, &sn, &co);
+                                v[q] = cmul(v[q], mk<R>(co, sn));
+                            }
+                        }
+                        fft_passes<R, M2, +1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+#pragma unroll
+                        for (int q = 0; q < E; ++q) rbase[tr + q * (M2 / E)] = v[q];
+                    }
+                    bar_arrive();
+                    state = WF_COL;
+                    WF_ACC(1, t_r0);
+                    continue;
+                }
                 C* __restrict__ rbase = p.field + ((size_t)S.w * p.n_pol + pol) * NN + (size_t)k1 * M2;
                 const R h = S.h;
                 C v[E];
@@ -558,6 +643,84 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : 3)) k_wf(Params<R> 
             bar_wait();
             WF_ACC(2, t_c0);
             const WfShared<R> S = sh_read(ver);
+            if constexpr (MT) {
+                const R z = S.z, h = S.h;
+                const int steps = S.steps;
+                xchg = S.xchg;
+                const CtrlNext<R> nx = controller_next<R>(p, z, h, steps, (R)0);   // (no step control here: h stays, or the one step ends)
+                const long long taken = S.taken + 1;
+#ifdef SSFM_WF_PROFILE
+                ++pn;
+#endif
+                const bool stop = nx.done || taken >= a.budget;
+                if (me == 0 && tid == 0) {
+                    Ctrl& cs = p.ctrl[S.w];
+                    if (p.hlog && steps < p.hlog_cap) p.hlog[(size_t)S.w * p.hlog_cap + steps] = (double)h;
+                    cs.z = (double)nx.z; cs.h = (double)nx.h; cs.steps = steps + 1; cs.done = nx.done;
+                }
+                const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h));
+                const R hh = nx.h / (R)2;
+#pragma unroll 1
+                for (unsigned u = (unsigned)me; u < units; u += total) {
+                    const int un2 = (int)(u % (unsigned)tiles) * T + c;
+                    C* __restrict__ rowp = p.field + ((size_t)S.w * p.n_pol + u / (unsigned)tiles) * NN;
+                    R* __restrict__ ts = a.tstash + ((size_t)team * units + u) * (size_t)(E * NT);
+                    C v[E];
+#pragma unroll
+                    for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + un2);
+                    if (p.has_nl) {                                 // the tile's Kerr phase: global -> shared behind the inverse transforms
+#pragma unroll                                                      // (every thread copies and reads its own entries only)
+                        for (int q = 0; q < E; ++q) cp_async<sizeof(R)>(&st_sm[q * NT + tid], ts + q * NT + tid);
+                        cp_async_commit();
+                    }
+                    apply_fourstep<true, R, E, M1>(p, v, un2, t);
+                    fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+#pragma unroll
+                    for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
+                    if (p.has_nl) cp_async_wait_all();
+                    if (stop) {
+#pragma unroll
+                        for (int q = 0; q < E; ++q) {
+                            if (p.has_nl) {
+                                R sn, co; kerr_sincos<SMALL>(st_sm[q * NT + tid], sct, &sn, &co);
+                                v[q] = cmul(v[q], mk<R>(co, sn));
+                            }
+                            rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
+                        }
+                        continue;
+                    }
+                    if (p.has_nl) {
+#pragma unroll
+                        for (int q = 0; q < E; ++q) {
+                            const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                            const R ph = mul_rn(hh, mul_rn(p.gamma, pw));
+                            const R tot = st_sm[q * NT + tid] + ph;
+                            ts[q * NT + tid] = ph;
+                            R sn, co; kerr_sincos<SMALL>(tot, sct, &sn, &co);
+                            v[q] = cmul(v[q], mk<R>(co, sn));
+                        }
+                    }
+                    fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                    apply_fourstep<false, R, E, M1>(p, v, un2, t);
+#pragma unroll
+                    for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
+                }
+                if (stop) {
+                    if (tid == 0) sh[ver & 1u].xchg = xchg;
+                    state = WF_GRAB;
+                    WF_ACC(4, t_c0);
+                    continue;
+                }
+                if (tid == 0) {
+                    WfShared<R>& o = sh[(ver ^ 1u) & 1u];
+                    o.w = S.w; o.xchg = xchg; o.steps = steps + 1; o.taken = taken; o.z = nx.z; o.h = nx.h;
+                }
+                ver ^= 1u;
+                bar_arrive();
+                state = WF_ROW;
+                WF_ACC(4, t_c0);
+                continue;
+            }
             C* __restrict__ rowp = p.field + ((size_t)S.w * p.n_pol + pol) * NN;
             const R z = S.z, h = S.h;
             const int steps = S.steps;

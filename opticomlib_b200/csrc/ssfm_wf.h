@@ -1,4 +1,4 @@
-// Host-side interface of the persistent whole-propagation kernel (ssfm_wf.cuh / ssfm_wf.cu).
+// Host-side interface of the persistent whole-propagation kernel (ssfm_wf.cuh / ssfm_wf_impl.inl).
 #pragma once
 #include <cuda_runtime.h>
 #include "ssfm_kernels.cuh"
@@ -19,6 +19,8 @@ struct WfLaunch {
     cudaStream_t side;       // side stream + event for the launch that fills the CTA slots the clusters leave (may be null)
     cudaEvent_t ev_side;
     cudaEvent_t ev0, ev1;    // recorded around the launch on the stream (may be null)
+    void* tstash;            // multi-tile cluster teams: Kerr phase of the waveforms in flight (may be null: variant not used)
+    size_t tstash_bytes;
 };
 constexpr size_t WF_SYNC_BYTES = 1u << 20;
 

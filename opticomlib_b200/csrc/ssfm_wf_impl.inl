@@ -1,4 +1,5 @@
-// Launch side of the persistent whole-propagation kernel k_wf (ssfm_wf.cuh).
+// Launch side of the persistent whole-propagation kernel k_wf (ssfm_wf.cuh).  Included by ssfm_wf_f32.cu and ssfm_wf_f64.cu
+// (one translation unit per precision: the instantiations compile in parallel), with SSFM_WF_REAL = float | double.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
 #include <atomic>
@@ -98,6 +99,101 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
         b.n_teams = (int)fill;
         WF_TRY(cudaStreamWaitEvent(l.side, l.ev0, 0));
         k_wf<R, M1, M2, SMALL, 0><<<(unsigned)(fill * total), GEO::NT, GEO::smem, l.side>>>(p, b);
+        WF_TRY(cudaGetLastError());
+        WF_TRY(cudaEventRecord(l.ev_side, l.side));
+        WF_TRY(cudaStreamWaitEvent(st, l.ev_side, 0));
+        ++ssfm_launches;
+    }
+    if (l.ev1) WF_TRY(cudaEventRecord(l.ev1, st));
+    if (teams_out) *teams_out = (int)(teams + fill);
+    return SSFM_OK;
+}
+
+// cluster teams with SEVERAL tiles per CTA (waveforms of 32 .. 64 tiles: 2^17, 2^18 samples, or 2^16 / 2^17 with two polarisations;
+// fixed step, one step, or a transfer function -- no adaptive step control): a team is ONE cluster of 16 CTAs whatever the
+// waveform length, every CTA carries units/16 tiles through each phase, and the team barrier is the hardware cluster barrier
+// instead of 64 arrivals on a counter in L2 (measured on B200: 64-CTA flag-based teams spend ~40 % of a step in their two
+// barriers).  The Kerr phase of the tiles in flight lives in a small L2-resident buffer (WfLaunch::tstash) instead of shared
+// memory.  The CTA slots that 16-CTA clusters cannot use (a cluster needs 16 SMs of one GPC: 14 clusters fit) are filled by one
+// launch of flag-based teams drawing from the same waveform counter, as in wf_launch_cluster.
+template <typename R, int M1, int M2, bool SMALL>
+int wf_launch_mt(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st, int coop_ctas) {
+    typedef wf_geom<R, M1, M2> GEO;
+    constexpr int CS = 16;
+    auto kern = k_wf<R, M1, M2, SMALL, 3>;
+    const long long units = (long long)p.n_pol * (p.n2 / GEO::T);
+    if (units <= CS || units % CS || (p.has_nl && !l.tstash)) return SSFM_ERR_UNSUPPORTED;
+    static int max_clusters_dev[64];
+    static bool init = false;
+    if (!init) { for (int& v : max_clusters_dev) v = 0; init = true; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& max_clusters = max_clusters_dev[(dev >= 0 && dev < 64) ? dev : 0];
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(GEO::NT); cfg.dynamicSmemBytes = GEO::smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (max_clusters == 0) {
+        WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
+        WF_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cfg.gridDim = dim3((unsigned)(CS * 64));
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+        max_clusters = n > 0 ? n : -1;
+    }
+    long long teams = max_clusters;
+    const size_t per_team = (size_t)units * 4096 * sizeof(R);
+    if (p.has_nl && teams > (long long)(l.tstash_bytes / per_team)) teams = (long long)(l.tstash_bytes / per_team);
+    if (getenv("SSFM_DEBUG"))
+        fprintf(stderr, "[ssfm] k_wf multi-tile cluster<%d,%d,%d>: %lld tiles per waveform, %d per CTA, %lld clusters\n", (int)sizeof(R), M1, M2,
+                units, (int)(units / CS), teams);
+    if (teams < 1) return SSFM_ERR_UNSUPPORTED;
+    // small batches keep more of the chip busy with flag-based teams (units CTAs per waveform instead of 16)
+    if (l.cluster < 1 && p.batch * CS * 14 < (long long)coop_ctas * 10 && p.batch < teams) return SSFM_ERR_UNSUPPORTED;
+    long long fill = (l.side && l.ev_side && l.ev0) ? (coop_ctas - teams * CS) / units : 0;   // flag-based teams in the free slots
+    if (teams > p.batch) teams = p.batch;
+    if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
+    if (fill > p.batch - teams) fill = p.batch - teams;
+    if (l.teams_cap > 0 && fill > l.teams_cap - teams) fill = l.teams_cap - teams;
+    if (getenv("SSFM_MT_NOFILL")) fill = 0;
+    const size_t head = 4096 + 256;
+    const size_t need = head + (size_t)fill * 256 + (size_t)fill * 2 * units * 16;
+    if (need > WF_SYNC_BYTES) fill = 0;
+    WF_TRY(cudaMemsetAsync(l.sync_buf, 0, fill > 0 ? need : head, st));
+    WfArgs<R> a;
+    std::memset(&a, 0, sizeof(a));
+    char* sb = (char*)l.sync_buf;
+    a.next_wf = (unsigned int*)(sb + 4096 + 128);
+    a.budget = l.budget;
+    a.n_teams = (int)teams;
+    a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
+    a.h_fixed = (R)l.h_fixed;
+    a.occ = 1; a.placement = 0;
+    a.tstash = (R*)l.tstash;
+    cfg.gridDim = dim3((unsigned)(teams * CS));
+    if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
+    WF_TRY(cudaLaunchKernelEx(&cfg, kern, p, a));
+    ++ssfm_launches;
+    if (fill > 0) {
+        auto kfill = k_wf<R, M1, M2, SMALL, 0>;
+        static bool fill_attr[64] = {false};
+        if (!fill_attr[(dev >= 0 && dev < 64) ? dev : 0]) {
+            WF_TRY(cudaFuncSetAttribute(kfill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
+            fill_attr[(dev >= 0 && dev < 64) ? dev : 0] = true;
+        }
+        WfArgs<R> b = a;
+        b.tstash = nullptr;
+        b.sm_cnt = (unsigned int*)sb;
+        b.grid_bar = (unsigned int*)(sb + 4096);
+        b.bar = (unsigned int*)(sb + head);
+        b.mail = (unsigned long long*)(sb + head + (size_t)fill * 128);
+        b.slots = (unsigned long long*)(sb + head + (size_t)fill * 256);
+        b.n_teams = (int)fill;
+        WF_TRY(cudaStreamWaitEvent(l.side, l.ev0, 0));
+        kfill<<<(unsigned)(fill * units), GEO::NT, GEO::smem, l.side>>>(p, b);
         WF_TRY(cudaGetLastError());
         WF_TRY(cudaEventRecord(l.ev_side, l.side));
         WF_TRY(cudaStreamWaitEvent(st, l.ev_side, 0));
@@ -211,6 +307,12 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
             if (rc != SSFM_ERR_UNSUPPORTED) return rc;
         }
     }
+    if constexpr (M1 * M2 >= (1 << 16) && M1 * M2 <= (1 << 18)) {        // 32 .. 64 tiles per waveform, no adaptive step control
+        if (l.cluster != 0 && (l.fixed || l.single) && total > 16 && total <= 64 && !getenv("SSFM_NO_MT")) {
+            const int rc = wf_launch_mt<R, M1, M2, SMALL>(p, l, teams_out, st, per_sm * l.num_sms);
+            if (rc != SSFM_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if constexpr (M1 * M2 >= (1 << 16)) {                                // (2^16 with two polarisations, 2^17 .. 2^20)
         // measured on B200 (scripts/exp_mc.py): one 2^20-sample waveform, fp32: 4.97 ms against 6.18 ms with flag-based teams
         // (+24 %); fp64: 7.57 against 7.40 ms (its phases are longer, the barrier is a smaller share, and clusters of 8 leave the
@@ -276,7 +378,6 @@ int wf_propagate(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStre
     return SSFM_ERR_UNSUPPORTED;
 }
 
-template int wf_propagate<float>(const Params<float>&, const WfLaunch&, int*, cudaStream_t);
-template int wf_propagate<double>(const Params<double>&, const WfLaunch&, int*, cudaStream_t);
+template int wf_propagate<SSFM_WF_REAL>(const Params<SSFM_WF_REAL>&, const WfLaunch&, int*, cudaStream_t);
 
 }  // namespace ssfm

@@ -152,3 +152,57 @@ def test_dm_matches_reference_output(ob):
         w = np.fft.fftfreq(n, ob.gv.dt) * 2 * np.pi
         ref = np.fft.ifft(np.fft.fft(x, axis=-1) * np.exp(1j * w ** 2 * (2500.0 * 1e-12 ** 2) / 2), axis=-1)
         assert rel_l2(out.signal, ref) <= 1e-12
+
+
+@pytest.mark.parametrize("n_samples", [1 << 16, 60001, 4096, 5000])
+def test_overlap_save_blocks_match_scipy_and_the_team_kernels(ob, monkeypatch, n_samples):
+    """Rows of >= 4096 samples are filtered block by block (k_ols: 4096-sample blocks with a halo of K samples, any row
+    length): against SciPy, against the whole-row transform path (power-of-two rows) and in place; a filter too narrow for
+    the blocks (K > 1024) must still take the older paths and agree."""
+    import torch
+    from scipy import signal as sg
+    from opticomlib_b200 import engine
+    rng = np.random.default_rng(n_samples)
+    rows = 5
+    x = rng.standard_normal((rows, n_samples)) + 1j * rng.standard_normal((rows, n_samples)) + (0.7 - 0.2j)
+    for order, bw in ((4, 7.5e9), (4, 20e9), (5, 30e9), (1, 10e9)):
+        sos = bessel_sos(order, bw, 640e9)
+        ref = sg.sosfiltfilt(sos, x, axis=-1)
+        monkeypatch.delenv("SSFM_FILTFILT_NO_OLS", raising=False)
+        a = ob.filtfilt_batch(x, sos)
+        assert rel_l2(a, ref) <= 1e-12
+        assert np.abs(a - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+        monkeypatch.setenv("SSFM_FILTFILT_NO_OLS", "1")
+        b = ob.filtfilt_batch(x, sos)
+        monkeypatch.delenv("SSFM_FILTFILT_NO_OLS", raising=False)
+        assert rel_l2(a, b) <= 1e-12
+        xd = torch.from_numpy(x).cuda()
+        engine.filtfilt_sos(xd, sos, out=xd)                              # in place: blocks go through a scratch chunk
+        assert rel_l2(xd.cpu().numpy(), ref) <= 1e-12
+    if n_samples >= 60001:
+        sos = bessel_sos(4, 2.0e9, 640e9)                                 # K ~ 3000: no block path
+        assert rel_l2(ob.filtfilt_batch(x, sos), sg.sosfiltfilt(sos, x, axis=-1)) <= 1e-11
+
+
+def test_overlap_save_photodetector_odd_length_with_sampler(ob):
+    """PD square law + noise beat terms + LPF + sampler through the block kernel on rows whose length is no power of two
+    (the square law runs in the block load, the sampler in the block store)."""
+    import torch
+    from scipy import signal as sg
+    from opticomlib_b200 import engine
+    rng = np.random.default_rng(77)
+    rows, n_pol, n = 3, 2, 50003
+    e = 0.03 * (rng.standard_normal((rows, n_pol, n)) + 1j * rng.standard_normal((rows, n_pol, n))) + 0.05
+    z = 0.002 * (rng.standard_normal((rows, n_pol, n)) + 1j * rng.standard_normal((rows, n_pol, n)))
+    extra = 1e-5 * rng.standard_normal((rows, n))
+    sos = bessel_sos(4, 7.5e9, 640e9)
+    r, r_load, i_dark, offset, stride = 0.9, 50.0, 1e-8, 17, 64
+    sig = r_load * (r * (np.abs(e) ** 2).sum(axis=1))
+    noi = r_load * (r * (2 * np.real(e * np.conj(z)) + np.abs(z) ** 2).sum(axis=1) + extra + i_dark)
+    want_s = sg.sosfiltfilt(sos, sig, axis=-1)[:, offset::stride]
+    want_n = sg.sosfiltfilt(sos, noi, axis=-1)[:, offset::stride]
+    got_s, got_n = engine.pd_lpf(torch.from_numpy(e).cuda(), sos, torch.from_numpy(z).cuda(), torch.from_numpy(extra).cuda(),
+                                 r, r_load, i_dark, offset, stride)
+    assert got_s.shape == want_s.shape
+    assert rel_l2(got_s.cpu().numpy(), want_s) <= TOL
+    assert rel_l2(got_n.cpu().numpy(), want_n) <= TOL

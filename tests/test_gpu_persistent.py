@@ -233,3 +233,54 @@ def test_multi_cluster_teams_match_oracle_and_flag_teams(ob, log2n, n_pol, preci
         plan.set_option("cluster", -1)
     np.testing.assert_array_equal(outs[1][1], outs[0][1])
     np.testing.assert_array_equal(outs[1][0], outs[0][0])          # same arithmetic, only the synchronisation differs
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("log2n,n_pol", [(17, 1), (16, 2), (18, 1)], ids=["2^17", "2^16x2pol", "2^18"])
+def test_multi_tile_cluster_teams_fixed_step(ob, log2n, n_pol, precision):
+    """Fixed-step propagation of waveforms of 32 / 64 tiles as ONE 16-CTA cluster per waveform with several tiles per CTA
+    (k_wf<.., TM = 3>, plan option cluster = 1; Kerr phase in the L2-resident team stash) against the oracle and bit for bit
+    against the flag-based teams (cluster = 0): more rows than teams, a last step shorter than h, a step budget with resume,
+    a zero-length call, DBP."""
+    import torch
+    from opticomlib_b200 import engine
+    n = 1 << log2n
+    rows = 19
+    kw = dict(length=2.3, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, h=0.5)       # 5 steps, the last one 0.3 km
+    base = _wave(n, 60 + log2n, power=8e-3, n_pol=n_pol)
+    x = np.stack([base * (1.0 + 0.05 * b) for b in range(rows)])
+    td = torch.complex64 if precision == "fp32" else torch.complex128
+    dev = torch.device("cuda", 0)
+    with np.errstate(all="ignore"):
+        refs = [oracle_fiber(x[b], DT, real=REAL[precision], **kw) for b in (0, rows - 1)]
+        ref_dbp = oracle_dbp(x[3], DT, real=REAL[precision], **kw)
+    assert refs[0]["steps"] == 5
+    outs = {}
+    for cluster in (1, 0):
+        plan = engine.get_plan(n, n_pol, rows, td, dev, lane=6)
+        plan.set_option("cluster", cluster)
+        f = torch.from_numpy(x).to(dev).to(td).contiguous()
+        info = plan.propagate(f, DT, **kw)
+        assert plan.last_timing()[0] == 2
+        assert plan.last_timing()[1] >= (14 if cluster == 1 else 1)           # teams in flight: 14 clusters (+ fill teams)
+        for ref, b in zip(refs, (0, rows - 1)):
+            assert int(info.steps[b]) == ref["steps"]
+            assert rel_l2(f[b].cpu().numpy().reshape(ref["out"].shape), ref["out"]) <= TOL[precision]
+        g = torch.from_numpy(x).to(dev).to(td).contiguous()                    # the same in budgets of two steps
+        info2 = plan.propagate(g, DT, max_steps=2, **kw)
+        while not info2.done.all():
+            info2 = plan.propagate(g, DT, max_steps=2, resume=True, **kw)
+        # (a budget boundary splits the merged Kerr rotation e^{j(a+b)} into e^{ja} e^{jb}: equal to rounding, not bit for bit)
+        assert rel_l2(g.cpu().numpy(), f.cpu().numpy()) <= (1e-5 if precision == "fp32" else 1e-13)
+        np.testing.assert_array_equal(info2.steps, info.steps)
+        z = torch.from_numpy(x).to(dev).to(td).contiguous()                    # zero length: nothing moves
+        info0 = plan.propagate(z, DT, **dict(kw, length=0.0))
+        assert int(info0.steps.max()) == 0
+        np.testing.assert_array_equal(z.cpu().numpy(), torch.from_numpy(x).to(td).numpy())
+        d = torch.from_numpy(x).to(dev).to(td).contiguous()                    # DBP = negated parameters
+        plan.propagate(d, DT, length=kw["length"], alpha=-kw["alpha"], beta_2=-kw["beta_2"], beta_3=-kw["beta_3"], gamma=-kw["gamma"], h=kw["h"])
+        assert rel_l2(d[3].cpu().numpy().reshape(ref_dbp["out"].shape), ref_dbp["out"]) <= TOL[precision]
+        outs[cluster] = (f.cpu().numpy(), info.steps.copy())
+        plan.set_option("cluster", -1)
+    np.testing.assert_array_equal(outs[1][1], outs[0][1])
+    np.testing.assert_array_equal(outs[1][0], outs[0][0])          # same arithmetic, only the team structure differs
