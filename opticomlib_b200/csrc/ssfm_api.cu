@@ -149,7 +149,7 @@ struct ssfm_plan_s {
     int fused = 1;               // 1: fused column kernel (2R+2W per step) when its barrier fits on the chip
     int num_sms = 0;
     int debug = 0;
-    int use_tw_full = 1;
+    int use_tw_full = -1;        // four-step twiddles: -1 auto, 0 two tables, 1 full table, 2 recurrence
     int l2_ahead = 0;
     int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
@@ -377,7 +377,11 @@ Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed,
     std::memset(&base, 0, sizeof(base));
     base.tw_col = (const C*)pl->tw_col; base.tw_row = (const C*)pl->tw_row;
     base.tw_lo = (const C*)pl->tw_lo;   base.tw_hi = (const C*)pl->tw_hi;
-    base.tw_full = pl->use_tw_full ? (const C*)pl->tw_full : nullptr;
+    // four-step twiddles: auto = recurrence for complex128 (measured on B200, config #3: 5.34e10 against 5.23e10 with the full
+    // table and 4.75e10 with two tables; the error stays ~1e-14), full table for complex64 (the recurrence doubles its error)
+    const int tw_mode = pl->use_tw_full < 0 ? (sizeof(R) == 8 ? 2 : 1) : pl->use_tw_full;
+    base.tw_full = tw_mode == 1 ? (const C*)pl->tw_full : nullptr;
+    base.tw_chain = tw_mode == 2 ? 1 : 0;
     base.small_phase = (!fixed && !single && pm <= (R)0.05 && pm >= (R)0) ? 1 : 0;   // |Kerr phase| <= phi_max in adaptive mode
     base.lo_bits = pl->lo_bits ? pl->lo_bits : ilog2(pl->n2);
     base.n = (int)pl->n; base.n1 = pl->n1; base.n2 = pl->n2; base.log2_n2 = ilog2(pl->n2);
@@ -449,9 +453,9 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         l.side = pl->wf_side; l.ev_side = pl->wf_ev_side;
         {   // waveforms of 32 .. 64 tiles without adaptive step control run as 16-CTA clusters with several tiles per CTA
             const long long units = (long long)pl->n_pol * (pl->n / 4096);
-            if ((fixed || single) && p.has_nl && units > 16 && units <= 64 && pl->n <= (1ll << 18) && pl->cluster != 0) {
-                if (!pl->tstash) {
-                    const size_t bytes = (size_t)16 * (size_t)units * 4096 * sizeof(R);
+            if (p.has_nl && units >= 2 && units <= 64 && pl->n <= (1ll << 18) && pl->cluster != 0) {
+                if (!pl->tstash) {                                  // (<= 16 tiles: the small clusters that fill the slots 16-CTA clusters leave)
+                    const size_t bytes = (size_t)(units > 16 ? 16 : 40) * (size_t)units * 4096 * sizeof(R);
                     if (cudaMalloc(&pl->tstash, bytes) == cudaSuccess) pl->tstash_bytes = bytes;
                     else { (void)cudaGetLastError(); pl->tstash = nullptr; }
                 }
@@ -930,7 +934,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "cluster") { pl->cluster = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "placement") { pl->placement = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "teams") { if (value < 0) return fail(SSFM_ERR_INVALID, "teams < 0"); pl->teams_cap = (int)value; }
-    else if (k == "tw_full") { pl->use_tw_full = value ? 1 : 0; }
+    else if (k == "tw_full") { pl->use_tw_full = value < 0 ? -1 : ((value == 2) ? 2 : (value ? 1 : 0)); }
     else if (k == "l2_ahead") { pl->l2_ahead = (int)value; }
     else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");
     return SSFM_OK;
@@ -1081,7 +1085,7 @@ Params<R> long_outer_params(ssfm_plan_t pl, void* field) {
     Params<R> p = base_params<R>(pl, pl->last, fixed, single);
     p.field = (C*)field; p.stash = (R*)pl->stash; p.ctrl = pl->ctrl; p.active = pl->active;
     p.ticket = pl->ticket; p.slots = pl->slots; p.hlog = pl->hlog; p.batch = 1;
-    p.tw_full = nullptr;
+    p.tw_full = nullptr; p.tw_chain = 0;
     p.n2_off = pl->long_rank * pl->n2;
     p.n_glob = (int)pl->long_n;
     p.inv_n = (R)1 / (R)pl->long_n;

@@ -52,6 +52,9 @@ struct Params {
     const C* tw_hi;      // W_N^(i*2^lo_bits)
     const C* tw_full;    // optional full four-step table W_N^{n2*k1} at [k1][n2] (N <= 2^20): one coalesced L2 load
                          // instead of two table look-ups and a complex product
+    int tw_chain;        // 1: four-step twiddles by recurrence (two interleaved chains seeded from tw_lo / tw_hi): 16 complex
+                         // products per thread instead of 16 loads of 16 B from L2 -- the full table is 2 x 16 B of L2 traffic per
+                         // sample and step next to the field's 4 x 16 B, and the L2 <-> SM path is what k_wf<double> waits for
     int l2_ahead;        // > 0: each CTA of the fused column kernel prefetches into L2 the tile that the CTA
                          // `l2_ahead` tickets later will load (about one CTA lifetime ahead)
     int small_phase;     // 1: every Kerr phase is <= 0.05 rad (adaptive mode with phi_max <= 0.05): short Taylor sincos
@@ -291,12 +294,39 @@ __device__ __forceinline__ void load_tables(C* dst, const C* __restrict__ src, i
     for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
 }
 
+// Four-step twiddles by recurrence: the seeds (two table look-ups and a product each) can be fetched before a barrier wait,
+// the sixteen products after the field has arrived.
+template <typename R> struct FsSeeds { typename cx_of<R>::type wa, wb, rho2; };
+template <typename R, int E, int M>
+__device__ __forceinline__ FsSeeds<R> fourstep_seeds(const Params<R>& p, int n2, int t) {
+    typedef typename cx_of<R>::type C;
+    const unsigned mask = (1u << p.lo_bits) - 1u;
+    const unsigned i0 = (unsigned)n2 * (unsigned)t, i1 = (unsigned)n2 * (unsigned)(M / E);   // < N
+    FsSeeds<R> s;
+    s.wa = cmul(__ldg(p.tw_lo + (i0 & mask)), __ldg(p.tw_hi + (i0 >> p.lo_bits)));
+    const C rho = cmul(__ldg(p.tw_lo + (i1 & mask)), __ldg(p.tw_hi + (i1 >> p.lo_bits)));
+    s.rho2 = cmul(rho, rho);
+    s.wb = cmul(s.wa, rho);
+    return s;
+}
+template <bool CONJ, typename R, int E>
+__device__ __forceinline__ void apply_fourstep_chain(typename cx_of<R>::type (&v)[E], FsSeeds<R> s) {
+#pragma unroll
+    for (int q = 0; q < E; q += 2) {
+        v[q] = CONJ ? cmulc(v[q], s.wa) : cmul(v[q], s.wa);
+        v[q + 1] = CONJ ? cmulc(v[q + 1], s.wb) : cmul(v[q + 1], s.wb);
+        if (q + 2 < E) { s.wa = cmul(s.wa, s.rho2); s.wb = cmul(s.wb, s.rho2); }
+    }
+}
+
 // v[q] *= W_N^{n2*k1} (or its conjugate), k1 = t + q*M/E.  The table choice is made ONCE outside the
 // unrolled loop (a per-element branch doubles the code of every iteration and costs ~10 %).
 template <bool CONJ, typename R, int E, int M>
 __device__ __forceinline__ void apply_fourstep(const Params<R>& p, typename cx_of<R>::type (&v)[E], int n2, int t) {
     typedef typename cx_of<R>::type C;
-    if (p.tw_full) {                                     // full table [k1][n2]: one coalesced L2 load per point
+    if (p.tw_chain) {                                    // W_N^{n2 (t + q M/E)} = W_N^{n2 t} (W_N^{n2 M/E})^q, even and odd q as two chains
+        apply_fourstep_chain<CONJ, R, E>(v, fourstep_seeds<R, E, M>(p, n2, t));
+    } else if (p.tw_full) {                              // full table [k1][n2]: one coalesced L2 load per point
         const C* __restrict__ base = p.tw_full + (size_t)t * p.n2 + n2;
 #pragma unroll
         for (int q = 0; q < E; ++q) {

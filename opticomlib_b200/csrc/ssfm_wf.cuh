@@ -63,6 +63,7 @@ struct WfArgs {
     int fixed, single, resume;
     R h_fixed;
     R* tstash;                    // TM == 3: Kerr phase of the waveforms in flight, [n_teams][units][16][256] (L2-resident)
+    int draw_min;                 // TM == 3 as the slower second launch: stop drawing when fewer waveforms than this are left
 };
 
 __host__ __device__ constexpr int wf_cmax(int a, int b) { return a > b ? a : b; }
@@ -432,7 +433,12 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                 ++seq;
                 if (CL) {                                       // CTA 0 of the cluster draws the waveform and posts it to every CTA
                     if (me == 0) {
-                        if (tid == 0) s_w = atomicAdd(a.next_wf, 1u);
+                        if (tid == 0) {
+                            // a team that is slower per waveform than the teams of the main launch leaves the last waveforms
+                            // to them (a late draw would finish long after everybody else)
+                            if (MT && a.draw_min > 0 && (int)(ld_relaxed_u32(a.next_wf) + (unsigned)a.draw_min) > p.batch) s_w = 0xffffffffu;
+                            else s_w = atomicAdd(a.next_wf, 1u);
+                        }
                         __syncthreads();
                         if (tid < (int)total) st_cluster_u32(&s_wcl[seq & 1u], (unsigned)tid, s_w);
                     }
@@ -472,10 +478,29 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     z0 = (R)cs.z; h_first = (R)cs.h; steps0 = cs.steps;
                 }
                 if constexpr (MT) {
-                    // several tiles per CTA (fixed step or one step only: the host never picks this variant for adaptive
-                    // step control, whose maximum would have to be known before any tile's Kerr rotation)
+                    // several tiles per CTA
                     if (!a.resume) {
-                        const R h0 = a.fixed ? a.h_fixed : p.length;
+                        R h0 = a.fixed ? a.h_fixed : p.length;
+                        if (!a.fixed && !a.single) {            // devices.py:1155-1156: max over the whole waveform, one more read of it
+                            R pm = 0;
+                            bool nan = false;
+#pragma unroll 1
+                            for (unsigned u = (unsigned)me; u < units; u += total) {
+                                const int un2 = (int)(u % (unsigned)tiles) * T + c;
+                                const C* __restrict__ inp = (p.field_in ? p.field_in : p.field) + ((size_t)w * p.n_pol + u / (unsigned)tiles) * NN;
+                                C v[E];
+#pragma unroll
+                                for (int q = 0; q < E; ++q) v[q] = __ldcg(inp + (size_t)(t + q * (M1 / E)) * M2 + un2);
+#pragma unroll
+                                for (int q = 0; q < E; ++q) {
+                                    const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                                    nan |= (pw != pw);
+                                    pm = pw > pm ? pw : pm;
+                                }
+                            }
+                            if (nan) pm = pw_nan<R>();
+                            h0 = p.phi_max / mul_rn(p.abs_gamma, team_max(pm));
+                        }
                         h_first = (p.length < h0) ? p.length : h0;
                         const int done0 = !((R)0 < p.length) || a.budget <= 0;
                         if (me == 0 && tid == 0) {
@@ -640,6 +665,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
 
             // -------------------------------------------------------------- column phase: end of step s ...
             WF_T0(t_c0);
+            FsSeeds<R> fs_seed;                                 // (MT: several tiles, seeds per tile inside the loop)
+            if (!MT && p.tw_chain) fs_seed = fourstep_seeds<R, E, M1>(p, n2, t);   // their L2 round trip hides behind the barrier wait
             bar_wait();
             WF_ACC(2, t_c0);
             const WfShared<R> S = sh_read(ver);
@@ -647,7 +674,40 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                 const R z = S.z, h = S.h;
                 const int steps = S.steps;
                 xchg = S.xchg;
-                const CtrlNext<R> nx = controller_next<R>(p, z, h, steps, (R)0);   // (no step control here: h stays, or the one step ends)
+                const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h));
+                R pmax = 0;
+                if (p.adaptive) {
+                    // Adaptive step control needs max|A|^2 over the WHOLE waveform before any tile's Kerr rotation: a first pass
+                    // over my tiles ends step s (inverse transforms, 1/N, attenuation, maximum) and stores the time-domain tile,
+                    // the second pass below re-reads it (each thread its own samples) for the merged rotation and the forward
+                    // transforms -- one more read and write of the field through L2 per step than the fixed-step schedule.
+                    R pm = 0;
+                    bool nan = false;
+#pragma unroll 1
+                    for (unsigned u = (unsigned)me; u < units; u += total) {
+                        const int un2 = (int)(u % (unsigned)tiles) * T + c;
+                        C* __restrict__ rowp = p.field + ((size_t)S.w * p.n_pol + u / (unsigned)tiles) * NN;
+                        C v[E];
+#pragma unroll
+                        for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + un2);
+                        apply_fourstep<true, R, E, M1>(p, v, un2, t);
+                        fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+#pragma unroll
+                        for (int q = 0; q < E; ++q) {
+                            v[q].x *= sc; v[q].y *= sc;
+                            const R pw = v[q].x * v[q].x + v[q].y * v[q].y;
+                            nan |= (pw != pw);
+                            pm = pw > pm ? pw : pm;
+                            rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
+                        }
+                    }
+                    if (nan) pm = pw_nan<R>();
+                    WF_T0(t_x0);
+                    pmax = team_max(pm);
+                    WF_ACC(3, t_x0);
+                }
+                const bool two_pass = p.adaptive != 0;
+                const CtrlNext<R> nx = controller_next<R>(p, z, h, steps, pmax);
                 const long long taken = S.taken + 1;
 #ifdef SSFM_WF_PROFILE
                 ++pn;
@@ -658,7 +718,6 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     if (p.hlog && steps < p.hlog_cap) p.hlog[(size_t)S.w * p.hlog_cap + steps] = (double)h;
                     cs.z = (double)nx.z; cs.h = (double)nx.h; cs.steps = steps + 1; cs.done = nx.done;
                 }
-                const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h));
                 const R hh = nx.h / (R)2;
 #pragma unroll 1
                 for (unsigned u = (unsigned)me; u < units; u += total) {
@@ -673,10 +732,12 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                         for (int q = 0; q < E; ++q) cp_async<sizeof(R)>(&st_sm[q * NT + tid], ts + q * NT + tid);
                         cp_async_commit();
                     }
-                    apply_fourstep<true, R, E, M1>(p, v, un2, t);
-                    fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                    if (!two_pass) {
+                        apply_fourstep<true, R, E, M1>(p, v, un2, t);
+                        fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
 #pragma unroll
-                    for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
+                        for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
+                    }
                     if (p.has_nl) cp_async_wait_all();
                     if (stop) {
 #pragma unroll
@@ -728,7 +789,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
             C v[E];
 #pragma unroll
             for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + n2);
-            apply_fourstep<true, R, E, M1>(p, v, n2, t);
+            if (p.tw_chain) apply_fourstep_chain<true, R, E>(v, fs_seed);
+            else apply_fourstep<true, R, E, M1>(p, v, n2, t);
             fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
             const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h)); // 1/N (exact) and exp(-alpha/2 h) (real part of D~ h)
 #pragma unroll

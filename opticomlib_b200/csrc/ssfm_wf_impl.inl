@@ -89,7 +89,50 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
     WF_TRY(cudaLaunchKernelEx(&cfg, kern, p, a));
     ++ssfm_launches;
-    if (fill > 0) {
+    // The slots the 16-CTA clusters cannot use: small clusters (2 CTAs by default) that carry a waveform with several tiles per
+    // CTA (k_wf<.., TM = 3>) -- hardware barrier, no flags through L2, barrier and exchange waits amortised over the tiles of a
+    // phase -- when the team stash is there; else flag-based teams of `total` CTAs.
+    int fcs = 2;
+    if (const char* e = getenv("SSFM_FILL_CS")) fcs = atoi(e);
+    const long long free_slots = (l.side && l.ev_side && l.ev0) ? coop_ctas - teams * total : 0;
+    const size_t per_team = (size_t)total * 4096 * sizeof(R);
+    // (measured on B200, config #3 in fp64: 5.77e10 with clusters of 2 against 5.33e10 with flag-based fill teams, 5.46e10 with
+    // clusters of 4, 4.78e10 with single CTAs; a waveform takes such a team ~6x as long as a 16-CTA cluster, so batches that
+    // the main teams finish in a few waveform times keep the flag-based teams)
+    const long long slow = ((long long)(total / (fcs > 0 ? fcs : 1)) * 8 + 9) / 10;
+    if (fcs >= 1 && fcs <= 8 && total % fcs == 0 && total > fcs && (l.tstash || !p.has_nl) && free_slots >= fcs &&
+        p.batch >= 3 * teams * slow) {
+        auto kf = k_wf<R, M1, M2, SMALL, 3>;
+        static bool attr_done[64] = {false};
+        if (!attr_done[(dev >= 0 && dev < 64) ? dev : 0]) {
+            WF_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::smem));
+            attr_done[(dev >= 0 && dev < 64) ? dev : 0] = true;
+        }
+        long long ft = free_slots / fcs;
+        if (p.has_nl && ft > (long long)(l.tstash_bytes / per_team)) ft = (long long)(l.tstash_bytes / per_team);
+        if (ft > p.batch - teams) ft = p.batch - teams;
+        if (l.teams_cap > 0 && ft > l.teams_cap - teams) ft = l.teams_cap - teams;
+        if (ft > 0) {
+            WfArgs<R> b = a;
+            b.n_teams = (int)ft;
+            b.tstash = (R*)l.tstash;
+            // a waveform takes a team of fcs CTAs about total/fcs x 0.6 times as long as a 16-CTA cluster
+            b.draw_min = (int)(teams * ((total / fcs) * 8 + 9) / 10);
+            cudaLaunchConfig_t fc{};
+            fc.blockDim = dim3(GEO::NT); fc.dynamicSmemBytes = GEO::smem; fc.stream = l.side;
+            cudaLaunchAttribute fa[1];
+            fa[0].id = cudaLaunchAttributeClusterDimension;
+            fa[0].val.clusterDim.x = (unsigned)fcs; fa[0].val.clusterDim.y = 1; fa[0].val.clusterDim.z = 1;
+            fc.attrs = fa; fc.numAttrs = 1;
+            fc.gridDim = dim3((unsigned)(ft * fcs));
+            WF_TRY(cudaStreamWaitEvent(l.side, l.ev0, 0));
+            WF_TRY(cudaLaunchKernelEx(&fc, kf, p, b));
+            WF_TRY(cudaEventRecord(l.ev_side, l.side));
+            WF_TRY(cudaStreamWaitEvent(st, l.ev_side, 0));
+            ++ssfm_launches;
+            fill = ft;
+        } else fill = 0;
+    } else if (fill > 0) {
         WfArgs<R> b = a;
         b.sm_cnt = (unsigned int*)sb;
         b.grid_bar = (unsigned int*)(sb + 4096);
@@ -119,16 +162,18 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
 template <typename R, int M1, int M2, bool SMALL>
 int wf_launch_mt(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_t st, int coop_ctas) {
     typedef wf_geom<R, M1, M2> GEO;
-    constexpr int CS = 16;
+    int CS = 16;
+    if (const char* e = getenv("SSFM_MT_CS")) CS = atoi(e);        // experiments: clusters of 2 / 4 / 8
+    if (CS < 1 || CS > 16 || (CS & (CS - 1))) CS = 16;
     auto kern = k_wf<R, M1, M2, SMALL, 3>;
     const long long units = (long long)p.n_pol * (p.n2 / GEO::T);
     if (units <= CS || units % CS || (p.has_nl && !l.tstash)) return SSFM_ERR_UNSUPPORTED;
-    static int max_clusters_dev[64];
+    static int max_clusters_dev[64][17];
     static bool init = false;
-    if (!init) { for (int& v : max_clusters_dev) v = 0; init = true; }
+    if (!init) { for (auto& r : max_clusters_dev) for (int& v : r) v = 0; init = true; }
     int dev = 0;
     cudaGetDevice(&dev);
-    int& max_clusters = max_clusters_dev[(dev >= 0 && dev < 64) ? dev : 0];
+    int& max_clusters = max_clusters_dev[(dev >= 0 && dev < 64) ? dev : 0][CS];
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(GEO::NT); cfg.dynamicSmemBytes = GEO::smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -153,6 +198,7 @@ int wf_launch_mt(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStre
     if (teams < 1) return SSFM_ERR_UNSUPPORTED;
     // small batches keep more of the chip busy with flag-based teams (units CTAs per waveform instead of 16)
     if (l.cluster < 1 && p.batch * CS * 14 < (long long)coop_ctas * 10 && p.batch < teams) return SSFM_ERR_UNSUPPORTED;
+    if (getenv("SSFM_DEBUG")) fprintf(stderr, "[ssfm] multi-tile: %lld teams of %d CTAs\n", teams, CS);
     long long fill = (l.side && l.ev_side && l.ev0) ? (coop_ctas - teams * CS) / units : 0;   // flag-based teams in the free slots
     if (teams > p.batch) teams = p.batch;
     if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
@@ -301,6 +347,12 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     if (teams > p.batch) teams = p.batch;
     if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
     if (teams < 1) return SSFM_ERR_UNSUPPORTED;                          // one waveform does not fit on the chip
+    if constexpr (M1 * M2 == (1 << 16)) {                                // experiments: 16-tile waveforms on multi-tile clusters of SSFM_MT_CS CTAs
+        if (getenv("SSFM_MT_CS") && l.cluster != 0 && total == 16) {
+            const int rc = wf_launch_mt<R, M1, M2, SMALL>(p, l, teams_out, st, per_sm * l.num_sms);
+            if (rc != SSFM_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if constexpr (M2 <= 256) {                                           // teams of <= 16 CTAs can be thread-block clusters
         if (l.cluster != 0 && total <= 16 && total >= 2 && (total & (total - 1)) == 0) {
             const int rc = wf_launch_cluster<R, M1, M2, SMALL>(p, l, teams_out, st, per_sm * l.num_sms);
@@ -308,7 +360,9 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
         }
     }
     if constexpr (M1 * M2 >= (1 << 16) && M1 * M2 <= (1 << 18)) {        // 32 .. 64 tiles per waveform, no adaptive step control
-        if (l.cluster != 0 && (l.fixed || l.single) && total > 16 && total <= 64 && !getenv("SSFM_NO_MT")) {
+        // (measured on B200 against flag-based / multi-cluster teams: fixed step 2^18 +6 %, 2^17 +9 %; adaptive steps -- two passes per
+        //  column phase -- fp64 +4 % / +6 %, fp32 +0 % / +16 %)
+        if (l.cluster != 0 && total > 16 && total <= 64 && !getenv("SSFM_NO_MT")) {
             const int rc = wf_launch_mt<R, M1, M2, SMALL>(p, l, teams_out, st, per_sm * l.num_sms);
             if (rc != SSFM_ERR_UNSUPPORTED) return rc;
         }

@@ -200,13 +200,19 @@ def test_degenerate_step_rules(ob, log2n):
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("variant", ["multi_cluster", "multi_tile"])
 @pytest.mark.parametrize("log2n,n_pol", [(17, 1), (16, 2), (18, 1)], ids=["2^17", "2^16x2pol", "2^18"])
-def test_multi_cluster_teams_match_oracle_and_flag_teams(ob, log2n, n_pol, precision):
-    """Teams of 32 / 64 CTAs as clusters of 8 with one flag hop between the cluster leaders (plan option cluster = 1) against
-    the oracle and against the flag-based cooperative teams (cluster = 0): several adaptive steps, rows with different step
-    counts, more rows than teams, a step budget with resume."""
+def test_multi_cluster_teams_match_oracle_and_flag_teams(ob, monkeypatch, log2n, n_pol, variant, precision):
+    """Waveforms of 32 / 64 tiles with plan option cluster = 1 -- as ONE 16-CTA cluster with several tiles per CTA and two
+    passes per column phase around the team maximum (multi_tile, the default), or as clusters of 8 with one flag hop between
+    the cluster leaders (multi_cluster, SSFM_NO_MT=1) -- against the oracle and against the flag-based cooperative teams
+    (cluster = 0): several adaptive steps, rows with different step counts, more rows than teams, a step budget with resume."""
     import torch
     from opticomlib_b200 import engine
+    if variant == "multi_cluster":
+        monkeypatch.setenv("SSFM_NO_MT", "1")
+    else:
+        monkeypatch.delenv("SSFM_NO_MT", raising=False)
     n = 1 << log2n
     rows = 11
     kw = dict(length=2.5, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.004)
@@ -284,3 +290,43 @@ def test_multi_tile_cluster_teams_fixed_step(ob, log2n, n_pol, precision):
         plan.set_option("cluster", -1)
     np.testing.assert_array_equal(outs[1][1], outs[0][1])
     np.testing.assert_array_equal(outs[1][0], outs[0][0])          # same arithmetic, only the team structure differs
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_small_cluster_fill_teams_with_adaptive_steps(ob, precision):
+    """A batch large enough that the CTA slots the 16-CTA clusters leave are filled by clusters of 2 CTAs carrying 8 tiles each
+    (k_wf<.., TM = 3>: two passes per column phase around the team maximum, Kerr phase in the L2-resident team stash, teams that
+    stop drawing near the end of the batch): adaptive steps with diverging step counts, bit for bit against the flag-based
+    teams and against the oracle."""
+    import torch
+    from opticomlib_b200 import engine
+    n, rows = 1 << 16, (340 if precision == "fp64" else 460)           # >= 3 x (14 | 21 clusters) x 7: the batch size from which
+    kw = dict(length=3.0, alpha=0.2, beta_2=-21.27, beta_3=0.127, gamma=1.3, phi_max=0.004)   # the small clusters are used
+    base = _wave(n, 91, power=8e-3)
+    scale = 1.0 + 0.7 * np.arange(rows) / rows
+    td = torch.complex64 if precision == "fp32" else torch.complex128
+    dev = torch.device("cuda", 0)
+    x = torch.from_numpy(base).to(dev).to(td)[None, :] * torch.from_numpy(scale).to(dev).to(td)[:, None]
+    x = x.contiguous()
+    picks = (0, rows // 2, rows - 1)
+    with np.errstate(all="ignore"):
+        refs = [oracle_fiber(x[b].cpu().numpy(), DT, real=REAL[precision], **kw) for b in picks]
+    assert refs[-1]["steps"] > refs[0]["steps"] >= 4
+    outs = {}
+    for cluster in (-1, 0):
+        plan = engine.get_plan(n, 1, rows, td, dev, lane=7)
+        plan.set_option("cluster", cluster)
+        f = x.clone()
+        info = plan.propagate(f, DT, **kw)
+        kind, in_flight, _ = plan.last_timing()
+        assert kind == 2
+        if cluster == -1:
+            assert in_flight > (27 if precision == "fp32" else 18)      # more teams than 16-CTA clusters + flag-based teams could be
+        for ref, b in zip(refs, picks):
+            assert int(info.steps[b]) == ref["steps"]
+            assert rel_l2(f[b].cpu().numpy(), ref["out"]) <= TOL[precision]
+        assert info.done.all()
+        outs[cluster] = (f.cpu().numpy(), info.steps.copy())
+        plan.set_option("cluster", -1)
+    np.testing.assert_array_equal(outs[-1][1], outs[0][1])
+    np.testing.assert_array_equal(outs[-1][0], outs[0][0])            # same arithmetic whatever the team structure
