@@ -166,9 +166,41 @@ template <int M, int E> struct RowExchange {
     }
 };
 
+// How a pass multiplies its inputs by W_{Ns*Rr}^{r*jm}, r = 1 .. Rr-1.  TableTwiddles: one table entry per r (the pass tables
+// of fft_plan; shared memory, or global memory read through L1).  ChainTwiddles: only W^{jm} is fetched, the powers are built
+// with 14 complex products arranged as four chains of depth <= 5 -- for kernels whose LSU path is busier than their FMA pipe.
+struct TableTwiddles {
+    template <int M, int E, int Ns, int S, int Rr, typename C>
+    __device__ static __forceinline__ void apply(C (&a)[Rr], const C* tw, int jm) {
+        const C* tp = tw + fft_plan<M, E>::table_offset(Ns) + jm;
+#pragma unroll
+        for (int r = 1; r < Rr; ++r) a[r] = twmul<S>(a[r], tp[(r - 1) * Ns]);
+    }
+};
+struct ChainTwiddles {
+    template <int M, int E, int Ns, int S, int Rr, typename C>
+    __device__ static __forceinline__ void apply(C (&a)[Rr], const C* tw, int jm) {
+        if constexpr (Rr != 16) TableTwiddles::apply<M, E, Ns, S, Rr>(a, tw, jm);
+        else {
+            C w[4];
+            w[0] = tw[fft_plan<M, E>::table_offset(Ns) + jm];          // W^{jm} (the r = 1 row of the pass table)
+            w[1] = cmul(w[0], w[0]);
+            w[2] = cmul(w[1], w[0]);
+            w[3] = cmul(w[1], w[1]);
+            const C w4 = w[3];
+#pragma unroll
+            for (int r = 1; r < 16; ++r) {
+                C& wr = w[(r - 1) & 3];
+                if (r > 4) wr = cmul(wr, w4);                           // W^{r jm} = W^{(r-4) jm} W^{4 jm}
+                a[r] = twmul<S>(a[r], wr);
+            }
+        }
+    }
+};
+
 // One M-point transform on v[E] (load layout v[q] = x[t + q*M/E]).  `sm` points at this transform's exchange
 // buffer (already offset by the column for ColExchange), `tw` at the pass tables in shared memory.
-template <typename R, int M, int S, typename X, int E, int Ns = 1>
+template <typename R, int M, int S, typename X, int E, int Ns = 1, typename TW = TableTwiddles>
 struct fft_passes {
     typedef typename cx_of<R>::type C;
     static constexpr int Rr = fft_plan<M, E>::radix_at(Ns);
@@ -180,12 +212,7 @@ struct fft_passes {
             C a[Rr];
 #pragma unroll
             for (int r = 0; r < Rr; ++r) a[r] = v[i + r * NB];
-            if constexpr (Ns > 1) {
-                constexpr int toff = fft_plan<M, E>::table_offset(Ns);
-                const C* tp = tw + toff + (j & (Ns - 1));
-#pragma unroll
-                for (int r = 1; r < Rr; ++r) a[r] = twmul<S>(a[r], tp[(r - 1) * Ns]);
-            }
+            if constexpr (Ns > 1) TW::template apply<M, E, Ns, S, Rr>(a, tw, j & (Ns - 1));
             if constexpr (Rr == 16) dft16<S>(a);
             else if constexpr (Rr == 8) dft8<S>(a);
             else if constexpr (Rr == 4) dft4<S>(a[0], a[1], a[2], a[3]);
@@ -201,12 +228,12 @@ struct fft_passes {
             X::sync();
 #pragma unroll
             for (int q = 0; q < E; ++q) v[q] = sm[X::idx(t + q * (M / E))];
-            fft_passes<R, M, S, X, E, Ns * Rr>::run(v, sm, tw, t);
+            fft_passes<R, M, S, X, E, Ns * Rr, TW>::run(v, sm, tw, t);
         }
     }
 };
-template <typename R, int M, int S, typename X, int E>
-struct fft_passes<R, M, S, X, E, M> {
+template <typename R, int M, int S, typename X, int E, typename TW>
+struct fft_passes<R, M, S, X, E, M, TW> {
     typedef typename cx_of<R>::type C;
     __device__ static __forceinline__ void run(C (&)[E], C*, const C*, int) {}
 };

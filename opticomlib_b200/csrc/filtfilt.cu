@@ -280,6 +280,9 @@ __global__ void k_fill_h2(double* out, Sos f) {
     }
     out[k] = g;
 }
+#ifndef OLS_TW
+#define OLS_TW ssfm::ChainTwiddles
+#endif
 template <bool PD>
 __global__ void __launch_bounds__(OLS_NT, 2) k_ols(OlsArgs a) {
     typedef ssfm::RowExchange<OLS_M, OLS_E> X;
@@ -371,13 +374,13 @@ __global__ void __launch_bounds__(OLS_NT, 2) k_ols(OlsArgs a) {
             }
         }
     }
-    ssfm::fft_passes<double, OLS_M, -1, X, OLS_E>::run(v, sm, a.tw, tid);
+    ssfm::fft_passes<double, OLS_M, -1, X, OLS_E, 1, OLS_TW>::run(v, sm, a.tw, tid);
 #pragma unroll
     for (int q = 0; q < OLS_E; ++q) {
         const double g = __ldg(a.h2 + tid + q * OLS_NT);
         v[q].x *= g; v[q].y *= g;
     }
-    ssfm::fft_passes<double, OLS_M, +1, X, OLS_E>::run(v, sm, a.tw, tid);
+    ssfm::fft_passes<double, OLS_M, +1, X, OLS_E, 1, OLS_TW>::run(v, sm, a.tw, tid);
 #pragma unroll
     for (int q = 0; q < OLS_E; ++q) {
         const int j = tid + q * OLS_NT;

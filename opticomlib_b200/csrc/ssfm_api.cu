@@ -455,7 +455,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
             const long long units = (long long)pl->n_pol * (pl->n / 4096);
             if (p.has_nl && units >= 2 && units <= 64 && pl->n <= (1ll << 18) && pl->cluster != 0) {
                 if (!pl->tstash) {                                  // (<= 16 tiles: the small clusters that fill the slots 16-CTA clusters leave)
-                    const size_t bytes = (size_t)(units > 16 ? 16 : 40) * (size_t)units * 4096 * sizeof(R);
+                    const size_t bytes = (size_t)(units > 16 ? 16 : (getenv("SSFM_STASH_TEAMS") ? atoi(getenv("SSFM_STASH_TEAMS")) : 40)) * (size_t)units * 4096 * sizeof(R);
                     if (cudaMalloc(&pl->tstash, bytes) == cudaSuccess) pl->tstash_bytes = bytes;
                     else { (void)cudaGetLastError(); pl->tstash = nullptr; }
                 }

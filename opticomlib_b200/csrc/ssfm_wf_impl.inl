@@ -70,6 +70,7 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     if (l.cluster < 1 && (teams + fill) * total * 10 < (long long)coop_ctas * 8) return SSFM_ERR_UNSUPPORTED;   // < 80 % of the chip
     if (teams > p.batch) teams = p.batch;
     if (l.teams_cap > 0 && teams > l.teams_cap) teams = l.teams_cap;
+    if (const char* e = getenv("SSFM_CL_CAP")) { const long long c = atoll(e); if (c > 0 && teams > c) teams = c; }   // experiments
     if (fill > p.batch - teams) fill = p.batch - teams;
     if (l.teams_cap > 0 && fill > l.teams_cap - teams) fill = l.teams_cap - teams;
     const size_t head = 4096 + 256;
@@ -101,7 +102,7 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     // the main teams finish in a few waveform times keep the flag-based teams)
     const long long slow = ((long long)(total / (fcs > 0 ? fcs : 1)) * 8 + 9) / 10;
     if (fcs >= 1 && fcs <= 8 && total % fcs == 0 && total > fcs && (l.tstash || !p.has_nl) && free_slots >= fcs &&
-        p.batch >= 3 * teams * slow) {
+        p.batch >= (getenv("SSFM_FILL_MIN") ? atoll(getenv("SSFM_FILL_MIN")) : 3 * teams * slow)) {
         auto kf = k_wf<R, M1, M2, SMALL, 3>;
         static bool attr_done[64] = {false};
         if (!attr_done[(dev >= 0 && dev < 64) ? dev : 0]) {

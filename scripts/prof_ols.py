@@ -1,0 +1,18 @@
+"""One pass of the overlap-save filter kernel at config-#4 sizes (for ncu captures): BPF and PD -> LPF -> SAMPLER on `frames` x 2^18."""
+import sys, torch
+sys.path.insert(0, '.')
+import opticomlib_b200 as ob
+from opticomlib_b200 import engine, workloads as wl
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+n = 1 << 18
+ob.gv(sps=64, R=10e9)
+dev = torch.device('cuda', 0)
+base = torch.from_numpy(wl.ook_field(15, 4096, 64, 0.0)).to(dev)
+rx = base[:n].repeat(frames, 1).contiguous()
+sos_b = ob.devices._bessel_sos(4, 20e9, ob.gv.fs)
+sos_l = ob.devices._bessel_sos(4, 7.5e9, ob.gv.fs)
+for i in range(2):
+    y = engine.filtfilt_sos(rx, sos_b)
+    s, nz = engine.pd_lpf(y, sos_l, None, None, 1.0, 50.0, 0.0, 32, 64)
+torch.cuda.synchronize()
+print('ok', frames, tuple(s.shape))
