@@ -436,10 +436,12 @@ def main():
             "peak_source": peak_src,
             "kernel_ms": {"k_wf": launch_ms}, "kernel_share_of_step": {"k_wf": launch_ms / (ms_total / a.steps)},
             "teams_in_flight": teams,
-            "note": "one persistent launch per propagation; achieved = 64 B (fp64) / 32 B (fp32) x sample*steps of the "
-                    "launch / its CUDA-event duration.  The waveforms in flight stay L2-resident, so DRAM traffic is far "
-                    "BELOW the algorithmic bytes (one field read + one write per propagation) and the kernel is bound by "
-                    "the FP64/FP32 pipe and L2, not by HBM: frac can exceed what a DRAM-streaming schedule could reach",
+            "note": "one persistent propagation = two concurrent launches of k_wf (16-CTA clusters; clusters of 2 CTAs with 8 tiles "
+                    "each in the CTA slots those leave), timed as one with CUDA events on the launching stream; achieved = 64 B "
+                    "(fp64) / 32 B (fp32) x sample*steps of the propagation / that duration.  The waveforms in flight stay "
+                    "L2-resident, so DRAM traffic is far BELOW the algorithmic bytes (one field read + one write per propagation) "
+                    "and the kernel is bound by the SM -- FP64 pipe plus L1TEX, see DESIGN.md section 3d -- not by HBM: frac can "
+                    "exceed what a DRAM-streaming schedule could reach",
             "algorithmic_bytes_per_launch": alg_bytes,
             "step": {"bytes_per_sample_step": step_bytes, "achieved": per_gpu * step_bytes / 1e9,
                      "frac": per_gpu * step_bytes / 1e9 / peak, "unit": "GB/s per GPU"},
@@ -687,13 +689,12 @@ def extra_cfg4(torch, dist, dev, rank, world):
     gain = 10 ** (-c4["span_loss_db"] / 20)
     best = None
     for it in range(3):                                               # pass 0 warms plans, tables and the allocator
-        y.copy_(rx0)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        engine.filtfilt_sos(y, sos_b, out=y)
+        engine.filtfilt_sos(rx0, sos_b, out=y)                        # received frames -> filtered frames (as devices.BPF returns a new signal)
         ev[1].record()
         nsteps = 0
         for _ in range(c4["spans"]):

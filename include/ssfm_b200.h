@@ -103,6 +103,22 @@ SSFM_API int ssfm_get_state(ssfm_plan_t plan, int32_t* steps_host, double* z_hos
  * the raw per-waveform controller records to (pinned) host memory on the same stream: n_waveforms records of 40 bytes
  * { double z; double h_next; uint64 scratch; int32 steps; int32 done; uint32 scratch; int32 pad }. */
 SSFM_API int ssfm_copy_state_async(ssfm_plan_t plan, void* records_host, void* stream);
+/* Streamed batches: ONE persistent launch carries a batch whose chunks are still being copied from the host, so the copies of
+ * the whole batch overlap its propagation and the kernel keeps every team busy across chunk boundaries (replaces the per-chunk
+ * launches of the host pipeline behind FIBER / fiber_batch for host buffers: reference call devices.py:1038 on NumPy arrays).
+ *   ready_dev[0]   number of waveforms (rows of `field`, in order) whose samples are on the device; the caller advances it in
+ *                  stream order behind every host-to-device copy (ssfm_stream_write_u32); the kernel draws waveform w only
+ *                  once ready_dev[0] > w;
+ *   done_dev[c]    incremented by the kernel, reaches rows_in_chunk(c) x n_pol x n_samples / 4096 when every sample of chunk c
+ *                  (chunk_rows consecutive waveforms; the last chunk may be shorter) holds its final value; the caller makes the
+ *                  stream of the device-to-host copy of chunk c wait for that (ssfm_stream_wait_geq_u32).
+ * Both arrays are device memory, zeroed by the caller before the call.  The call never blocks; SSFM_ERR_UNSUPPORTED (nothing
+ * enqueued) when the plan's geometry has no persistent kernel. */
+SSFM_API int ssfm_propagate_streamed(ssfm_plan_t plan, void* field_dev, const ssfm_fiber_params* prm, const uint32_t* ready_dev,
+                                     uint32_t* done_dev, int64_t chunk_rows, void* stream);
+/* Stream memory operations (CUDA driver cuStreamWriteValue32 / cuStreamWaitValue32 >=) for the two counters above. */
+SSFM_API int ssfm_stream_write_u32(void* stream, void* dev_ptr, uint32_t value);
+SSFM_API int ssfm_stream_wait_geq_u32(void* stream, const void* dev_ptr, uint32_t value);
 /* Progress of one waveform WHILE an asynchronous ssfm_propagate (option "async") is running: the controller record of
  * `row` is copied on a stream of its own (it does not wait for the propagation).  The reference updates a tqdm bar after
  * every step (devices.py:1164-1170, 1188-1191); this is the device-side counter such a bar polls. */

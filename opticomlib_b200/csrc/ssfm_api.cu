@@ -157,6 +157,9 @@ struct ssfm_plan_s {
     void* dim_tab = nullptr;     // k_wf: imag(D~) per bin (transposed order), refilled by every propagation
     void* tstash = nullptr;      // k_wf, multi-tile cluster teams: Kerr phase of the waveforms in flight (allocated on first use)
     size_t tstash_bytes = 0;
+    const unsigned int* s_ready = nullptr;   // ssfm_propagate_streamed: arrival / completion counters of the call in progress
+    unsigned int* s_done = nullptr;
+    long long s_chunk_rows = 0;
     int async_mode = 0;          // 1: ssfm_propagate returns once the persistent kernel is enqueued (host pipelines)
     int cluster = -1;            // k_wf: teams as thread-block clusters (-1 = auto, 0 = never, 1 = always when possible)
     void* wf_sync = nullptr;     // k_wf barriers / mailboxes / max words
@@ -462,6 +465,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
                 l.tstash = pl->tstash; l.tstash_bytes = pl->tstash_bytes;
             }
         }
+        l.ready = pl->s_ready; l.done = pl->s_done; l.chunk_rows = (int)pl->s_chunk_rows;
         int teams = 0;
         const int rc = wf_propagate<R>(p, l, &teams, st);
         if (rc == SSFM_OK) {
@@ -471,6 +475,7 @@ int propagate_t(ssfm_plan_t pl, void* field, const ssfm_fiber_params& prm, long 
         }
         if (rc != SSFM_ERR_UNSUPPORTED) return rc;
     }
+    if (pl->s_ready) return SSFM_ERR_UNSUPPORTED;         // a streamed batch needs the persistent kernel (nothing has been enqueued)
     pl->last_kind = 1;
     { const int rs = ensure_stash(pl); if (rs) return rs; }
     int ci = 0;
@@ -1027,6 +1032,53 @@ int ssfm_copy_state_async(ssfm_plan_t pl, void* dst_host, void* stream) {
     CU_TRY(cudaSetDevice(pl->device));
     CU_TRY(cudaMemcpyAsync(dst_host, pl->ctrl, sizeof(Ctrl) * (size_t)pl->batch, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return SSFM_OK;
+}
+
+// ---- streamed batches: one persistent launch for a batch whose chunks are still on their way from the host ----------------
+namespace {
+typedef int (*stream_memop_fn)(void* /*CUstream*/, unsigned long long /*CUdeviceptr*/, unsigned int, unsigned int);
+stream_memop_fn driver_entry(const char* name) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return (stream_memop_fn)fn;
+}
+}  // namespace
+
+int ssfm_stream_write_u32(void* stream, void* dev_ptr, uint32_t value) {
+    static stream_memop_fn fn = driver_entry("cuStreamWriteValue32");
+    if (!fn) return fail(SSFM_ERR_UNSUPPORTED, "cuStreamWriteValue32 is not available from this driver");
+    if (!dev_ptr) return fail(SSFM_ERR_INVALID, "null pointer");
+    const int rc = fn(stream, (unsigned long long)dev_ptr, value, 0u /* CU_STREAM_WRITE_VALUE_DEFAULT */);
+    if (rc) return fail(SSFM_ERR_CUDA, "cuStreamWriteValue32 failed with driver error " + std::to_string(rc));
+    return SSFM_OK;
+}
+
+int ssfm_stream_wait_geq_u32(void* stream, const void* dev_ptr, uint32_t value) {
+    static stream_memop_fn fn = driver_entry("cuStreamWaitValue32");
+    if (!fn) return fail(SSFM_ERR_UNSUPPORTED, "cuStreamWaitValue32 is not available from this driver");
+    if (!dev_ptr) return fail(SSFM_ERR_INVALID, "null pointer");
+    const int rc = fn(stream, (unsigned long long)dev_ptr, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc) return fail(SSFM_ERR_CUDA, "cuStreamWaitValue32 failed with driver error " + std::to_string(rc));
+    return SSFM_OK;
+}
+
+int ssfm_propagate_streamed(ssfm_plan_t pl, void* field, const ssfm_fiber_params* prm, const uint32_t* ready_dev,
+                            uint32_t* done_dev, int64_t chunk_rows, void* stream) {
+    if (!pl || !field || !prm || !ready_dev || !done_dev) return fail(SSFM_ERR_INVALID, "null plan, field, params or counters");
+    if (chunk_rows < 1) return fail(SSFM_ERR_INVALID, "chunk_rows must be >= 1");
+    if (!pl->propagates || pl->chirp_m || pl->long_n || !pl->persistent || !pl->wf_sync)
+        return SSFM_ERR_UNSUPPORTED;                       // only the persistent kernel adopts waveforms as they arrive
+    pl->s_ready = ready_dev; pl->s_done = done_dev; pl->s_chunk_rows = chunk_rows;
+    const int was_async = pl->async_mode;
+    pl->async_mode = 1;                                    // the caller enqueues the copies AFTER this call returns
+    const int rc = ssfm_propagate(pl, field, prm, 0, 0, stream);
+    pl->async_mode = was_async;
+    pl->s_ready = nullptr; pl->s_done = nullptr; pl->s_chunk_rows = 0;
+    return rc;
 }
 
 int ssfm_get_step_log(ssfm_plan_t pl, double* out, int64_t cap) {

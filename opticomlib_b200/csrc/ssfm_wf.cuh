@@ -64,6 +64,13 @@ struct WfArgs {
     R h_fixed;
     R* tstash;                    // TM == 3: Kerr phase of the waveforms in flight, [n_teams][units][16][256] (L2-resident)
     int draw_min;                 // TM == 3 as the slower second launch: stop drawing when fewer waveforms than this are left
+    // streamed batches (ssfm_propagate_streamed): the waveforms arrive from the host WHILE the kernel runs.  ready[0] = number of
+    // waveforms whose samples have landed (written in stream order behind every chunk's copy): a drawn waveform waits for it.
+    // done[c] counts the 4096-sample tiles of chunk c (chunk_rows waveforms each) whose final samples are stored: the stream
+    // that copies chunk c back to the host waits for it to reach chunk rows x tiles per waveform.  Null: nothing of this.
+    const unsigned int* ready;
+    unsigned int* done;
+    int chunk_rows;
 };
 
 __host__ __device__ constexpr int wf_cmax(int a, int b) { return a > b ? a : b; }
@@ -96,6 +103,18 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
     return v;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// waveform w of a streamed batch: wait until the host-to-device copy of its chunk has been flagged (one thread)
+template <typename A> __device__ __forceinline__ void wait_arrival(const A& a, unsigned int w, int batch) {
+    if (a.ready && w < (unsigned int)batch) {
+        while (ld_relaxed_sys_u32(a.ready) <= w) __nanosleep(500);
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+}
 
 enum { WF_GRAB = 0, WF_ROW = 1, WF_COL = 2, WF_END = 3 };
 #ifndef SSFM_WF_CTAS_F32
@@ -159,6 +178,13 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
     typedef typename cx_of<R>::type C;
     constexpr bool CL = (TM == 1 || TM == 3), MC = (TM == 2), MT = (TM == 3);
     typedef wf_geom<R, M1, M2> GEO;
+    // pass twiddles: complex128 builds the 15 powers of a radix-16 pass from ONE table entry (14 complex products) instead of
+    // 15 shared-memory loads of 16 B -- its LSU path is busier than its FP64 pipe; complex64 keeps the table
+#ifdef SSFM_WF_TABLE_TWIDDLES
+    typedef TableTwiddles WFTW;
+#else
+    typedef typename std::conditional<sizeof(R) == 8, ChainTwiddles, TableTwiddles>::type WFTW;
+#endif
     constexpr int E = GEO::E, NT = GEO::NT, T = GEO::T, G = GEO::G, PM = GEO::PM;
     static_assert(points_per_thread<R>::value == 16, "k_wf assumes 16 points per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -418,6 +444,17 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
     auto grab_fence = [&]() {
         if (!CL) { bar_arrive(); bar_wait(); }
     };
+    // streamed batches: this CTA's `ntiles` tiles of waveform w hold their final samples (every thread's stores are ordered before
+    // the count by the CTA barrier and the system-scope fence of thread 0; the reader is a copy engine)
+    auto mark_done = [&](unsigned int w, unsigned int ntiles) {
+        if (!a.done) return;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            atomicAdd(a.done + w / (unsigned int)a.chunk_rows, ntiles);
+        }
+    };
+    const unsigned int my_tiles = MT ? (units - (unsigned)me + total - 1u) / total : 1u;
     auto sh_read = [&](unsigned v) -> WfShared<R> {
         const volatile WfShared<R>* q = &sh[v & 1u];
         WfShared<R> r;
@@ -438,6 +475,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                             // to them (a late draw would finish long after everybody else)
                             if (MT && a.draw_min > 0 && (int)(ld_relaxed_u32(a.next_wf) + (unsigned)a.draw_min) > p.batch) s_w = 0xffffffffu;
                             else s_w = atomicAdd(a.next_wf, 1u);
+                            wait_arrival(a, s_w, p.batch);
                         }
                         __syncthreads();
                         if (tid < (int)total) st_cluster_u32(&s_wcl[seq & 1u], (unsigned)tid, s_w);
@@ -450,6 +488,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     unsigned int wn;
                     if (me == 0) {
                         wn = atomicAdd(a.next_wf, 1u);
+                        wait_arrival(a, wn, p.batch);
                         *mb = ((unsigned long long)seq << 32) | (unsigned long long)wn;
                     } else {
                         unsigned long long m;
@@ -474,7 +513,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                 int steps0 = 0;
                 if (a.resume) {
                     const Ctrl cs = p.ctrl[w];
-                    if (cs.done) { grab_fence(); continue; }    // stays in WF_GRAB: next waveform
+                    if (cs.done) { mark_done(w, my_tiles); grab_fence(); continue; }    // stays in WF_GRAB: next waveform
                     z0 = (R)cs.z; h_first = (R)cs.h; steps0 = cs.steps;
                 }
                 if constexpr (MT) {
@@ -507,7 +546,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                             Ctrl& cs = p.ctrl[w];
                             cs.z = 0.0; cs.h = (double)h_first; cs.pmax = 0ull; cs.steps = 0; cs.arrived = 0u; cs.done = !((R)0 < p.length);
                         }
-                        if (done0) { grab_fence(); continue; }
+                        if (done0) { mark_done(w, my_tiles); grab_fence(); continue; }
                     }
                     if (tid == 0) {
                         WfShared<R>& o = sh[(ver ^ 1u) & 1u];
@@ -534,7 +573,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                                 v[q] = cmul(v[q], mk<R>(co, sn));
                             }
                         }
-                        fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                        fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
                         apply_fourstep<false, R, E, M1>(p, v, un2, t);
 #pragma unroll
                         for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
@@ -570,7 +609,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                         Ctrl& cs = p.ctrl[w];
                         cs.z = 0.0; cs.h = (double)h_first; cs.pmax = 0ull; cs.steps = 0; cs.arrived = 0u; cs.done = !((R)0 < p.length);
                     }
-                    if (done0) { grab_fence(); continue; }
+                    if (done0) { mark_done(w, my_tiles); grab_fence(); continue; }
                 }
                 if (tid == 0) {                                  // (the last readers of this version are two team barriers back)
                     WfShared<R>& o = sh[(ver ^ 1u) & 1u];
@@ -588,7 +627,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                         v[q] = cmul(v[q], mk<R>(co, sn));
                     }
                 }
-                fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
                 apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
                 for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
@@ -612,7 +651,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                         C v[E];
 #pragma unroll
                         for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
-                        fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+                        fft_passes<R, M2, -1, RowExchange<M2, E>, E, 1, WFTW>::run(v, xb + g * PM, tw2, tr);
                         if (p.xfer) {
                             const C* __restrict__ hrow = p.xfer + (size_t)uk1 * M2;
 #pragma unroll
@@ -626,7 +665,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                                 v[q] = cmul(v[q], mk<R>(co, sn));
                             }
                         }
-                        fft_passes<R, M2, +1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+                        fft_passes<R, M2, +1, RowExchange<M2, E>, E, 1, WFTW>::run(v, xb + g * PM, tw2, tr);
 #pragma unroll
                         for (int q = 0; q < E; ++q) rbase[tr + q * (M2 / E)] = v[q];
                     }
@@ -640,7 +679,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                 C v[E];
 #pragma unroll
                 for (int q = 0; q < E; ++q) v[q] = __ldcg(rbase + tr + q * (M2 / E));
-                fft_passes<R, M2, -1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+                fft_passes<R, M2, -1, RowExchange<M2, E>, E, 1, WFTW>::run(v, xb + g * PM, tw2, tr);
                 if (p.xfer) {                                   // an arbitrary transfer function H[k] in transposed order: zero-phase
                     const C* __restrict__ hrow = p.xfer + (size_t)k1 * M2;      // filters (|H|^2), DM, FBG -- one pass over the rows,
 #pragma unroll                                                  // FFT -> x H -> IFFT with the waveforms in flight L2-resident
@@ -654,7 +693,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                         v[q] = cmul(v[q], mk<R>(co, sn));
                     }
                 }
-                fft_passes<R, M2, +1, RowExchange<M2, E>, E>::run(v, xb + g * PM, tw2, tr);
+                fft_passes<R, M2, +1, RowExchange<M2, E>, E, 1, WFTW>::run(v, xb + g * PM, tw2, tr);
 #pragma unroll
                 for (int q = 0; q < E; ++q) rbase[tr + q * (M2 / E)] = v[q];
                 bar_arrive();
@@ -691,7 +730,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
 #pragma unroll
                         for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + un2);
                         apply_fourstep<true, R, E, M1>(p, v, un2, t);
-                        fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                        fft_passes<R, M1, +1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
 #pragma unroll
                         for (int q = 0; q < E; ++q) {
                             v[q].x *= sc; v[q].y *= sc;
@@ -734,7 +773,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     }
                     if (!two_pass) {
                         apply_fourstep<true, R, E, M1>(p, v, un2, t);
-                        fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                        fft_passes<R, M1, +1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
 #pragma unroll
                         for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
                     }
@@ -761,13 +800,14 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                             v[q] = cmul(v[q], mk<R>(co, sn));
                         }
                     }
-                    fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+                    fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
                     apply_fourstep<false, R, E, M1>(p, v, un2, t);
 #pragma unroll
                     for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
                 }
                 if (stop) {
                     if (tid == 0) sh[ver & 1u].xchg = xchg;
+                    mark_done(S.w, my_tiles);
                     state = WF_GRAB;
                     WF_ACC(4, t_c0);
                     continue;
@@ -791,7 +831,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
             for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + n2);
             if (p.tw_chain) apply_fourstep_chain<true, R, E>(v, fs_seed);
             else apply_fourstep<true, R, E, M1>(p, v, n2, t);
-            fft_passes<R, M1, +1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+            fft_passes<R, M1, +1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
             const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h)); // 1/N (exact) and exp(-alpha/2 h) (real part of D~ h)
 #pragma unroll
             for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
@@ -831,6 +871,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
                 }
                 if (tid == 0) sh[ver & 1u].xchg = xchg;         // (adaptive mode: every warp read this version before its exchange)
+                mark_done(S.w, my_tiles);
                 state = WF_GRAB;
                 WF_ACC(4, t_c0);
                 continue;
@@ -853,7 +894,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     v[q] = cmul(v[q], mk<R>(co, sn));
                 }
             }
-            fft_passes<R, M1, -1, ColExchange<T>, E>::run(v, xb + c, tw1, t);
+            fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
             apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
             for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];

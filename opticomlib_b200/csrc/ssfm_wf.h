@@ -21,6 +21,9 @@ struct WfLaunch {
     cudaEvent_t ev0, ev1;    // recorded around the launch on the stream (may be null)
     void* tstash;            // multi-tile cluster teams: Kerr phase of the waveforms in flight (may be null: variant not used)
     size_t tstash_bytes;
+    const unsigned int* ready;   // streamed batches (ssfm_propagate_streamed): arrival counter, completion counters per chunk
+    unsigned int* done;
+    int chunk_rows;
 };
 constexpr size_t WF_SYNC_BYTES = 1u << 20;
 

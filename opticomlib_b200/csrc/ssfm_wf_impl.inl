@@ -85,6 +85,7 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     a.n_teams = (int)teams;
     a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
     a.h_fixed = (R)l.h_fixed;
+    a.ready = l.ready; a.done = l.done; a.chunk_rows = l.chunk_rows;
     a.occ = 1; a.placement = 0;
     cfg.gridDim = dim3((unsigned)(teams * total));
     if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
@@ -98,11 +99,12 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
     const long long free_slots = (l.side && l.ev_side && l.ev0) ? coop_ctas - teams * total : 0;
     const size_t per_team = (size_t)total * 4096 * sizeof(R);
     // (measured on B200, config #3 in fp64: 5.77e10 with clusters of 2 against 5.33e10 with flag-based fill teams, 5.46e10 with
-    // clusters of 4, 4.78e10 with single CTAs; a waveform takes such a team ~6x as long as a 16-CTA cluster, so batches that
-    // the main teams finish in a few waveform times keep the flag-based teams)
+    // clusters of 4, 4.78e10 with single CTAs; a waveform takes such a team ~6x as long as a 16-CTA cluster: the small clusters stop
+    // drawing when fewer than teams x slow waveforms are left (WfArgs::draw_min), and batches below twice that -- where they would
+    // hardly draw at all -- keep the flag-based teams; the 256-row chunks of the host pipeline are above it)
     const long long slow = ((long long)(total / (fcs > 0 ? fcs : 1)) * 8 + 9) / 10;
     if (fcs >= 1 && fcs <= 8 && total % fcs == 0 && total > fcs && (l.tstash || !p.has_nl) && free_slots >= fcs &&
-        p.batch >= (getenv("SSFM_FILL_MIN") ? atoll(getenv("SSFM_FILL_MIN")) : 3 * teams * slow)) {
+        p.batch >= (getenv("SSFM_FILL_MIN") ? atoll(getenv("SSFM_FILL_MIN")) : 2 * teams * slow)) {
         auto kf = k_wf<R, M1, M2, SMALL, 3>;
         static bool attr_done[64] = {false};
         if (!attr_done[(dev >= 0 && dev < 64) ? dev : 0]) {
@@ -218,6 +220,7 @@ int wf_launch_mt(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStre
     a.n_teams = (int)teams;
     a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
     a.h_fixed = (R)l.h_fixed;
+    a.ready = l.ready; a.done = l.done; a.chunk_rows = l.chunk_rows;
     a.occ = 1; a.placement = 0;
     a.tstash = (R*)l.tstash;
     cfg.gridDim = dim3((unsigned)(teams * CS));
@@ -310,6 +313,7 @@ int wf_launch_mc(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStre
     a.n_teams = (int)teams;
     a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
     a.h_fixed = (R)l.h_fixed;
+    a.ready = l.ready; a.done = l.done; a.chunk_rows = l.chunk_rows;
     a.occ = 1; a.placement = 0;
     cfg.gridDim = dim3((unsigned)(teams * total));
     if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));
@@ -390,6 +394,7 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     if (need > WF_SYNC_BYTES) return SSFM_ERR_UNSUPPORTED;
     WF_TRY(cudaMemsetAsync(l.sync_buf, 0, need, st));
     WfArgs<R> a;
+    std::memset(&a, 0, sizeof(a));
     char* sb = (char*)l.sync_buf;
     a.sm_cnt = (unsigned int*)sb;
     a.grid_bar = (unsigned int*)(sb + 4096);
@@ -404,6 +409,7 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
     a.n_teams = (int)teams;
     a.fixed = l.fixed; a.single = l.single; a.resume = l.resume;
     a.h_fixed = (R)l.h_fixed;
+    a.ready = l.ready; a.done = l.done; a.chunk_rows = l.chunk_rows;
     Params<R> pp = p;
     void* args[2] = {(void*)&pp, (void*)&a};
     if (l.ev0) WF_TRY(cudaEventRecord(l.ev0, st));

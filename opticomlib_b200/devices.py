@@ -13,6 +13,7 @@ or CUDA tensors; the reference has no batch API.
 """
 from __future__ import annotations
 
+import os
 import sys
 
 import numpy as np
@@ -143,6 +144,12 @@ HOST_CHUNK_BYTES = 256 << 20    # largest chunk of rows on the device
 HOST_MIN_CHUNKS = 12            # ... and at least this many chunks when the batch allows it (see host_chunk_rows)
 
 
+# Pinned host batches: one persistent launch that adopts waveforms as their chunks arrive (set to False to pipeline one launch
+# per chunk as before)
+HOST_SINGLE_LAUNCH = os.environ.get("SSFM_HOST_SINGLE_LAUNCH", "1") != "0"
+HOST_SINGLE_CHUNK_BYTES = 32 << 20        # no launch per chunk there, so its chunks are small (at most 256 of them)
+
+
 def host_chunk_rows(B, P, N, tdtype):
     """Rows per chunk of the host pipelines.  Only the first chunk's H2D copy and the last chunk's D2H copy are exposed
     (everything else overlaps a propagation), so chunks should be SMALL -- at least HOST_MIN_CHUNKS of them -- but a chunk
@@ -184,6 +191,10 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
     if pipe == "auto":
         pipe = "async" if (host.is_pinned() and out.is_pinned()) else "threads"
     if pipe != "threads" and not want_log and fused and persistent in (None, True):
+        if pipe == "async" and host.dtype == tdtype and len(chunks) > 1 and HOST_SINGLE_LAUNCH and not chunk_waveforms:
+            res = _propagate_host_single_launch(host, out, tdtype, dev, args, chunks)
+            if res is not None:
+                return res
         return _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes, pipe)
     steps = np.zeros(B, np.int32); z = np.zeros(B); hn = np.zeros(B); done = np.zeros(B, bool)
     logs, errors = {}, []
@@ -224,6 +235,51 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
         for ci, (r0, r1) in enumerate(chunks):
             h_log[r0:r1, :logs[ci].shape[1]] = logs[ci]
     return out, engine.StepInfo(steps, z, hn, done, h_log)
+
+
+def _propagate_host_single_launch(host, out, tdtype, dev, args, chunks):
+    """Pinned host buffers in and out, ONE persistent launch for the whole batch (C-ABI ``ssfm_propagate_streamed``): the kernel
+    is enqueued first and adopts a waveform as soon as the host-to-device copy of its chunk has been flagged (a stream memory
+    operation behind every copy); a third stream copies a chunk back as soon as the kernel has counted all of its tiles as
+    final.  The copies of the whole batch overlap its propagation, and -- unlike one launch per chunk -- the teams never drain
+    at a chunk boundary and the small multi-tile clusters see the whole batch.  Returns None (nothing enqueued) when the
+    geometry has no persistent kernel or the driver lacks stream memory operations: the caller then pipelines chunk by chunk."""
+    import ctypes
+    torch = engine._torch()
+    lib = engine._lib.load()
+    B = host.shape[0]
+    P, N = (1, host.shape[1]) if host.ndim == 2 else (host.shape[1], host.shape[2])
+    if (P * N) % 4096 or B * P * N * host.element_size() > (64 << 30):
+        return None
+    tiles = (P * N) // 4096
+    # no launch per chunk here, so the chunks can be small: ~32 MiB each (at most 256 of them) -- only the first copy in and the
+    # last copy out are exposed
+    rows = max(1, HOST_SINGLE_CHUNK_BYTES // (P * N * host.element_size()), -(-B // 256))
+    chunks = [(r0, min(B, r0 + rows)) for r0 in range(0, B, rows)]
+    rec = torch.empty(B * engine.STATE_RECORD, dtype=torch.uint8, pin_memory=True)
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        x = torch.empty(tuple(host.shape), dtype=tdtype, device=dev)
+        flags = torch.zeros(1 + len(chunks), dtype=torch.int32, device=dev)      # [ready | done per chunk]
+        plan = engine.get_plan(N, P, B, tdtype, dev, lane=0)
+        _set_schedule(plan, True, True, 0)
+        h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ready_ptr, done_ptr = flags.data_ptr(), flags.data_ptr() + 4
+        reset = torch.cuda.Event(); reset.record(main)                        # buffer and zeroed flags exist; recorded BEFORE the kernel,
+        if not plan.propagate_streamed(x, ready_ptr, done_ptr, rows, *args, state_out=rec):   # which waits for the copies below
+            return None
+        h2d.wait_event(reset); d2h.wait_event(reset)
+        with torch.cuda.stream(h2d):
+            for r0, r1 in chunks:
+                x[r0:r1].copy_(host[r0:r1], non_blocking=True)
+                engine._lib.check(lib.ssfm_stream_write_u32(ctypes.c_void_p(h2d.cuda_stream), ctypes.c_void_p(ready_ptr), r1))
+        with torch.cuda.stream(d2h):
+            for ci, (r0, r1) in enumerate(chunks):
+                engine._lib.check(lib.ssfm_stream_wait_geq_u32(ctypes.c_void_p(d2h.cuda_stream), ctypes.c_void_p(done_ptr + 4 * ci),
+                                                               (r1 - r0) * tiles))
+                out[r0:r1].copy_(x[r0:r1], non_blocking=True)
+        h2d.synchronize(); d2h.synchronize(); main.synchronize()
+    return out, engine.decode_state(rec.numpy())
 
 
 def _propagate_host_pipelined(host, out, tdtype, dev, chunk_waveforms, args, rows, chunks, lanes, pipe="async"):

@@ -134,6 +134,29 @@ class Plan:
                     self.set_option("async", 0)
         return None if state_out is not None else self.state(want_log)
 
+    def propagate_streamed(self, field, ready_ptr, done_ptr, chunk_rows, dt, length, alpha=0.0, beta_2=0.0, beta_3=0.0, gamma=0.0,
+                           phi_max=0.01, h=None, state_out=None) -> bool:
+        """Enqueue ONE persistent launch over all rows of ``field`` that adopts row w once ``ready_ptr[0] > w`` and counts
+        finished tiles per chunk in ``done_ptr`` (C-ABI ``ssfm_propagate_streamed``; both device pointers, zeroed).  Never
+        blocks.  False when this geometry has no persistent kernel (nothing was enqueued)."""
+        torch = _torch()
+        if field.dtype != self.cdtype or not field.is_cuda or not field.is_contiguous():
+            raise ValueError("field must be a contiguous CUDA tensor of dtype %s" % self.cdtype)
+        if field.numel() != self.batch * self.n_pol * self.n:
+            raise ValueError("field has %d elements, plan expects %d" % (field.numel(), self.batch * self.n_pol * self.n))
+        prm = _lib.FiberParams(float(dt), float(length), float(alpha), float(beta_2), float(beta_3), float(gamma),
+                               float(phi_max), math.nan if h is None else float(h))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.ssfm_propagate_streamed(self.handle, field.data_ptr(), ctypes.byref(prm), ctypes.c_void_p(ready_ptr),
+                                                  ctypes.c_void_p(done_ptr), int(chunk_rows), ctypes.c_void_p(stream))
+            if rc == _lib.SSFM_ERR_UNSUPPORTED:
+                return False
+            _lib.check(rc)
+            if state_out is not None:
+                _lib.check(self.lib.ssfm_copy_state_async(self.handle, state_out.data_ptr(), ctypes.c_void_p(stream)))
+        return True
+
     def time_step_kernels(self, field, dt, reps=5, **fiber):
         """Average device time [ms] of (column forward, row, column inverse) over ``reps`` steps.
         Advances ``field`` -- pass a scratch copy.  Measurement hook for bench.py."""

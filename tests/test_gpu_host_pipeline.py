@@ -53,8 +53,13 @@ def _oracle_rows(x, precision, kw):
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("single_launch", [True, False], ids=["one_launch", "launch_per_chunk"])
 @pytest.mark.parametrize("log2n,rows,chunk_rows", [(13, 44, 6), (16, 41, 5)], ids=["2^13x44", "2^16x41"])
-def test_pinned_async_pipeline_matches_oracle(ob, monkeypatch, precision, log2n, rows, chunk_rows):
+def test_pinned_async_pipeline_matches_oracle(ob, monkeypatch, precision, single_launch, log2n, rows, chunk_rows):
+    """The two pipelines behind fiber_batch for pinned host buffers -- ONE persistent launch that adopts waveforms as their
+    chunks arrive (ssfm_propagate_streamed; the path bench.py's e2e times; same dtype on host and device) and one launch per
+    chunk over three streams (the fallback, and the path for fp32 computation on complex128 host data) -- against the oracle:
+    rows with diverging step counts, >= 8 chunks, a ragged last chunk."""
     import torch
     from opticomlib_b200 import devices
     n = 1 << log2n
@@ -63,20 +68,32 @@ def test_pinned_async_pipeline_matches_oracle(ob, monkeypatch, precision, log2n,
     steps_ref = np.array([r["steps"] for r in refs])
     assert len(set(steps_ref.tolist())) >= 5, "the rows were meant to need different numbers of steps"
 
-    # small chunks: >= 8 chunks round-robin over the three lanes, and a ragged last one
+    # small chunks: >= 8 chunks (round-robin over the three lanes when every chunk is a launch), and a ragged last one
     monkeypatch.setattr(devices, "HOST_CHUNK_BYTES", chunk_rows * n * 16)
-    calls = []
-    real = devices._propagate_host_pipelined
+    monkeypatch.setattr(devices, "HOST_SINGLE_CHUNK_BYTES", chunk_rows * n * (8 if precision == "fp32" else 16))
+    monkeypatch.setattr(devices, "HOST_SINGLE_LAUNCH", single_launch)
+    calls, singles = [], []
+    real, real_single = devices._propagate_host_pipelined, devices._propagate_host_single_launch
 
     def spy(*a, **k):
         calls.append(len(a[7]))                                   # chunks
         return real(*a, **k)
 
+    def spy_single(*a, **k):
+        res = real_single(*a, **k)
+        singles.append(res is not None)
+        return res
+
     monkeypatch.setattr(devices, "_propagate_host_pipelined", spy)
-    host = torch.from_numpy(x).pin_memory()
-    out = torch.empty(host.shape, dtype=torch.complex64 if precision == "fp32" else torch.complex128, pin_memory=True)
+    monkeypatch.setattr(devices, "_propagate_host_single_launch", spy_single)
+    tdt = torch.complex64 if precision == "fp32" else torch.complex128
+    host = torch.from_numpy(x).to(tdt if single_launch else torch.complex128).pin_memory()   # (one launch: host dtype = compute dtype)
+    out = torch.empty(host.shape, dtype=tdt, pin_memory=True)
     res, info = ob.fiber_batch(host, DT, precision=precision, out=out, **KW)
-    assert calls and calls[0] >= 8, "the pinned inputs did not take the asynchronous pipeline (or too few chunks): %r" % calls
+    if single_launch:
+        assert singles == [True] and not calls, "the pinned inputs did not take the single streamed launch: %r %r" % (singles, calls)
+    else:
+        assert calls and calls[0] >= 8, "the pinned inputs did not take the asynchronous pipeline (or too few chunks): %r" % calls
     assert res.data_ptr() == out.data_ptr()
     np.testing.assert_array_equal(info.steps, steps_ref)
     got = res.numpy()
