@@ -336,6 +336,7 @@ def main():
     del x0, work                                                        # the host path stages its own chunks
     engine.clear_plans(); torch.cuda.empty_cache()
     sched = dict(persistent=(a.schedule == "persistent"))
+    single_launch = devices.HOST_SINGLE_LAUNCH and a.schedule == "persistent" and tdtype == torch.complex128 and 4096 <= n <= (1 << 20)
     devices.fiber_batch(xh, w["dt"], precision=a.precision, out=out_h, **sched, **fiber)   # warm
     barrier()
     e2e_units, t0 = 0, time.perf_counter()
@@ -490,12 +491,17 @@ def main():
                    "untimed device copy before each timed propagation" % (rows * n * csize / 2 ** 20), **fiber},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "exposed_copy_ms": e2e_ms - ms_total / a.steps,
-                "chunks_per_gpu": -(-rows // devices.host_chunk_rows(rows, 1, n, tdtype)),
+                "chunks_per_gpu": (-(-rows // max(1, devices.HOST_SINGLE_CHUNK_BYTES // (n * csize), -(-rows // 256))) if single_launch
+                                   else -(-rows // devices.host_chunk_rows(rows, 1, n, tdtype))),
                 "numa_node_of_rank0": (numa[0] if numa else None),
-                "api": "opticomlib_b200.fiber_batch(pinned host complex128 -> pinned host %s), rows streamed in chunks over %d "
-                       "streams (H2D / propagate / D2H overlapped, one enqueueing host thread); exposed_copy_ms = e2e ms per step "
-                       "- device-resident ms per step (the first chunk's H2D and the last chunk's D2H)"
-                       % ("complex128" if csize == 16 else "complex64", devices.HOST_LANES)},
+                "api": ("opticomlib_b200.fiber_batch(pinned host complex128 -> pinned host complex128): ONE persistent launch per "
+                        "propagation that adopts a waveform once the host-to-device copy of its ~32 MiB chunk has been flagged "
+                        "(ssfm_propagate_streamed; stream memory operations), chunks copied back by a third stream as the kernel "
+                        "counts them finished; exposed_copy_ms = e2e ms per step - device-resident ms per step" if single_launch else
+                        "opticomlib_b200.fiber_batch(pinned host complex128 -> pinned host %s), rows streamed in chunks over %d "
+                        "streams, one launch per chunk (H2D / propagate / D2H overlapped, one enqueueing host thread); exposed_copy_ms "
+                        "= e2e ms per step - device-resident ms per step (the first chunk's H2D and the last chunk's D2H)"
+                        % ("complex128" if csize == 16 else "complex64", devices.HOST_LANES))},
         "e2e_parity": e2e_parity,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -637,6 +637,33 @@ def edfa_fiber_batch(field, rows, G, NF, dt, length, alpha=0.0, beta_2=0.0, beta
     lanes = min(HOST_LANES, len(chunks))
     args = (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h)
     rec = torch.empty(B * engine.STATE_RECORD, dtype=torch.uint8, pin_memory=True)
+    if tdtype == torch.complex128 and HOST_SINGLE_LAUNCH and len(chunks) > 1 and N % 4096 == 0 and B * N * 16 <= (64 << 30):
+        # the whole batch is generated on the device, ONE persistent launch propagates it, and a second stream copies every
+        # ~32 MiB chunk to the host as soon as the kernel has counted its tiles as final (ssfm_propagate_streamed with all
+        # rows "arrived" from the start)
+        import ctypes
+        lib = engine._lib.load()
+        srows = max(1, HOST_SINGLE_CHUNK_BYTES // (N * 16), -(-B // 256))
+        sch = [(r0, min(B, r0 + srows)) for r0 in range(0, B, srows)]
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            xdev = torch.empty((B, N), dtype=torch.complex128, device=dev)
+            engine.edfa(x, B, G, p_ase, seed, out_pol=1, out=xdev, first_row=first_row)
+            flags = torch.zeros(1 + len(sch), dtype=torch.int32, device=dev)
+            flags[0] = B
+            plan = engine.get_plan(N, 1, B, tdtype, dev, lane=0)
+            _set_schedule(plan, True, True)
+            reset = torch.cuda.Event(); reset.record(main)
+            if plan.propagate_streamed(xdev, flags.data_ptr(), flags.data_ptr() + 4, srows, *args, state_out=rec):
+                d2h = torch.cuda.Stream(device=dev)
+                d2h.wait_event(reset)
+                with torch.cuda.stream(d2h):
+                    for ci, (r0, r1) in enumerate(sch):
+                        engine._lib.check(lib.ssfm_stream_wait_geq_u32(ctypes.c_void_p(d2h.cuda_stream), ctypes.c_void_p(flags.data_ptr() + 4 + 4 * ci),
+                                                                       (r1 - r0) * (N // 4096)))
+                        out[r0:r1].copy_(xdev[r0:r1], non_blocking=True)
+                d2h.synchronize(); main.synchronize()
+                return out, engine.decode_state(rec.numpy())
     with torch.cuda.device(dev):
         ln = [(torch.cuda.Stream(device=dev), torch.empty((crows, N), dtype=torch.complex128, device=dev),
                torch.empty((crows, N), dtype=tdtype, device=dev) if tdtype != torch.complex128 else None) for _ in range(lanes)]

@@ -212,9 +212,11 @@ def test_batch_containers_chain_stays_on_device(ob):
     assert rel_l2(lp.noise.cpu().numpy(), oracle_sosfiltfilt(sos_l, 0.1 * np.abs(fld) ** 2)) <= TOL
 
 
+@pytest.mark.parametrize("single_launch", [True, False], ids=["one_launch", "launch_per_chunk"])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
-def test_generated_monte_carlo_pipeline_equals_monolithic(ob, monkeypatch, precision):
-    """edfa_fiber_batch (chunks generated, propagated and copied out on three streams) against edfa_batch + fiber_batch on the
+def test_generated_monte_carlo_pipeline_equals_monolithic(ob, monkeypatch, precision, single_launch):
+    """edfa_fiber_batch (fp64: the batch generated on the device, ONE streamed launch, chunks copied out as the kernel finishes
+    them; otherwise chunks generated, propagated and copied out on three streams) against edfa_batch + fiber_batch on the
     whole batch at once: the noise of a row depends on (seed, global row index) only, so the rows are bit-identical."""
     import torch
     from opticomlib_b200 import devices
@@ -223,6 +225,8 @@ def test_generated_monte_carlo_pipeline_equals_monolithic(ob, monkeypatch, preci
     base = _field(1, 1, n, 12)[0, 0] * 3.0
     kw = dict(length=8.0, alpha=0.2, beta_2=-20.0, gamma=2.0, phi_max=0.01)
     monkeypatch.setattr(devices, "HOST_CHUNK_BYTES", 4 * n * 16)              # 8 chunks, ragged last one
+    monkeypatch.setattr(devices, "HOST_SINGLE_CHUNK_BYTES", 4 * n * 16)
+    monkeypatch.setattr(devices, "HOST_SINGLE_LAUNCH", single_launch)
     got, info = ob.edfa_fiber_batch(base, rows, 10.0, 5.0, ob.gv.dt, seed=77, precision=precision, **kw)
     assert got.is_pinned() and tuple(got.shape) == (rows, n)
     whole = ob.edfa_batch(base, rows, 10.0, 5.0, n_pol_out=1, seed=77)
