@@ -266,18 +266,28 @@ def _propagate_host_single_launch(host, out, tdtype, dev, args, chunks):
         h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         ready_ptr, done_ptr = flags.data_ptr(), flags.data_ptr() + 4
         reset = torch.cuda.Event(); reset.record(main)                        # buffer and zeroed flags exist; recorded BEFORE the kernel,
-        if not plan.propagate_streamed(x, ready_ptr, done_ptr, rows, *args, state_out=rec):   # which waits for the copies below
+        h2d.wait_event(reset); d2h.wait_event(reset)                          # which waits for the copies below
+        # the driver must offer stream memory operations BEFORE a kernel that depends on them is enqueued
+        if (lib.ssfm_stream_write_u32(ctypes.c_void_p(h2d.cuda_stream), ctypes.c_void_p(ready_ptr), 0) != 0 or
+                lib.ssfm_stream_wait_geq_u32(ctypes.c_void_p(d2h.cuda_stream), ctypes.c_void_p(ready_ptr), 0) != 0):
             return None
-        h2d.wait_event(reset); d2h.wait_event(reset)
-        with torch.cuda.stream(h2d):
-            for r0, r1 in chunks:
-                x[r0:r1].copy_(host[r0:r1], non_blocking=True)
-                engine._lib.check(lib.ssfm_stream_write_u32(ctypes.c_void_p(h2d.cuda_stream), ctypes.c_void_p(ready_ptr), r1))
-        with torch.cuda.stream(d2h):
-            for ci, (r0, r1) in enumerate(chunks):
-                engine._lib.check(lib.ssfm_stream_wait_geq_u32(ctypes.c_void_p(d2h.cuda_stream), ctypes.c_void_p(done_ptr + 4 * ci),
-                                                               (r1 - r0) * tiles))
-                out[r0:r1].copy_(x[r0:r1], non_blocking=True)
+        if not plan.propagate_streamed(x, ready_ptr, done_ptr, rows, *args, state_out=rec):
+            return None
+        try:
+            with torch.cuda.stream(h2d):
+                for r0, r1 in chunks:
+                    x[r0:r1].copy_(host[r0:r1], non_blocking=True)
+                    engine._lib.check(lib.ssfm_stream_write_u32(ctypes.c_void_p(h2d.cuda_stream), ctypes.c_void_p(ready_ptr), r1))
+            with torch.cuda.stream(d2h):
+                for ci, (r0, r1) in enumerate(chunks):
+                    engine._lib.check(lib.ssfm_stream_wait_geq_u32(ctypes.c_void_p(d2h.cuda_stream), ctypes.c_void_p(done_ptr + 4 * ci),
+                                                                   (r1 - r0) * tiles))
+                    out[r0:r1].copy_(x[r0:r1], non_blocking=True)
+        except BaseException:
+            with torch.cuda.stream(h2d):                                      # never leave the kernel waiting for rows that will not come
+                flags[:1].fill_(B)
+            h2d.synchronize(); main.synchronize()
+            raise
         h2d.synchronize(); d2h.synchronize(); main.synchronize()
     return out, engine.decode_state(rec.numpy())
 
