@@ -647,7 +647,11 @@ def edfa_fiber_batch(field, rows, G, NF, dt, length, alpha=0.0, beta_2=0.0, beta
     lanes = min(HOST_LANES, len(chunks))
     args = (dt, length, alpha, beta_2, beta_3, gamma, phi_max, h)
     rec = torch.empty(B * engine.STATE_RECORD, dtype=torch.uint8, pin_memory=True)
-    if tdtype == torch.complex128 and HOST_SINGLE_LAUNCH and len(chunks) > 1 and N % 4096 == 0 and B * N * 16 <= (64 << 30):
+    if (tdtype == torch.complex128 and HOST_SINGLE_LAUNCH and len(chunks) > 1 and N % 4096 == 0 and B * N * 16 <= (64 << 30)
+            and B * N >= (1 << 26)):
+        # (smaller batches -- one GPU's share of 4096 x 2^16 at 8 GPUs -- keep one launch per chunk: a chunk of the single launch
+        # is only complete when the slowest team that drew one of its rows is done, which delays the first copies out by a
+        # few ms; measured at 8 GPUs, where the copies are what the run waits for: 58 against 51 ms)
         # the whole batch is generated on the device, ONE persistent launch propagates it, and a second stream copies every
         # ~32 MiB chunk to the host as soon as the kernel has counted its tiles as final (ssfm_propagate_streamed with all
         # rows "arrived" from the start)
