@@ -395,6 +395,141 @@ __global__ void __launch_bounds__(OLS_NT, 2) k_ols(OlsArgs a) {
     }
 }
 
+// ---- photodetector -> low-pass -> SAMPLER when the sampler keeps one sample in `stride` (stride >= 32): the outputs wanted are
+// so few that evaluating the zero-phase response as a FIR filter AT those samples only -- 2K + 1 taps each, the taps being the
+// response of k_ols to a unit impulse -- costs (2K + 1)/stride multiply-adds per input sample and component (26 for K = 848,
+// stride 64) against ~130 FP64 instructions per input sample for the block transforms, and needs no exchange at all.
+// One CTA = 64 consecutive outputs of one row.  The span of input samples they need (stride * 63 + 2K + 1) is detected (square
+// law, beat terms) straight into shared memory as a matrix X[kk][a] = sample (stride * a + kk) of the span, so that
+//   y[j] = sum_kk sum_kb h[kb * stride + kk] X[kk][j + kb]
+// is, for every kk, a short FIR (ceil((2K + 1)/stride) taps) along a row of X.  A thread owns 4 consecutive outputs and a few
+// values of kk: per tap it loads ONE new sample and ONE tap for 8 multiply-adds (a sliding window in registers), so the kernel
+// is bound by the FP64 pipe, not by shared memory (one load per multiply-add in the naive form: measured 5.4 ms for
+// 1024 x 2^18 samples, no faster than the block transforms).  Rows of X are stored de-interleaved by 4 (column a at
+// (a % 4) * AQ + a / 4), which makes the window loads of the 16 threads of a group consecutive 16-byte words.
+constexpr int FIR_NT = 256, FIR_TO = 64, FIR_R = 4, FIR_TPG = FIR_TO / FIR_R, FIR_G = FIR_NT / FIR_TPG;   // 16 threads x 16 groups
+struct FirArgs {
+    PdSrc pd;
+    const double2* taps;     // taps[k].x = zero-phase impulse response at lag k - K, k = 0 .. 2K (output of k_ols on an impulse at K)
+    double* out_sig;
+    double* out_noise;
+    long long n, m, offset, stride, row0;
+    int K, AQ, kb_total;     // halo; quarter pitch of a row of X (even); ceil((2K + 1) / stride) rounded up to a multiple of 4
+};
+__device__ __forceinline__ int fir_col(int a, int AQ) { return (a & 3) * AQ + (a >> 2); }
+template <bool SIMPLE>       // SIMPLE: one polarisation, no optical noise field (the common receiver): 8 samples per thread in flight
+__global__ void __launch_bounds__(FIR_NT, 2) k_pd_fir(FirArgs a) {
+    extern __shared__ __align__(16) unsigned char fir_smem[];
+    const int S = (int)a.stride, ntap = 2 * a.K + 1, A = 4 * a.AQ + 1;  // (odd pitch: the stores of the detection phase spread over the banks)
+    double2* xs = reinterpret_cast<double2*>(fir_smem);                 // [stride][4 * AQ + 1] detected samples (signal, noise)
+    double* hs = reinterpret_cast<double*>(xs + (size_t)S * A);         // [kb_total * stride] taps, zero-padded
+    const int tid = threadIdx.x;
+    const long long per_row = (a.m + FIR_TO - 1) / FIR_TO;
+    const long long row = blockIdx.x / per_row;
+    const long long j0 = (blockIdx.x % per_row) * FIR_TO;               // first output of this CTA
+    const long long g0 = a.offset + (long long)S * j0 - a.K;            // first input sample of the span
+    const int span = S * (FIR_TO - 1) + ntap;
+    const int fill = S * (FIR_TO + a.kb_total + 2);                     // every column the windows touch is written (zeros beyond the span:
+    for (int i = tid; i < a.kb_total * S; i += FIR_NT) {               // they meet zero taps, but 0 x garbage could be NaN)
+        const int kk = i / a.kb_total, kb = i % a.kb_total, k = kb * S + kk;   // hs[kk][kb] = tap kb * stride + kk
+        hs[i] = k < ntap ? a.taps[k].x : 0.0;
+    }
+    const PdSrc& s = a.pd;
+    const long long r = a.row0 + row;
+    constexpr int NL = SIMPLE ? 8 : 2;
+    // sample u of the span = row (u mod stride), column (u / stride) of X; the pair advances by FIR_NT without a division
+    const int dkk = FIR_NT % S, dcol = FIR_NT / S;
+    int kk_u = tid % S, col_u = tid / S;
+    const double2* f0 = s.field + (r * s.n_pol) * a.n;
+    const double2* f1 = f0 + a.n;
+    const double2* z0 = s.noise ? s.noise + (r * s.n_pol) * a.n : nullptr;
+    const double2* z1 = z0 ? z0 + a.n : nullptr;
+    const double* xe = (s.extra && s.noise_out) ? s.extra + r * a.n : nullptr;
+    const bool pol2 = s.n_pol > 1;
+#pragma unroll 1
+    for (int u0 = tid; u0 < fill; u0 += NL * FIR_NT) {
+        double2 e[NL][SIMPLE ? 1 : 2], z[NL][SIMPLE ? 1 : 2];
+        double ex[NL];
+        bool in[NL];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            const int u = u0 + i * FIR_NT;
+            const long long gi = g0 + u;
+            in[i] = u < span && gi >= 0 && gi < a.n;
+            ex[i] = 0.0;
+            e[i][0] = in[i] ? f0[gi] : make_double2(0.0, 0.0);
+            if (!SIMPLE) {
+                e[i][1] = (in[i] && pol2) ? f1[gi] : make_double2(0.0, 0.0);
+                z[i][0] = (in[i] && z0) ? z0[gi] : make_double2(0.0, 0.0);
+                z[i][1] = (in[i] && z0 && pol2) ? z1[gi] : make_double2(0.0, 0.0);
+            }
+            if (in[i] && xe) ex[i] = xe[gi];
+        }
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            const int u = u0 + i * FIR_NT;
+            if (u < fill) {
+                double sig = 0.0, noi = 0.0;
+#pragma unroll
+                for (int p = 0; p < (SIMPLE ? 1 : 2); ++p) {
+                    sig += e[i][p].x * e[i][p].x + e[i][p].y * e[i][p].y;
+                    if (!SIMPLE) noi += 2.0 * (e[i][p].x * z[i][p].x + e[i][p].y * z[i][p].y) + (z[i][p].x * z[i][p].x + z[i][p].y * z[i][p].y);
+                }
+                double2 v;                                              // (samples outside the row only reach outputs within K of its
+                v.x = in[i] ? s.r_load * (s.r * sig) : 0.0;             //  ends, which the exact end segments replace)
+                v.y = (in[i] && s.noise_out) ? s.r_load * (s.r * noi + ex[i] + s.i_dark) : 0.0;
+                xs[(size_t)kk_u * A + fir_col(col_u, a.AQ)] = v;
+            }
+            kk_u += dkk; col_u += dcol;
+            if (kk_u >= S) { kk_u -= S; ++col_u; }
+        }
+    }
+    __syncthreads();
+    const int t = tid % FIR_TPG, g = tid / FIR_TPG;                     // outputs 4 t .. 4 t + 3; rows kk = g, g + 16, ...
+    double2 acc[FIR_R];
+#pragma unroll
+    for (int q = 0; q < FIR_R; ++q) acc[q] = make_double2(0.0, 0.0);
+    const int kb4 = a.kb_total;                                         // (a multiple of 4: the host pads with zero taps)
+#pragma unroll 1
+    for (int kk = g; kk < S; kk += FIR_G) {
+        // column 4 (t + q) + c of row kk sits at xr[c * AQ + t + q]: four pointers, one index
+        const double2* p0 = xs + (size_t)kk * A + t;
+        const double2* p1 = p0 + a.AQ;
+        const double2* p2 = p1 + a.AQ;
+        const double2* p3 = p2 + a.AQ;
+        const double2* hq = reinterpret_cast<const double2*>(hs + (size_t)kk * kb4);   // taps of this row, consecutive in kb
+        double2 w0 = p0[0], w1 = p1[0], w2 = p2[0];
+#pragma unroll 2
+        for (int q = 0; q < kb4 / 4; ++q) {
+            const double2 h01 = hq[2 * q], h23 = hq[2 * q + 1];
+            const double2 w3 = p3[q], w4 = p0[q + 1], w5 = p1[q + 1], w6 = p2[q + 1];
+#define FIR_TAP(h, a0, a1, a2, a3)                                                    \
+            acc[0].x = fma(h, a0.x, acc[0].x); acc[0].y = fma(h, a0.y, acc[0].y);     \
+            acc[1].x = fma(h, a1.x, acc[1].x); acc[1].y = fma(h, a1.y, acc[1].y);     \
+            acc[2].x = fma(h, a2.x, acc[2].x); acc[2].y = fma(h, a2.y, acc[2].y);     \
+            acc[3].x = fma(h, a3.x, acc[3].x); acc[3].y = fma(h, a3.y, acc[3].y);
+            FIR_TAP(h01.x, w0, w1, w2, w3)
+            FIR_TAP(h01.y, w1, w2, w3, w4)
+            FIR_TAP(h23.x, w2, w3, w4, w5)
+            FIR_TAP(h23.y, w3, w4, w5, w6)
+#undef FIR_TAP
+            w0 = w4; w1 = w5; w2 = w6;
+        }
+    }
+    __syncthreads();                                                    // the sample matrix is free: partial sums go there
+    double2* red = xs;                                                  // [FIR_G][FIR_TO]
+#pragma unroll
+    for (int q = 0; q < FIR_R; ++q) red[g * FIR_TO + 4 * t + q] = acc[q];
+    __syncthreads();
+    if (tid < FIR_TO && j0 + tid < a.m) {
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int q = 0; q < FIR_G; ++q) { sx += red[q * FIR_TO + tid].x; sy += red[q * FIR_TO + tid].y; }
+        a.out_sig[r * a.m + j0 + tid] = sx;
+        if (a.out_noise) a.out_noise[r * a.m + j0 + tid] = sy;
+    }
+}
+
 // Philox4x32-10 counter-based generator + Box-Muller: N(0, 1) doubles, reproducible from (seed, element index) alone,
 // whatever the launch geometry (the reference draws its noise from NumPy's global stream: devices.py:933, 1523, 1527 --
 // a device-side generator can only be validated statistically).
@@ -594,8 +729,51 @@ int zero_phase(const Sos& f, double rho, const double2* x, const PdSrc* pd, doub
                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
                     a.wave = 2 * sms;
                 }
+                // sampler with a large stride: evaluate the response as a FIR filter at the wanted samples only (k_pd_fir); its
+                // taps are what the block kernel returns for a unit impulse
+                const bool fir = pd && real_out && stride >= 32 && stride <= 64 && Kp <= 1000 && !getenv("SSFM_PD_NO_FIR");
+                if (fir) {
+                    double2* imp = nullptr;
+                    if ((e = cudaMallocAsync((void**)&imp, sizeof(double2) * 2 * OLS_M, st)) != cudaSuccess) {
+                        cudaFreeAsync(h2, st); cudaStreamWaitEvent(st, sd.join, 0); return cuda_fail(e);
+                    }
+                    cudaMemsetAsync(imp, 0, sizeof(double2) * 2 * OLS_M, st);
+                    const double one = 1.0;
+                    cudaMemcpyAsync(&imp[Kp].x, &one, sizeof(double), cudaMemcpyHostToDevice, st);   // impulse at sample K of a 4096-sample row
+                    OlsArgs ia = a;
+                    ia.x = imp; ia.y = imp + OLS_M; ia.n = OLS_M; ia.nb = (OLS_M + ia.L - 1) / ia.L; ia.row0 = 0; ia.wave = 1 << 30;
+                    ia.offset = 0; ia.stride = 1; ia.m = OLS_M;
+                    k_ols<false><<<(unsigned)ia.nb, OLS_NT, smem, st>>>(ia);
+                    FirArgs fa{};
+                    fa.pd = *pd; fa.taps = imp + OLS_M; fa.out_sig = out_sig; fa.out_noise = out_noise;
+                    fa.n = n; fa.m = m; fa.offset = offset; fa.stride = stride; fa.row0 = 0; fa.K = (int)Kp;
+                    fa.kb_total = (int)(((2 * Kp + 1 + stride - 1) / stride + 3) & ~3ll);   // padded to a multiple of 4 with zero taps
+                    fa.AQ = (((FIR_TO + fa.kb_total + 2 + 3) / 4) + 1) & ~1;        // columns 0 .. FIR_TO + kb_total + 1 of X, de-interleaved by 4
+                    const size_t fsm = sizeof(double2) * (size_t)stride * (4 * fa.AQ + 1) + sizeof(double) * (size_t)fa.kb_total * stride;
+                    const bool simple = pd->n_pol == 1 && !pd->noise;
+                    static bool fir_attr[64] = {false};
+                    if (!fir_attr[(device >= 0 && device < 64) ? device : 0]) {
+                        cudaFuncSetAttribute(k_pd_fir<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+                        cudaFuncSetAttribute(k_pd_fir<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+                        fir_attr[(device >= 0 && device < 64) ? device : 0] = true;
+                    }
+                    const long long per_row = (m + FIR_TO - 1) / FIR_TO;
+                    const long long rows_per = std::max<long long>(1, std::min<long long>(rows, 0x7fffffffll / per_row));
+                    if (fsm <= 113 * 1024) {
+                        for (long long r0 = 0; r0 < rows; r0 += rows_per) {
+                            fa.row0 = r0;
+                            const unsigned grid = (unsigned)(std::min(rows_per, rows - r0) * per_row);
+                            if (simple) k_pd_fir<true><<<grid, FIR_NT, fsm, st>>>(fa);
+                            else k_pd_fir<false><<<grid, FIR_NT, fsm, st>>>(fa);
+                        }
+                    }
+                    e = cudaGetLastError();
+                    cudaFreeAsync(imp, st);
+                    if (fsm > 113 * 1024) e = cudaErrorInvalidValue;
+                    if (e != cudaSuccess) { cudaFreeAsync(h2, st); cudaStreamWaitEvent(st, sd.join, 0); return cuda_fail(e); }
+                }
                 const long long per = in_place ? chunk : std::max<long long>(1, std::min<long long>(rows, (long long)(0x7fffffffll / a.nb)));
-                for (long long r0 = 0; r0 < rows; r0 += per) {
+                for (long long r0 = 0; r0 < rows && !fir; r0 += per) {
                     const long long nr = std::min(per, rows - r0);
                     a.row0 = r0;
                     if (pd) {
