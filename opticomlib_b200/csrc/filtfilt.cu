@@ -395,7 +395,8 @@ __global__ void __launch_bounds__(OLS_NT, 2) k_ols(OlsArgs a) {
     }
 }
 
-// ---- photodetector -> low-pass -> SAMPLER when the sampler keeps one sample in `stride` (stride >= 32): the outputs wanted are
+// ---- photodetector -> low-pass -> SAMPLER (reference PD devices.py:1514-1552, its closing LPF 1363-1368, SAMPLER 1871-1891:
+// output[instant :: sps]) when the sampler keeps one sample in `stride` (stride >= 32): the outputs wanted are
 // so few that evaluating the zero-phase response as a FIR filter AT those samples only -- 2K + 1 taps each, the taps being the
 // response of k_ols to a unit impulse -- costs (2K + 1)/stride multiply-adds per input sample and component (26 for K = 848,
 // stride 64) against ~130 FP64 instructions per input sample for the block transforms, and needs no exchange at all.
