@@ -43,5 +43,15 @@ engine.filtfilt_sos(x, sos, out=x)
 e2 = torch.from_numpy(wave(9001, 2, 2)).to(dev)
 s, nz = engine.pd_lpf(e2, sos, 0.01 * e2, engine.gaussian_noise((2, 9001), 1e-6, 1), 0.9, 50.0, 1e-8, 8, 16)
 s2, _ = engine.pd_lpf(e2, sos)
+s3, n3 = engine.pd_lpf(e2, sos, 0.01 * e2, engine.gaussian_noise((2, 9001), 1e-6, 1), 0.9, 50.0, 1e-8, 5, 40)     # stride 40: k_pd_fir<false>
+s4, _ = engine.pd_lpf(e2[:, 0, :].contiguous(), sos, None, None, 1.0, 50.0, 0.0, 3, 64)                              # k_pd_fir<true>
+# streamed batch: pinned host rows -> ONE launch that adopts them as they arrive -> pinned host rows
+from opticomlib_b200 import devices
+devices.HOST_CHUNK_BYTES = 2 * (1 << 13) * 16; devices.HOST_SINGLE_CHUNK_BYTES = 2 * (1 << 13) * 16
+host = torch.from_numpy(wave(1 << 13, 9) * (1 + np.arange(9))[:, None] ** 0.5).pin_memory()
+outp = torch.empty(host.shape, dtype=torch.complex128, pin_memory=True)
+res, info = ob.fiber_batch(host, dt, precision='fp64', out=outp, **adapt)
+print('streamed batch', info.steps.tolist(), bool(info.done.all()), flush=True)
 torch.cuda.synchronize()
+print('decimating FIR ok', tuple(s3.shape), tuple(s4.shape))
 print('overlap-save filters ok', tuple(y.shape), tuple(s.shape), tuple(s2.shape), float((y - x).abs().max()))
