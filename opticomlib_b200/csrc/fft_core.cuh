@@ -154,6 +154,14 @@ template <int T> struct ColExchange {
     __device__ static __forceinline__ int idx(int a) { return a * T; }
     __device__ static __forceinline__ void sync() { __syncthreads(); }
 };
+// The same layout for T = 16 columns handled as two independent halves of 8 columns by threads 0..127 / 128..255 of a 256-thread
+// CTA: each half synchronises on its own named barrier, so the halves drift apart and one half's butterflies overlap the other
+// half's exchange (and each barrier waits for 4 warps instead of 8).
+template <int T> struct ColExchangeHalves {
+    static constexpr int stride = T;
+    __device__ static __forceinline__ int idx(int a) { return a * T; }
+    __device__ static __forceinline__ void sync() { asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory"); }
+};
 // Row transforms: one padded private buffer per transform (one pad slot every E points keeps both the
 // scattered writes and the contiguous reads conflict-free); the M/E threads of one transform are
 // consecutive, so when they fit in a warp a warp barrier is enough.

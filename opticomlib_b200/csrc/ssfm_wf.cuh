@@ -180,6 +180,14 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
     typedef wf_geom<R, M1, M2> GEO;
     // pass twiddles: complex128 builds the 15 powers of a radix-16 pass from ONE table entry (14 complex products) instead of
     // 15 shared-memory loads of 16 B -- its LSU path is busier than its FP64 pipe; complex64 keeps the table
+#ifdef SSFM_WF_NO_HALVES
+    constexpr bool HALVES = false;
+#else
+    // 256-point column transforms in complex128: two half-CTAs with their own barriers (measured on B200, config #3: fp64 5.78e10 ->
+    // 5.89e10; fp32, three CTAs per SM, 1.02e11 -> 9.2e10: off)
+    constexpr bool HALVES = (GEO::T == 16 && GEO::NT == 256 && sizeof(R) == 8);
+#endif
+    typedef typename std::conditional<HALVES, ColExchangeHalves<GEO::T>, ColExchange<GEO::T>>::type CX;
 #ifdef SSFM_WF_TABLE_TWIDDLES
     typedef TableTwiddles WFTW;
 #else
@@ -270,7 +278,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
     }
 
     const int pol = me / tiles, tile = me % tiles;
-    const int c = tid % T, t = tid / T;                        // column phase: column c of the tile, thread t of its transform
+    const int c = HALVES ? ((tid & 7) | ((tid >> 7) << 3)) : tid % T;   // column phase: column c of the tile, thread t of its transform
+    const int t = HALVES ? ((tid & 127) >> 3) : tid / T;                // (HALVES: columns 0..7 on warps 0..3, columns 8..15 on warps 4..7)
     const int n2 = tile * T + c;
     const int g = tid / (M2 / E), tr = tid % (M2 / E);         // row phase: row g of the group, thread tr of its transform
     const int k1 = tile * G + g;
@@ -573,7 +582,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                                 v[q] = cmul(v[q], mk<R>(co, sn));
                             }
                         }
-                        fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
+                        fft_passes<R, M1, -1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
                         apply_fourstep<false, R, E, M1>(p, v, un2, t);
 #pragma unroll
                         for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
@@ -627,7 +636,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                         v[q] = cmul(v[q], mk<R>(co, sn));
                     }
                 }
-                fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
+                fft_passes<R, M1, -1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
                 apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
                 for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
@@ -730,7 +739,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
 #pragma unroll
                         for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + un2);
                         apply_fourstep<true, R, E, M1>(p, v, un2, t);
-                        fft_passes<R, M1, +1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
+                        fft_passes<R, M1, +1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
 #pragma unroll
                         for (int q = 0; q < E; ++q) {
                             v[q].x *= sc; v[q].y *= sc;
@@ -773,7 +782,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     }
                     if (!two_pass) {
                         apply_fourstep<true, R, E, M1>(p, v, un2, t);
-                        fft_passes<R, M1, +1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
+                        fft_passes<R, M1, +1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
 #pragma unroll
                         for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
                     }
@@ -800,7 +809,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                             v[q] = cmul(v[q], mk<R>(co, sn));
                         }
                     }
-                    fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
+                    fft_passes<R, M1, -1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
                     apply_fourstep<false, R, E, M1>(p, v, un2, t);
 #pragma unroll
                     for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
@@ -831,7 +840,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
             for (int q = 0; q < E; ++q) v[q] = __ldcg(rowp + (size_t)(t + q * (M1 / E)) * M2 + n2);
             if (p.tw_chain) apply_fourstep_chain<true, R, E>(v, fs_seed);
             else apply_fourstep<true, R, E, M1>(p, v, n2, t);
-            fft_passes<R, M1, +1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
+            fft_passes<R, M1, +1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
             const R sc = p.inv_n * exp_r(mul_rn(p.att_half, h)); // 1/N (exact) and exp(-alpha/2 h) (real part of D~ h)
 #pragma unroll
             for (int q = 0; q < E; ++q) { v[q].x *= sc; v[q].y *= sc; }
@@ -894,7 +903,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     v[q] = cmul(v[q], mk<R>(co, sn));
                 }
             }
-            fft_passes<R, M1, -1, ColExchange<T>, E, 1, WFTW>::run(v, xb + c, tw1, t);
+            fft_passes<R, M1, -1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
             apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
             for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
