@@ -327,6 +327,17 @@ def test_small_cluster_fill_teams_with_adaptive_steps(ob, precision):
             assert rel_l2(f[b].cpu().numpy(), ref["out"]) <= TOL[precision]
         assert info.done.all()
         outs[cluster] = (f.cpu().numpy(), info.steps.copy())
+        if cluster == -1:                                             # the same batch in budgets of 3 steps with resume: rows finish at
+            g = x.clone()                                             # different calls, later calls skip the rows that are done
+            info2 = plan.propagate(g, DT, max_steps=3, **kw)
+            calls = 1
+            while not info2.done.all():
+                info2 = plan.propagate(g, DT, max_steps=3, resume=True, **kw)
+                calls += 1
+                assert calls < 40
+            assert calls >= 3
+            np.testing.assert_array_equal(info2.steps, info.steps)
+            assert rel_l2(g.cpu().numpy(), outs[-1][0]) <= (1e-5 if precision == "fp32" else 1e-13)
         plan.set_option("cluster", -1)
     np.testing.assert_array_equal(outs[-1][1], outs[0][1])
     np.testing.assert_array_equal(outs[-1][0], outs[0][0])            # same arithmetic whatever the team structure
