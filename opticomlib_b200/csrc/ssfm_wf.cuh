@@ -19,7 +19,14 @@
 // -> controller -> merged Kerr rotation of the second half step of step s and the first half step of
 // step s+1 -> forward transform).  The phases of one waveform are separated by team barriers.
 //
-// Three variants of the team synchronisation (template parameter TM; CL := TM == 1, MC := TM == 2):
+// Four variants of the team structure (template parameter TM; CL := TM == 1 or 3, MC := TM == 2, MT := TM == 3):
+//   MT          (TM == 3) a team is ONE cluster of 2 .. 16 CTAs whatever the waveform length and every CTA carries several
+//               4096-sample tiles through each phase (a loop around the phase body): barrier, exchange and load latencies are paid
+//               once per phase, not once per tile.  The Kerr phase of the tiles in flight lives in an L2-resident team stash
+//               (WfArgs::tstash) and is staged into shared memory with cp.async; adaptive step control makes two passes over the
+//               CTA's tiles per column phase (end of step -> store -> team maximum -> re-read -> merged rotation -> forward
+//               transforms).  Used for waveforms of 32 .. 64 tiles (one 16-CTA cluster each) and, as clusters of 2, for the CTA
+//               slots that 16-CTA clusters cannot use;
 //   MC          teams of 32 .. 256 CTAs (N = 2^17 .. 2^20) made of thread-block clusters of 8: the team barrier is the hardware
 //               barrier inside every cluster plus ONE flag hop between the cluster leaders (4 .. 32 arrivals on the counter in
 //               L2 instead of 32 .. 256, and only the leaders poll); the maxima travel through st.async inside a cluster and as

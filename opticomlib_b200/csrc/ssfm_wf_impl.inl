@@ -156,7 +156,7 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
 }
 
 // cluster teams with SEVERAL tiles per CTA (waveforms of 32 .. 64 tiles: 2^17, 2^18 samples, or 2^16 / 2^17 with two polarisations;
-// fixed step, one step, or a transfer function -- no adaptive step control): a team is ONE cluster of 16 CTAs whatever the
+// fixed or adaptive steps -- the latter with two passes per column phase -- or a transfer function): a team is ONE cluster of 16 CTAs whatever the
 // waveform length, every CTA carries units/16 tiles through each phase, and the team barrier is the hardware cluster barrier
 // instead of 64 arrivals on a counter in L2 (measured on B200: 64-CTA flag-based teams spend ~40 % of a step in their two
 // barriers).  The Kerr phase of the tiles in flight lives in a small L2-resident buffer (WfLaunch::tstash) instead of shared
@@ -364,7 +364,7 @@ int wf_launch(const Params<R>& p, const WfLaunch& l, int* teams_out, cudaStream_
             if (rc != SSFM_ERR_UNSUPPORTED) return rc;
         }
     }
-    if constexpr (M1 * M2 >= (1 << 16) && M1 * M2 <= (1 << 18)) {        // 32 .. 64 tiles per waveform, no adaptive step control
+    if constexpr (M1 * M2 >= (1 << 16) && M1 * M2 <= (1 << 18)) {        // 32 .. 64 tiles per waveform
         // (measured on B200 against flag-based / multi-cluster teams: fixed step 2^18 +6 %, 2^17 +9 %; adaptive steps -- two passes per
         //  column phase -- fp64 +4 % / +6 %, fp32 +0 % / +16 %)
         if (l.cluster != 0 && total > 16 && total <= 64 && !getenv("SSFM_NO_MT")) {
