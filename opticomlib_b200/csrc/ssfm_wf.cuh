@@ -192,7 +192,12 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
 #else
     // 256-point column transforms in complex128: two half-CTAs with their own barriers (measured on B200, config #3: fp64 5.78e10 ->
     // 5.89e10; fp32, three CTAs per SM, 1.02e11 -> 9.2e10: off)
+#ifdef SSFM_WF_HALVES_T8    // (512-point column transforms, halves of 4 columns = 64-byte segments of global memory: DBP of 128 x 2^18
+                            //  3.87e10 -> 3.43e10, the same loss as in fp32 -- a warp access then touches 8 lines instead of 4)
+    constexpr bool HALVES = ((GEO::T == 16 || GEO::T == 8) && GEO::NT == 256 && sizeof(R) == 8);
+#else
     constexpr bool HALVES = (GEO::T == 16 && GEO::NT == 256 && sizeof(R) == 8);
+#endif
 #endif
     typedef typename std::conditional<HALVES, ColExchangeHalves<GEO::T>, ColExchange<GEO::T>>::type CX;
 #ifdef SSFM_WF_TABLE_TWIDDLES
@@ -285,8 +290,9 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
     }
 
     const int pol = me / tiles, tile = me % tiles;
-    const int c = HALVES ? ((tid & 7) | ((tid >> 7) << 3)) : tid % T;   // column phase: column c of the tile, thread t of its transform
-    const int t = HALVES ? ((tid & 127) >> 3) : tid / T;                // (HALVES: columns 0..7 on warps 0..3, columns 8..15 on warps 4..7)
+    constexpr int HT = T / 2;                                           // (HALVES: columns 0..T/2-1 on warps 0..3, the rest on warps 4..7)
+    const int c = HALVES ? ((tid & (HT - 1)) | ((tid >> 7) * HT)) : tid % T;   // column phase: column c of the tile, thread t of its transform
+    const int t = HALVES ? ((tid & 127) / HT) : tid / T;
     const int n2 = tile * T + c;
     const int g = tid / (M2 / E), tr = tid % (M2 / E);         // row phase: row g of the group, thread tr of its transform
     const int k1 = tile * G + g;
