@@ -150,6 +150,7 @@ struct ssfm_plan_s {
     int num_sms = 0;
     int debug = 0;
     int use_tw_full = -1;        // four-step twiddles: -1 auto, 0 two tables, 1 full table, 2 recurrence
+    int lin_sep = -1;            // k_wf: separable linear operator where it applies (-1 auto = on, 0 off)
     int l2_ahead = 0;
     int persistent = 1;          // 1: whole propagation as one persistent kernel (k_wf) when the geometry allows it
     int teams_cap = 0;           // k_wf: at most this many teams (0 = as many as fit)
@@ -385,6 +386,8 @@ Params<R> base_params(ssfm_plan_t pl, const ssfm_fiber_params& prm, bool& fixed,
     const int tw_mode = pl->use_tw_full < 0 ? (sizeof(R) == 8 ? 2 : 1) : pl->use_tw_full;
     base.tw_full = tw_mode == 1 ? (const C*)pl->tw_full : nullptr;
     base.tw_chain = tw_mode == 2 ? 1 : 0;
+    // separable linear operator of k_wf (complex128, beta_3 = 0, rows of 256 bins): plan option "lin_sep", -1 = auto (on)
+    base.lin_sep = (sizeof(R) == 8 && pl->lin_sep != 0 && b3 == (R)0 && pl->n2 == 256 && !pl->long_n) ? 1 : 0;
     base.small_phase = (!fixed && !single && pm <= (R)0.05 && pm >= (R)0) ? 1 : 0;   // |Kerr phase| <= phi_max in adaptive mode
     base.lo_bits = pl->lo_bits ? pl->lo_bits : ilog2(pl->n2);
     base.n = (int)pl->n; base.n1 = pl->n1; base.n2 = pl->n2; base.log2_n2 = ilog2(pl->n2);
@@ -939,6 +942,7 @@ int ssfm_plan_set_option(ssfm_plan_t pl, const char* name, int64_t value) {
     else if (k == "cluster") { pl->cluster = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "placement") { pl->placement = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "teams") { if (value < 0) return fail(SSFM_ERR_INVALID, "teams < 0"); pl->teams_cap = (int)value; }
+    else if (k == "lin_sep") { pl->lin_sep = value < 0 ? -1 : (value ? 1 : 0); }
     else if (k == "tw_full") { pl->use_tw_full = value < 0 ? -1 : ((value == 2) ? 2 : (value ? 1 : 0)); }
     else if (k == "l2_ahead") { pl->l2_ahead = (int)value; }
     else return fail(SSFM_ERR_INVALID, "unknown option '" + k + "'");

@@ -52,6 +52,7 @@ struct Params {
     const C* tw_hi;      // W_N^(i*2^lo_bits)
     const C* tw_full;    // optional full four-step table W_N^{n2*k1} at [k1][n2] (N <= 2^20): one coalesced L2 load
                          // instead of two table look-ups and a complex product
+    int lin_sep;         // k_wf<double> with rows of 256 bins and beta_3 = 0: linear operator in separable form (ssfm_wf.cuh: lin_sep_table)
     int tw_chain;        // 1: four-step twiddles by recurrence (two interleaved chains seeded from tw_lo / tw_hi): 16 complex
                          // products per thread instead of 16 loads of 16 B from L2 -- the full table is 2 x 16 B of L2 traffic per
                          // sample and step next to the field's 4 x 16 B, and the L2 <-> SM path is what k_wf<double> waits for

@@ -91,7 +91,9 @@ struct wf_geom {
     static constexpr int TAB1 = fft_plan<M1, E>::table_size;
     static constexpr int TAB2 = (M1 == M2) ? 0 : fft_plan<M2, E>::table_size;
     static constexpr int XB = wf_cmax(M1 * T, G * PM);
-    static constexpr size_t smem_full = sizeof(C) * (size_t)(XB + TAB1 + TAB2 + SC_N) + sizeof(R) * (size_t)(E * NT);
+    // separable linear operator (complex128, rows of 256 bins, beta_3 = 0): exp(j theta (M1 k2')^2) for |k2'| <= M2/2
+    static constexpr int LSEP = (sizeof(R) == 8 && M2 == 256) ? (M2 / 2 + 1) : 0;
+    static constexpr size_t smem_full = sizeof(C) * (size_t)(XB + TAB1 + TAB2 + SC_N + LSEP) + sizeof(R) * (size_t)(E * NT);
     // Two CTAs per SM need <= (228 KB / 2 - 1 KB) each.  When the pass tables do not fit next to the exchange buffer
     // and the stash (fp64, transforms of 1024 points or N1 != N2 >= 512) they are read through L1 from global memory.
     static constexpr bool TABS = smem_full <= 115712;
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
     C* tw1s = xb + GEO::XB;                                    // pass tables of the N1-point (column) transforms
     C* tw2s = tw1s + (TABS ? GEO::TAB1 : 0);                   // ... of the N2-point (row) transforms when N2 != N1
     C* sct = tw2s + (TABS ? GEO::TAB2 : 0);                    // sincos table
-    R* st_sm = reinterpret_cast<R*>(sct + SC_N);               // [E][NT] Kerr phase of the current step of MY tile
+    C* btab = sct + SC_N;                                      // [LSEP] separable linear operator, see lin_sep_table below
+    R* st_sm = reinterpret_cast<R*>(btab + GEO::LSEP);         // [E][NT] Kerr phase of the current step of MY tile
     const C* tw1 = TABS ? tw1s : p.tw_col;
     const C* tw2 = TABS ? ((M1 == M2) ? tw1s : tw2s) : p.tw_row;
 
@@ -477,6 +480,48 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
         }
     };
     const unsigned int my_tiles = MT ? (units - (unsigned)me + total - 1u) / total : 1u;
+    // Separable linear operator (Params::lin_sep: complex128, beta_3 = 0, rows of 256 bins).  With the signed bin index
+    // s = k1 + M1 k2' (k2' = k2 below M2/2, k2 - M2 above: the fftfreq wrap) the phase of devices.py:1145,1179 is
+    //   imag(D~) h = theta s^2 = theta k1^2 + 2 theta M1 k1 k2' + theta M1^2 k2'^2,     theta = h c2 wscale^2,
+    // so exp(j imag(D~) h) = A(k1) G(k1)^k2' B(|k2'|): B is a table of M2/2 + 1 entries that the CTA fills as soon as the step
+    // size is known (before the team barrier, i.e. for free), and along a thread's 16 bins (k2' = tr + 16 q', q' = -8 .. 7) the
+    // rest is a geometric sequence: two sincos and 15 complex products per thread instead of 16 loads of imag(D~) from L2 --
+    // whose latency nothing hid, the cluster barrier having just emptied L1 -- and 16 sincos.  Differs from the tabulated
+    // evaluation by rounding (~1e-13 rad on phases of ~1e3 rad); complex64 keeps the table: there the reference's own float32
+    // rounding of the phase must be reproduced.
+    auto lin_sep_table = [&](R hstep) {
+        if constexpr (GEO::LSEP > 0) {
+            if (p.lin_sep && tid < GEO::LSEP) {
+                const double th = (double)hstep * (double)p.c2 * p.wscale * p.wscale;
+                const double m = (double)tid * (double)M1;
+                double sn, cs;
+                sincos_r(th * m * m, sct, &sn, &cs);
+                btab[tid] = mk<R>((R)cs, (R)sn);
+            }
+        }
+    };
+    auto lin_sep_apply = [&](C (&v)[E], R hstep, int row_k1) {
+        if constexpr (GEO::LSEP > 0) {
+            constexpr int ST = M2 / E;
+            const double th = (double)hstep * (double)p.c2 * p.wscale * p.wscale;
+            const double k1d = (double)row_k1;
+            double sn, cs;
+            sincos_r(th * k1d * (k1d + 2.0 * (double)M1 * (double)(tr - 8 * ST)), sct, &sn, &cs);   // A G^(tr - 8 ST)
+            C wa = mk<R>((R)cs, (R)sn);
+            sincos_r(th * 2.0 * (double)M1 * (double)ST * k1d, sct, &sn, &cs);                        // G^ST
+            const C rho = mk<R>((R)cs, (R)sn);
+            const C rho2 = cmul(rho, rho);
+            C wb = cmul(wa, rho);
+#pragma unroll
+            for (int i = 0; i < E; i += 2) {                    // i <-> q' = i - 8 <-> register q = (i + 8) & 15
+                const int m0 = i < 8 ? (8 - i) * ST - tr : (i - 8) * ST + tr;
+                const int m1 = i + 1 < 8 ? (7 - i) * ST - tr : (i - 7) * ST + tr;
+                v[(i + 8) & 15] = cmul(v[(i + 8) & 15], cmul(wa, btab[m0]));
+                v[(i + 9) & 15] = cmul(v[(i + 9) & 15], cmul(wb, btab[m1]));
+                if (i + 2 < E) { wa = cmul(wa, rho2); wb = cmul(wb, rho2); }
+            }
+        }
+    };
     auto sh_read = [&](unsigned v) -> WfShared<R> {
         const volatile WfShared<R>* q = &sh[v & 1u];
         WfShared<R> r;
@@ -600,6 +645,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
 #pragma unroll
                         for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + un2] = v[q];
                     }
+                    lin_sep_table(h_first);
                     bar_arrive();
                     state = WF_ROW;
                     continue;
@@ -653,6 +699,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                 apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
                 for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
+                lin_sep_table(h_first);
                 bar_arrive();
                 state = WF_ROW;
                 continue;
@@ -678,6 +725,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                             const C* __restrict__ hrow = p.xfer + (size_t)uk1 * M2;
 #pragma unroll
                             for (int q = 0; q < E; ++q) v[q] = cmul(v[q], __ldg(hrow + tr + q * (M2 / E)));
+                        } else if (GEO::LSEP > 0 && p.lin_sep) {
+                            lin_sep_apply(v, h, uk1);
                         } else {
                             const R* __restrict__ drow = p.dim_tab + (size_t)uk1 * M2;
 #pragma unroll
@@ -706,6 +755,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     const C* __restrict__ hrow = p.xfer + (size_t)k1 * M2;      // filters (|H|^2), DM, FBG -- one pass over the rows,
 #pragma unroll                                                  // FFT -> x H -> IFFT with the waveforms in flight L2-resident
                     for (int q = 0; q < E; ++q) v[q] = cmul(v[q], __ldg(hrow + tr + q * (M2 / E)));
+                } else if (GEO::LSEP > 0 && p.lin_sep) {
+                    lin_sep_apply(v, h, k1);
                 } else {
                     const R* __restrict__ drow = p.dim_tab + (size_t)k1 * M2;   // imag(D~) of my row's bins (k_fill_dim)
 #pragma unroll
@@ -839,6 +890,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                     o.w = S.w; o.xchg = xchg; o.steps = steps + 1; o.taken = taken; o.z = nx.z; o.h = nx.h;
                 }
                 ver ^= 1u;
+                lin_sep_table(nx.h);
                 bar_arrive();
                 state = WF_ROW;
                 WF_ACC(4, t_c0);
@@ -920,6 +972,7 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
             apply_fourstep<false, R, E, M1>(p, v, n2, t);
 #pragma unroll
             for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
+            lin_sep_table(nx.h);
             bar_arrive();
             state = WF_ROW;
             WF_ACC(4, t_c0);

@@ -85,7 +85,7 @@ class Plan:
         """Every scheduling knob back to its default (a cached plan is shared by whoever asks for the same shape: an option
         left behind by one caller must not steer the next)."""
         for name, value in (("chunk_waveforms", 0), ("fused", 1), ("persistent", 1), ("teams", 0), ("cluster", -1),
-                            ("placement", -1), ("burst_steps", 8), ("debug", 0), ("tw_full", -1), ("l2_ahead", 0), ("async", 0)):
+                            ("placement", -1), ("burst_steps", 8), ("debug", 0), ("tw_full", -1), ("lin_sep", -1), ("l2_ahead", 0), ("async", 0)):
             self.set_option(name, value)
 
     def peek(self, row=0):
