@@ -969,7 +969,8 @@ __global__ void __launch_bounds__(256, (sizeof(R) == 8 ? 2 : SSFM_WF_CTAS_F32)) 
                 }
             }
             fft_passes<R, M1, -1, CX, E, 1, WFTW>::run(v, xb + c, tw1, t);
-            apply_fourstep<false, R, E, M1>(p, v, n2, t);
+            if (p.tw_chain) apply_fourstep_chain<false, R, E>(v, fs_seed);   // (the seeds of the phase's first twiddle: a second look-up
+            else apply_fourstep<false, R, E, M1>(p, v, n2, t);               //  would miss L1, which the barrier wait emptied)
 #pragma unroll
             for (int q = 0; q < E; ++q) rowp[(size_t)(t + q * (M1 / E)) * M2 + n2] = v[q];
             lin_sep_table(nx.h);
