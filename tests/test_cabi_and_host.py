@@ -48,6 +48,12 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.ssfm_plan_create(ctypes.byref(h), 4096, 1, 0, _lib.SSFM_C64, 0) == _lib.SSFM_ERR_INVALID
     assert lib.ssfm_plan_create(ctypes.byref(h), 4096, 1, 1, 7, 0) == _lib.SSFM_ERR_INVALID
     assert lib.ssfm_plan_destroy(None) == 0
+    # streamed batches: null arguments are refused; without a driver the stream memory operations report "unsupported"
+    # (the host path then pipelines one launch per chunk) -- nothing may crash
+    assert lib.ssfm_propagate_streamed(None, None, None, None, None, 1, None) == _lib.SSFM_ERR_INVALID
+    assert b"null" in lib.ssfm_last_error()
+    for fn in (lib.ssfm_stream_write_u32, lib.ssfm_stream_wait_geq_u32):
+        assert fn(None, None, 0) in (_lib.SSFM_ERR_INVALID, _lib.SSFM_ERR_UNSUPPORTED)
     with pytest.raises(ValueError):
         _lib.check(_lib.SSFM_ERR_INVALID)
 
