@@ -119,7 +119,7 @@ int wf_launch_cluster(const Params<R>& p, const WfLaunch& l, int* teams_out, cud
             WfArgs<R> b = a;
             b.n_teams = (int)ft;
             b.tstash = (R*)l.tstash;
-            // a waveform takes a team of fcs CTAs about total/fcs x 0.6 times as long as a 16-CTA cluster
+            // a waveform takes a team of fcs CTAs about total/fcs x 0.8 times as long as a 16-CTA cluster (`slow` above)
             b.draw_min = (int)(teams * ((total / fcs) * 8 + 9) / 10);
             cudaLaunchConfig_t fc{};
             fc.blockDim = dim3(GEO::NT); fc.dynamicSmemBytes = GEO::smem; fc.stream = l.side;
