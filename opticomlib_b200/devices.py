@@ -237,6 +237,13 @@ def _propagate_host_streamed(host, out, tdtype, dev, want_log, chunk_waveforms, 
     return out, engine.StepInfo(steps, z, hn, done, h_log)
 
 
+def single_launch_chunks(B, row_bytes):
+    """Row ranges of the copies around the single streamed launch: ~HOST_SINGLE_CHUNK_BYTES each, at most 256 of them (the
+    kernel is not launched per chunk, so only the first copy in and the last copy out are exposed)."""
+    rows = max(1, HOST_SINGLE_CHUNK_BYTES // max(1, row_bytes), -(-B // 256))
+    return rows, [(r0, min(B, r0 + rows)) for r0 in range(0, B, rows)]
+
+
 def _propagate_host_single_launch(host, out, tdtype, dev, args, chunks):
     """Pinned host buffers in and out, ONE persistent launch for the whole batch (C-ABI ``ssfm_propagate_streamed``): the kernel
     is enqueued first and adopts a waveform as soon as the host-to-device copy of its chunk has been flagged (a stream memory
@@ -254,8 +261,7 @@ def _propagate_host_single_launch(host, out, tdtype, dev, args, chunks):
     tiles = (P * N) // 4096
     # no launch per chunk here, so the chunks can be small: ~32 MiB each (at most 256 of them) -- only the first copy in and the
     # last copy out are exposed
-    rows = max(1, HOST_SINGLE_CHUNK_BYTES // (P * N * host.element_size()), -(-B // 256))
-    chunks = [(r0, min(B, r0 + rows)) for r0 in range(0, B, rows)]
+    rows, chunks = single_launch_chunks(B, P * N * host.element_size())
     rec = torch.empty(B * engine.STATE_RECORD, dtype=torch.uint8, pin_memory=True)
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
@@ -657,8 +663,7 @@ def edfa_fiber_batch(field, rows, G, NF, dt, length, alpha=0.0, beta_2=0.0, beta
         # rows "arrived" from the start)
         import ctypes
         lib = engine._lib.load()
-        srows = max(1, HOST_SINGLE_CHUNK_BYTES // (N * 16), -(-B // 256))
-        sch = [(r0, min(B, r0 + srows)) for r0 in range(0, B, srows)]
+        srows, sch = single_launch_chunks(B, N * 16)
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             xdev = torch.empty((B, N), dtype=torch.complex128, device=dev)

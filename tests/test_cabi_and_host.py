@@ -145,6 +145,20 @@ def test_host_chunk_rule_and_length_validation():
             dv._check_length(bad)
 
 
+def test_single_launch_chunks_cover_the_batch():
+    """Copy chunks around the single streamed launch: contiguous, complete, ~32 MiB each, never more than 256."""
+    from opticomlib_b200 import devices
+    for B, row_bytes in ((4096, 1 << 20), (512, 1 << 20), (41, 1 << 20), (1, 1 << 20), (100000, 4096 * 16), (7, 1 << 30)):
+        rows, chunks = devices.single_launch_chunks(B, row_bytes)
+        assert chunks[0][0] == 0 and chunks[-1][1] == B and len(chunks) <= 256
+        assert all(a1 == b0 for (_, a1), (b0, _) in zip(chunks, chunks[1:]))
+        assert all(0 < r1 - r0 <= rows for r0, r1 in chunks)
+        if B * row_bytes > 256 * devices.HOST_SINGLE_CHUNK_BYTES:
+            assert len(chunks) in (255, 256) or rows * 256 >= B
+        elif row_bytes <= devices.HOST_SINGLE_CHUNK_BYTES:
+            assert rows * row_bytes <= devices.HOST_SINGLE_CHUNK_BYTES
+
+
 def test_pd_argument_validation_matches_the_reference_without_a_gpu():
     """PD validates before it touches the device: same exception types and messages as devices.py:1493-1512."""
     import opticomlib_b200 as ob
